@@ -1,0 +1,37 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "golden_3bx32.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_weights_bin():
+    return os.path.join(GOLDEN, "ref_3bx32.bin.txt")
+
+
+@pytest.fixture(scope="session")
+def golden_weights_txt():
+    return os.path.join(GOLDEN, "ref_3bx32.txt")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle import oracle_py
+    oracle_py.build()
+    return oracle_py
