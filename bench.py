@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — batched NN evals/sec of the self-play evaluation hot path (BASELINE.json metric).
+
+A "step" is one forward pass of the engine over one batch of synthetic 19x19 positions
+(workload = BASELINE.json configs[1]: 19x19, 10bx128 net, batch 256 per GPU).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a), one process per GPU
+  python bench.py --impl reference --gpus N ...            the reference's own Eigen CPU forward
+                                                           (oracle/_ref, compiled from /root/reference) on host cores
+
+One JSON line on stdout from rank 0.  `value` = whole-job evals/s with inputs resident in HBM, device-timed
+with CUDA events on the engine's stream (max over ranks); `e2e` = the same metric through the C ABI
+(sb_submit/sb_wait) with pinned HOST buffers, H2D + D2H inside the timed region; `roofline` = the conv3x3
+tensor-core kernel against the measured dense bf16/fp16 peak; `cpu_baseline` = the reference Eigen forward
+on this box's host cores (rank 0, N=1 only).  Weak scaling: every rank evaluates its own batch; the only
+collective is the NCCL broadcast of the packed weight blob from rank 0 at load.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from sayuri_b200 import synth  # noqa: E402
+
+METRIC = "nn_evals_per_sec"
+UNIT = "evals/s"
+
+
+def algorithmic_flops_per_eval(blocks, C, P, V, n_se, S=361):
+    """direct-conv, 2 flop/MAC, no Winograd discount, no padding waste."""
+    conv = 2 * S * (9 * 43 * C + blocks * 2 * 9 * C * C + C * P + 5 * P + C * V + V)
+    fc = 2 * (3 * P * P + 5 * P + 9 * V * V + 45 * V)
+    se = n_se * 2 * (3 * C * (C // 4) + (C // 4) * 2 * C)
+    return conv + fc + se
+
+
+def conv3x3_flops_per_eval(blocks, C, S=361):
+    """Algorithmic flops of the 3x3 convolutions only (what the dominant kernel computes)."""
+    return 2 * S * (9 * 43 * C + blocks * 2 * 9 * C * C)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"tflops_sustained": d.get("bf16_tflops_sustained"), "tflops_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def weights_file(net, seed=20260417):
+    path = os.path.join(tempfile.gettempdir(), "sb_bench_%s_seed%d.bin" % (net, seed))
+    if not os.path.exists(path):
+        tmp = path + ".%d.tmp" % os.getpid()
+        synth.write_synth_net(tmp, net, seed=seed)
+        os.replace(tmp, path)
+    return path
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref = unmodified
+    loader.cc + blas_forward_pipe.cc + Eigen), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle.oracle_py import Reference
+    blocks, C, P, V = synth.NETS[args.net]
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "gpu_launches": 0,
+            "config": {"workload": "19x19 board, %s net (P=%d,V=%d, SE every 3rd block, mish), batch-%d NN forward" % (args.net, P, V, args.batch),
+                       "net": args.net, "board": 19, "batch_per_gpu": args.batch}}
+    if not Reference.available():
+        line["unavailable"] = "oracle/_ref is not built (needs /root/reference at build time)"
+        print(json.dumps(line), flush=True)
+        return
+    ref = Reference(weights_file(args.net), winograd=True)   # reference default (config.cc:32)
+    n_pos = 32
+    planes = synth.synth_positions(n_pos, 19, seed=20260418)
+    sample_s = min(args.ref_seconds, max(0.5, 150.0 / max(args.steps, 1)))   # whole run stays within a few minutes
+    for _ in range(min(args.warmup, 1)):
+        ref.time_forward(planes, n_pos, 19, cores, 1.0)
+    total_n, total_t = 0, 0.0
+    for _ in range(args.steps):
+        n, t = ref.time_forward(planes, n_pos, 19, cores, sample_s)
+        total_n += n
+        total_t += t
+    value = total_n / total_t
+    line.update({"value": value, "ms_per_step": 1e3 * args.batch / value,
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                                  "sample": "%d steps x %.1f s of BlasForwardPipe::Forward (Winograd, Eigen %s build) on %d threads, %d synthetic positions round-robin"
+                                            % (args.steps, sample_s, Reference.variant, cores, n_pos)},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    from sayuri_b200 import engine
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    blocks, C, P, V = synth.NETS[args.net]
+    stack = synth.default_stack(blocks)
+    n_se = sum(1 for s in stack if s.endswith("-SE"))
+    B = args.batch
+    precision = {"fp32_split": engine.PRECISION_FP32_SPLIT, "fp16": engine.PRECISION_FP16}[args.precision]
+
+    # ---- weights: rank 0 parses + packs, everyone else receives the packed blob over NCCL ----------
+    pipe = engine.B200ForwardPipe()
+    if rank == 0:
+        pipe.initialize(weights_file(args.net), 19, B, gpus=[local_rank], precision=precision)
+    else:
+        desc = dict(version=5, blocks=blocks, channels=C, P=P, V=V, activation=5,
+                    se_sizes=[C // 4 if s.endswith("-SE") else 0 for s in stack])
+        pipe.initialize_from_tensors(desc, None, 19, B, gpus=[local_rank], precision=precision)
+    if world > 1:
+        _, nbytes = pipe.weights_blob(0)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            pipe.weights_export(buf.data_ptr(), nbytes)
+        torch.cuda.synchronize()
+        dist.broadcast(buf, src=0)            # the path's only collective (NVLink/NVSwitch)
+        torch.cuda.synchronize()
+        if rank != 0:
+            pipe.weights_import(buf.data_ptr(), nbytes)
+        cs = torch.tensor([pipe.weights_checksum(0) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if int(lo) != int(hi):
+            raise RuntimeError("weight replicas differ after broadcast")
+        del buf
+
+    # ---- inputs: synthetic positions in pinned host memory (two alternating batches) ----------------
+    pinned = engine.PinnedArray((2, B, engine.PLANE_FLOATS))
+    pos = synth.synth_positions(min(B, 64), 19, seed=20260418 + rank).reshape(-1, engine.PLANE_FLOATS)
+    for k in range(2):
+        for i in range(B):
+            pinned.array[k, i] = pos[(i + 7 * k) % pos.shape[0]]
+    sizes = [19] * B
+    offs = [0] * B
+    outs = [np.zeros(B, dtype=engine.OUTPUT_DTYPE) for _ in range(2)]
+
+    def barrier():
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def reduce_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # upload once: inputs resident in HBM for the device-timed loop
+    pipe.submit(0, 0, pinned.array[0], sizes, offs)
+    pipe.wait(0, 0, outs[0])
+    pipe.submit(0, 1, pinned.array[1], sizes, offs)
+    pipe.wait(0, 1, outs[1])
+    if not np.isfinite(outs[0]["probabilities"]).all():
+        raise RuntimeError("non-finite outputs")
+
+    # ---- (1) device-timed, inputs resident: warm-up W, then exactly K steps -------------------------
+    pipe.time_forward(0, 0, args.warmup, flush_l2=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = pipe.launch_count()
+    ms, _, _ = pipe.time_forward(0, 0, args.steps, flush_l2=True)
+    launches = pipe.launch_count() - launches0
+    clocks = sampler.stop()
+    barrier()
+    t_dev = reduce_max(float(ms.sum()) / 1e3)
+    value = world * B * args.steps / t_dev
+
+    # ---- roofline of the dominant kernel (conv3x3_tc), events around every launch, separate pass ----
+    _, conv_ms, conv_n = pipe.time_forward(0, 0, 0, flush_l2=False, profile_conv=True)
+    peaks = measured_peaks()
+    conv_flops = conv3x3_flops_per_eval(blocks, C) * B
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+    peak = peaks["tflops_sustained"]
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "kernel": "conv3x3_tc_kernel<%s>" % ("true" if precision == engine.PRECISION_FP32_SPLIT else "false"),
+                "launches_per_step": conv_n, "kernel_ms_per_step": conv_ms,
+                "kernel_share_of_step": conv_ms / float(ms.mean()) if len(ms) else None,
+                "algorithmic_flops_per_launch_avg": conv_flops / max(conv_n, 1),
+                "peak_source": peaks["source"] + ", dense bf16/fp16 sustained; kernel timed inside the step",
+                "tensor_flops_issued_per_algorithmic": 3 * (400.0 / 361.0) if precision == engine.PRECISION_FP32_SPLIT else (400.0 / 361.0),
+                "note": "fp32-faithful rung issues 3 fp16 MMAs per algorithmic MAC (hi*hi + lo*hi + hi*lo) on a 400-row/361-cell canvas"}
+
+    # ---- (2) end to end through the C ABI: pinned host in, host out, 2 slots pipelined --------------
+    def e2e_loop(steps):
+        for s in range(steps):
+            slot = s & 1
+            if s >= 2:
+                pipe.wait(0, slot, outs[slot])
+            pipe.submit(0, slot, pinned.array[slot], sizes, offs)
+        for s in range(max(steps - 2, 0), steps):
+            pipe.wait(0, s & 1, outs[s & 1])
+
+    e2e_loop(max(args.warmup, 2))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    t_e2e = reduce_max(t_e2e)
+    e2e = {"value": world * B * args.steps / t_e2e, "unit": UNIT,
+           "h2d_bytes_per_step": B * engine.PLANE_FLOATS * 4 + 2 * B * 4,
+           "d2h_bytes_per_step": B * (2 * 361 + 8) * 4,
+           "timing": "host perf_counter around K pipelined sb_submit/sb_wait steps (2 slots), device idle on both sides"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16x3-split/f32-accum" if precision == engine.PRECISION_FP32_SPLIT else "f16/f32-accum",
+            "data": "synthetic",
+            "config": {"workload": "19x19 board, %s net (P=%d,V=%d, SE every 3rd block, mish), batch-%d NN forward per GPU" % (args.net, P, V, B),
+                       "net": args.net, "board": 19, "batch_per_gpu": B, "precision": args.precision,
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush)",
+                       "parallelism": "replica per GPU, weights NCCL-broadcast from rank 0"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "algorithmic_gflop_per_eval": algorithmic_flops_per_eval(blocks, C, P, V, n_se) / 1e9}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference's Eigen forward on host cores -----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle.oracle_py import Reference
+            if Reference.available():
+                cores = os.cpu_count() or 1
+                ref = Reference(weights_file(args.net), winograd=True)
+                rp = synth.synth_positions(32, 19, seed=20260418)
+                n, t = ref.time_forward(rp, 32, 19, cores, args.cpu_seconds)
+                line["cpu_baseline"] = {"value": n / t, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": "%.0f s of BlasForwardPipe::Forward (Winograd, Eigen %s build) on %d threads over 32 of the same synthetic positions"
+                                                  % (args.cpu_seconds, Reference.variant, cores)}
+            else:
+                from oracle.oracle_py import Oracle
+                orc = Oracle(weights_file(args.net))
+                rp = synth.synth_positions(8, 19, seed=20260418)
+                t0 = time.perf_counter()
+                k = 0
+                while time.perf_counter() - t0 < args.cpu_seconds:
+                    orc.forward(rp[k % 8], 19, 0)
+                    k += 1
+                line["cpu_baseline"] = {"value": k / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": "%.0f s of the scalar C oracle on 1 thread" % args.cpu_seconds}
+        except Exception as ex:  # the baseline is reported, never load-bearing
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+    pinned.free()
+    pipe.destroy()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--net", default="10bx128", choices=sorted(synth.NETS))
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--precision", default="fp32_split", choices=["fp32_split", "fp16"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-seconds", type=float, default=3.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

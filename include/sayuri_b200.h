@@ -1,0 +1,177 @@
+/*
+ * sayuri_b200 — C ABI of the Blackwell-native (sm_100a) batched NN evaluation engine that drops in behind
+ * Sayuri's NetworkForwardPipe / BatchForwardPipe plugin interface.
+ *
+ * Every entry point cites the reference interface it replaces (paths under /root/reference).  All
+ * arguments are plain pointers and sizes; no C++ or torch types cross this boundary.  Functions return
+ * 0 on success or a negative sb_status; sb_last_error() gives the message (the C++ shim turns non-zero
+ * into std::runtime_error exactly like ReportCUDAErrors, src/neural/cuda/cuda_common.cc:55-62).
+ *
+ * There is NO CPU fallback: without a CUDA device (or with the library missing) every compute entry
+ * point fails with SB_ERR_CUDA / the loader raises.
+ */
+#ifndef SAYURI_B200_H_
+#define SAYURI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_MAX_BOARD_SIZE 19                 /* src/game/types.h:5-7 (MAX_BOARD_SIZE)            */
+#define SB_MAX_INTERSECTIONS 361             /* kNumIntersections                                 */
+#define SB_INPUT_CHANNELS 43                 /* src/neural/network_basic.h:10 (kInputChannels)    */
+#define SB_PLANE_FLOATS (SB_INPUT_CHANNELS * SB_MAX_INTERSECTIONS) /* InputData::planes size      */
+
+typedef enum sb_status {
+    SB_OK = 0,
+    SB_ERR_INVALID = -1,     /* bad argument / unsupported network (rejected loudly, never approximated) */
+    SB_ERR_CUDA = -2,        /* CUDA runtime / driver error, no device, kernel fault                     */
+    SB_ERR_IO = -3,          /* weight file unreadable or malformed                                      */
+    SB_ERR_STATE = -4        /* call sequence error (e.g. wait on an idle slot)                          */
+} sb_status;
+
+/* Arithmetic of the convolution tower.  (SURVEY.md §7 "precision ladder".) */
+typedef enum sb_precision {
+    SB_PRECISION_FP32_SPLIT = 0, /* default: fp16 hi+lo operand split, 3 tcgen05 passes, fp32 accumulate:
+                                    fp32-faithful, meets the 1e-4 parity bar vs the Eigen forward          */
+    SB_PRECISION_FP16 = 1,       /* single fp16 pass, fp32 accumulate: the reference's own --fp16 trade
+                                    (config.cc:33); OutputResult.fp16 = true                               */
+    SB_PRECISION_SIMT_DEBUG = 2  /* fp32 CUDA-core convolution on the same buffers: on-device cross-check
+                                    of the tensor-core kernel, test use only                               */
+} sb_precision;
+
+/* Network description == the scalar fields of DNNWeights (src/neural/description.h:164-215). */
+typedef struct sb_net_desc {
+    int version;            /* 3..5 (43-plane encoder, 5 policy planes, 15 misc outputs)           */
+    int input_channels;     /* 43                                                                  */
+    int blocks;             /* residual_blocks                                                     */
+    int channels;           /* residual_channels                                                   */
+    int policy_channels;    /* policy_head_channels                                                */
+    int value_channels;     /* value_head_channels                                                 */
+    int activation;         /* same ints as enum Activation, src/neural/activation.h:8-17          */
+    const int* se_sizes;    /* [blocks]: 0 = plain ResidualBlock, >0 = squeeze width of ...-SE     */
+} sb_net_desc;
+
+/* One tensor, fp32, caller-owned for the duration of the call only. */
+typedef struct sb_tensor {
+    const float* data;
+    long long count;
+} sb_tensor;
+
+/*
+ * Weights in the loader's tensor order (src/neural/loader.cc:658-747) AFTER ProcessWeights
+ * (loader.cc:775-831): batch-norm already folded, so every layer contributes exactly two tensors
+ * {weights, biases}: input conv; per block conv1, conv2 [, squeeze FC, excite FC]; policy head conv,
+ * policy intermediate FC, prob conv, pass FC; value head conv, value intermediate FC, ownership conv,
+ * misc FC.  Conv weights are UNTRANSFORMED OIHW (ConvLayer::GetWeights, never GetTransformF);
+ * FC weights [out][in].
+ */
+typedef struct sb_weights {
+    const sb_tensor* tensors;
+    int n_tensors;
+} sb_weights;
+
+/* POD mirror of OutputResult (src/neural/network_basic.h:36-63): raw, pre-activation outputs. */
+typedef struct sb_output {
+    float probabilities[SB_MAX_INTERSECTIONS]; /* logits of the requested policy plane, native n*n order */
+    float ownership[SB_MAX_INTERSECTIONS];     /* raw (tanh is applied by Network::TransformResult)      */
+    float pass_probability;                    /* pass logit of the requested plane                      */
+    float wdl[3];
+    float stm_winrate;
+    float final_score;
+    float q_error;
+    float score_error;
+    int board_size;
+    int offset;                                /* PolicyBufferOffset echoed                              */
+    int fp16;                                  /* 1 if SB_PRECISION_FP16 was used                        */
+} sb_output;
+
+typedef struct sb_engine sb_engine;
+
+/* ---- lifetime: CudaForwardPipe::Initialize/Construct/Release/Destroy, ------------------------------
+ *      src/neural/cuda/cuda_forward_pipe.cc:14-25,44-131; NNGraph::ConstructGraph :133-613            */
+
+/* Build one replica of the net on each listed GPU for an N x N canvas and up to max_batch positions per
+ * forward.  `w` may be NULL: the weight blob is then left to be filled through sb_weights_blob()
+ * (NCCL broadcast from the rank that parsed the file).  Host tensors are copied; nothing is retained. */
+int sb_create(sb_engine** out, const sb_net_desc* desc, const sb_weights* w, const int* gpu_ids, int n_gpus,
+              int board_size, int max_batch, int precision);
+
+/* Same, reading the reference weight-file format itself (text or float32bin):
+ * DNNLoader::FromFile/Parse/FillWeights/ProcessWeights, src/neural/loader.cc:26-121,628-831. */
+int sb_create_from_file(sb_engine** out, const char* weights_path, const int* gpu_ids, int n_gpus,
+                        int board_size, int max_batch, int precision);
+
+/* CudaForwardPipe::Construct(option, nullptr) on board/batch change (network.cc:494-498): keeps the
+ * weights, re-allocates activations only if the board changed or max_batch grew. */
+int sb_reconfigure(sb_engine* e, int board_size, int max_batch);
+
+/* Weight hot-swap (same architecture): replaces the reference's process restart on new weights
+ * (src/selfplay/engine.cc:63-90). */
+int sb_reload_weights(sb_engine* e, const sb_net_desc* desc, const sb_weights* w);
+int sb_reload_weights_from_file(sb_engine* e, const char* weights_path);
+
+void sb_destroy(sb_engine* e);                 /* CudaForwardPipe::Destroy / NNGraph::DestroyGraph :1092-1136 */
+const char* sb_last_error(const sb_engine* e); /* e may be NULL: message of the last failed sb_create*        */
+
+int sb_num_gpus(const sb_engine* e);           /* CudaForwardPipe::GetNumWorkers, cuda_forward_pipe.cc:40-42  */
+int sb_num_slots(const sb_engine* e);          /* pipeline depth per GPU (independent in-flight batches)      */
+int sb_max_batch(const sb_engine* e);
+int sb_board_size(const sb_engine* e);
+int sb_get_net_desc(const sb_engine* e, sb_net_desc* desc, int* se_sizes, int se_capacity);
+
+/* ---- the hot path: CudaForwardPipe::BatchForward -> NNGraph::BatchForward, --------------------------
+ *      src/neural/cuda/cuda_forward_pipe.cc:32-34,684-1018 (+ FillOutputs :1020-1090);
+ *      the canvas re-layout of BatchForwardPipe::SendQueryAndWait (batch_forward_pipe.cc:15-33,48-67)
+ *      happens on the device.                                                                          */
+
+/* Blocking forward of n positions on replica `gpu` (index into gpu_ids).  planes[i] points at sample i's
+ * InputData::planes: 43 * bs_i * bs_i floats, NCHW, packed at the sample's native board size.
+ * One caller per (gpu, slot 0) at a time, like the reference's one worker thread per GPU. */
+int sb_forward_batch(sb_engine* e, int gpu, int n, const float* const* planes, const int* board_sizes,
+                     const int* policy_offsets, sb_output* out);
+
+/* Asynchronous pair for overlapping H2D / compute / D2H of independent batches (slot < sb_num_slots).
+ * planes: n samples `plane_stride` floats apart (SB_PLANE_FLOATS for an array of InputData::planes).
+ * If the buffer came from sb_host_alloc() it is DMA'd in place and must stay valid until sb_wait. */
+int sb_submit(sb_engine* e, int gpu, int slot, int n, const float* planes, long long plane_stride,
+              const int* board_sizes, const int* policy_offsets);
+int sb_wait(sb_engine* e, int gpu, int slot, sb_output* out);
+
+/* Pinned host memory (the reference's host_input_planes_ / host_output_* buffers, cuda_forward_pipe.cc:560-577). */
+void* sb_host_alloc(size_t bytes);
+void sb_host_free(void* p);
+
+/* ---- weights on the device: one contiguous blob per replica (pre-packed fp16 hi/lo K-major conv
+ *      matrices + fp32 biases/FCs) so that a reload is ONE collective instead of the reference's
+ *      per-tensor MallocAndCopy (cuda_common.cc:228-243).                                              */
+int sb_weights_blob(sb_engine* e, int gpu, void** device_ptr, size_t* bytes);
+/* Device-to-device copies of the blob out of / into replica `gpu` (e.g. a torch.distributed / NCCL
+ * broadcast buffer on the same device).  `bytes` must equal the blob size. */
+int sb_weights_export(sb_engine* e, int gpu, void* device_dst, size_t bytes);
+int sb_weights_import(sb_engine* e, int gpu, const void* device_src, size_t bytes);
+uint64_t sb_weights_checksum(sb_engine* e, int gpu);   /* FNV-1a of the blob, to verify replicas agree */
+
+/* ---- measurement (bench.py; device timing on the engine's own stream with CUDA events) ------------- */
+
+/* Re-run the forward of the batch last submitted to (gpu, slot), inputs resident in HBM, `iters` times;
+ * ms_each[i] = device time of iteration i.  flush_l2 != 0 writes a buffer larger than L2 between
+ * iterations.  conv_ms / conv_launches (optional) receive the summed device time and the count of
+ * conv3x3 launches measured with events around each launch in one extra, separate pass. */
+int sb_time_forward(sb_engine* e, int gpu, int slot, int iters, int flush_l2, float* ms_each,
+                    float* conv_ms, int* conv_launches);
+long long sb_launch_count(const sb_engine* e);  /* kernels launched by this engine so far */
+
+/* ---- debugging / tests -------------------------------------------------------------------------- */
+/* Tower output of sample `sample` of the last batch on (gpu, slot) as fp32 NCHW [channels][n*n]. */
+int sb_debug_read_trunk(sb_engine* e, int gpu, int slot, int sample, float* out);
+/* Named integer knobs: "bo_mode" (UMMA descriptor base-offset mode 0/1). */
+int sb_set_option(sb_engine* e, const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAYURI_B200_H_ */

@@ -1,0 +1,412 @@
+// HBM-/latency-bound kernels around the tensor-core convolution: input unpack + canvas placement,
+// SE squeeze/excite, SE scale, head 1x1 convs, head pooling + FCs, output gather.  All plain SIMT with
+// vectorised (16 B) row accesses; per-sample reductions run in a fixed order (batch-invariant results).
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void load8(const __half* hi, const __half* lo, bool split, float (&v)[8]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(hi);
+    const __half* ha = reinterpret_cast<const __half*>(&a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __half2float(ha[i]);
+    if (split) {
+        const uint4 b = *reinterpret_cast<const uint4*>(lo);
+        const __half* hb = reinterpret_cast<const __half*>(&b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += __half2float(hb[i]);
+    }
+}
+
+__device__ __forceinline__ void store8(__half* hi, __half* lo, bool split, const float (&v)[8]) {
+    __align__(16) __half oh[8];
+    __align__(16) __half ol[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_f16(v[i], oh[i], ol[i]);
+    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(oh);
+    if (split) *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(ol);
+}
+
+// ------------------------------------------------------------------------------------------------
+// unpack_planes: fp32 NCHW planes at each sample's NATIVE board size (InputData.planes,
+// /root/reference/src/neural/network_basic.h:23-34, encoder.cc:31-50) -> NHWC canvas rows with Cin
+// padded 43 -> 64, top-left placement on the N x N canvas with zeros elsewhere (the re-layout of
+// BatchForwardPipe::SendQueryAndWait, batch_forward_pipe.cc:15-33), fp16 hi/lo split, and the per-row
+// board mask (ApplyMask, cuda_forward_pipe.cc:636-682).  One thread per (canvas row, 8-channel group).
+__global__ void unpack_planes_kernel(const float* __restrict__ planes, size_t sample_stride,
+                                     const int* __restrict__ board_sizes, Geom g, int n, int n_rows,
+                                     __half* __restrict__ hi, __half* __restrict__ lo, bool split,
+                                     uint8_t* __restrict__ mask) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = idx >> 3, cg = idx & 7;
+    if (r >= n_rows) return;
+    const int b = r / g.SS, rem = r - b * g.SS;
+    const int y = rem / g.P, x = rem - y * g.P;
+    int bs = 0;
+    if (b < n) bs = board_sizes[b];
+    const bool live = (b < n) && (y < bs) && (x < bs);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cg * 8 + i;
+        v[i] = (live && c < kInputChannels) ? planes[(size_t)b * sample_stride + (size_t)c * bs * bs + y * bs + x] : 0.f;
+    }
+    const size_t off = (size_t)(kGuardRows + r) * kInputChannelsPadded + cg * 8;
+    store8(hi + off, lo + off, split, v);
+    if (cg == 0) mask[kGuardRows + r] = live ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// se_pool_fc: GlobalPooling<false> + squeeze FC + excite FC of SEUnit::Forward
+// (/root/reference/src/neural/blas/se_unit.cc:9-37,70-90; GPU twins cuda_kernels.cu:241-321 and the
+// cuBLAS FCs cuda_layers.cc:975-1017).  One CTA (256 threads) per sample; writes sigmoid(gamma) and
+// beta, [n][2C].  Mean divides by the sample's own n^2, (n-14)/10 uses the sample's own n.
+__global__ void __launch_bounds__(256)
+se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_lo, bool split,
+                  const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int C, int pitch,
+                  int se, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                  const float* __restrict__ b2, int act, float* __restrict__ gb) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.x;
+    const int bs = board_sizes[b];
+    const int halfC = C >> 1;
+    const int n_rg = 256 / halfC;                 // row groups
+    float* part_sum = sm;                          // [n_rg][C]
+    float* part_max = sm + n_rg * C;               // [n_rg][C]
+    float* pool = part_max + n_rg * C;             // [3C]
+    float* hid = pool + 3 * C;                     // [se]
+    const int tid = threadIdx.x;
+    const int rg = tid / halfC, c2 = tid - rg * halfC;
+    if (rg < n_rg) {
+        float s0 = 0.f, s1 = 0.f, m0 = -5000.f, m1 = -5000.f;   // "crazy negative value", se_unit.cc:22
+        const int row0 = kGuardRows + b * g.SS;
+        for (int r = rg; r < g.SS; r += n_rg) {
+            if (!mask[row0 + r]) continue;
+            const size_t off = (size_t)(row0 + r) * pitch + 2 * c2;
+            float2 v = __half22float2(*reinterpret_cast<const __half2*>(u_hi + off));
+            if (split) {
+                const float2 l = __half22float2(*reinterpret_cast<const __half2*>(u_lo + off));
+                v.x += l.x;
+                v.y += l.y;
+            }
+            s0 += v.x;
+            s1 += v.y;
+            m0 = fmaxf(m0, v.x);
+            m1 = fmaxf(m1, v.y);
+        }
+        part_sum[rg * C + 2 * c2] = s0;
+        part_sum[rg * C + 2 * c2 + 1] = s1;
+        part_max[rg * C + 2 * c2] = m0;
+        part_max[rg * C + 2 * c2 + 1] = m1;
+    }
+    __syncthreads();
+    const float b_coeff = ((float)bs - 14.0f) / 10.f;   // se_unit.h:17-20
+    for (int c = tid; c < C; c += 256) {
+        float s = 0.f, m = -5000.f;
+        for (int k = 0; k < n_rg; ++k) {
+            s += part_sum[k * C + c];
+            m = fmaxf(m, part_max[k * C + c]);
+        }
+        const float mean = s / (float)(bs * bs);
+        pool[c] = mean;
+        pool[C + c] = mean * b_coeff;
+        pool[2 * C + c] = m;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int o = warp; o < se; o += 8) {        // squeeze: 3C -> se, activation
+        float acc = 0.f;
+        for (int i = lane; i < 3 * C; i += 32) acc += w1[(size_t)o * 3 * C + i] * pool[i];
+        acc = warp_sum(acc);
+        if (lane == 0) hid[o] = activate(acc + b1[o], act);
+    }
+    __syncthreads();
+    for (int o = tid; o < 2 * C; o += 256) {     // excite: se -> 2C, identity
+        float acc = 0.f;
+        for (int i = 0; i < se; ++i) acc += w2[(size_t)o * se + i] * hid[i];
+        acc += b2[o];
+        if (o < C) acc = 1.0f / (1.0f + expf(-acc));   // gamma = sigmoid, se_unit.cc:103
+        gb[(size_t)b * 2 * C + o] = acc;
+    }
+}
+
+// se_apply: x' = act(sigmoid(gamma) * u + beta + skip) on board cells, 0 elsewhere
+// (SEUnit::SEProcess, se_unit.cc:92-128; GPU twin se_scale_kernel cuda_kernels.cu:391-440).  In place on u.
+__global__ void se_apply_kernel(__half* __restrict__ u_hi, __half* __restrict__ u_lo,
+                                const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, bool split,
+                                const uint8_t* __restrict__ mask, const float* __restrict__ gb, Geom g, int C,
+                                int pitch, int n_rows, int act) {
+    const int groups = C >> 3;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(idx / groups), cg = (int)(idx - (size_t)r * groups);
+    if (r >= n_rows) return;
+    const int row = kGuardRows + r;
+    const size_t off = (size_t)row * pitch + cg * 8;
+    float o[8];
+    if (mask[row]) {
+        const int b = r / g.SS;
+        float u[8], x[8];
+        load8(u_hi + off, u_lo + off, split, u);
+        load8(x_hi + off, x_lo + off, split, x);
+        const float* ga = gb + (size_t)b * 2 * C + cg * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = activate(ga[i] * u[i] + ga[C + i] + x[i], act);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    }
+    store8(u_hi + off, u_lo + off, split, o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// head_conv: the two head-entry 1x1 convolutions fused into one pass over the trunk:
+//   pv[row][0:P]   = act(Wp x + bp)   (policy, blas_forward_pipe.cc:430-442)
+//   pv[row][P:P+V] = act(Wv x + bv)   (value,  blas_forward_pipe.cc:513-522)
+// fp32 out, zero on non-board rows.  One thread per canvas row; W^T [C][PV] broadcast from shared memory.
+template <int PV>
+__global__ void __launch_bounds__(128)
+head_conv_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, bool split,
+                 const uint8_t* __restrict__ mask, const float* __restrict__ wT, const float* __restrict__ bias,
+                 int C, int pitch, int n_rows, int act, float* __restrict__ pv) {
+    extern __shared__ float sw[];   // [C][PV] + [PV]
+    for (int i = threadIdx.x; i < C * PV; i += blockDim.x) sw[i] = wT[i];
+    float* sb_ = sw + C * PV;
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) sb_[i] = bias[i];
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int row = kGuardRows + r;
+    float acc[PV];
+    const bool live = mask[row] != 0;
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < PV; ++j) acc[j] = sb_[j];
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            float x[8];
+            const size_t off = (size_t)row * pitch + c0;
+            load8(x_hi + off, x_lo + off, split, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4* w4 = reinterpret_cast<const float4*>(sw + (c0 + i) * PV);
+#pragma unroll
+                for (int j4 = 0; j4 < PV / 4; ++j4) {
+                    const float4 w = w4[j4];
+                    acc[4 * j4 + 0] += x[i] * w.x;
+                    acc[4 * j4 + 1] += x[i] * w.y;
+                    acc[4 * j4 + 2] += x[i] * w.z;
+                    acc[4 * j4 + 3] += x[i] * w.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PV; ++j) acc[j] = activate(acc[j], act);
+    } else {
+#pragma unroll
+        for (int j = 0; j < PV; ++j) acc[j] = 0.f;
+    }
+    float4* o = reinterpret_cast<float4*>(pv + (size_t)row * PV);
+#pragma unroll
+    for (int j4 = 0; j4 < PV / 4; ++j4) o[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+}
+
+struct HeadWeights {
+    const float* p_inter_w;  // [P][3P]
+    const float* p_inter_b;  // [P]
+    const float* pass_w;     // [5][P]
+    const float* pass_b;     // [5]
+    const float* v_inter_w;  // [3V][3V]
+    const float* v_inter_b;  // [3V]
+    const float* misc_w;     // [15][3V]
+    const float* misc_b;     // [15]
+    const float* prob_w;     // [5][P]
+    const float* prob_b;     // [5]
+    const float* own_w;      // [V]
+    const float* own_b;      // [1]
+};
+
+// head_pool_fc: GlobalPooling<false> of the policy planes, GlobalPooling<true> of the value planes
+// (se_unit.cc:9-68) and the four small FCs (blas_forward_pipe.cc:473-481,501-507,524-532,549-555).
+// One CTA (256 threads) per sample.  Writes pint[n][P], pass5[n][5], misc15[n][15].
+__global__ void __launch_bounds__(256)
+head_pool_fc_kernel(const float* __restrict__ pv, const uint8_t* __restrict__ mask,
+                    const int* __restrict__ board_sizes, Geom g, int P, int V, HeadWeights hw, int act,
+                    float* __restrict__ pint, float* __restrict__ pass5, float* __restrict__ misc15) {
+    extern __shared__ float sm[];
+    const int PV = P + V;
+    const int b = blockIdx.x, bs = board_sizes[b];
+    const int n_rg = 256 / PV;
+    float* part_sum = sm;                    // [n_rg][PV]
+    float* part_max = sm + n_rg * PV;        // [n_rg][PV]
+    float* ppool = part_max + n_rg * PV;     // [3P]
+    float* vpool = ppool + 3 * P;            // [3V]
+    float* spint = vpool + 3 * V;            // [P]
+    float* svint = spint + P;                // [3V]
+    const int tid = threadIdx.x;
+    const int rg = tid / PV, c = tid - rg * PV;
+    const int row0 = kGuardRows + b * g.SS;
+    if (rg < n_rg) {
+        float s = 0.f, m = -5000.f;
+        for (int r = rg; r < g.SS; r += n_rg) {
+            if (!mask[row0 + r]) continue;
+            const float v = pv[(size_t)(row0 + r) * PV + c];
+            s += v;
+            m = fmaxf(m, v);
+        }
+        part_sum[rg * PV + c] = s;
+        part_max[rg * PV + c] = m;
+    }
+    __syncthreads();
+    const float b_diff = (float)bs - 14.0f;
+    if (tid < PV) {
+        float s = 0.f, m = -5000.f;
+        for (int k = 0; k < n_rg; ++k) {
+            s += part_sum[k * PV + tid];
+            m = fmaxf(m, part_max[k * PV + tid]);
+        }
+        const float mean = s / (float)(bs * bs);
+        if (tid < P) {
+            ppool[tid] = mean;
+            ppool[P + tid] = mean * (b_diff / 10.f);
+            ppool[2 * P + tid] = m;
+        } else {
+            const int v = tid - P;
+            vpool[v] = mean;
+            vpool[V + v] = mean * (b_diff / 10.f);
+            vpool[2 * V + v] = mean * (b_diff * b_diff / 100.f - 0.1f);
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int o = warp; o < P + 3 * V; o += 8) {
+        if (o < P) {
+            float acc = 0.f;
+            for (int i = lane; i < 3 * P; i += 32) acc += hw.p_inter_w[o * 3 * P + i] * ppool[i];
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const float r = activate(acc + hw.p_inter_b[o], act);
+                spint[o] = r;
+                pint[(size_t)b * P + o] = r;
+            }
+        } else {
+            const int ov = o - P;
+            float acc = 0.f;
+            for (int i = lane; i < 3 * V; i += 32) acc += hw.v_inter_w[ov * 3 * V + i] * vpool[i];
+            acc = warp_sum(acc);
+            if (lane == 0) svint[ov] = activate(acc + hw.v_inter_b[ov], act);
+        }
+    }
+    __syncthreads();
+    for (int o = warp; o < 20; o += 8) {
+        if (o < 5) {
+            float acc = 0.f;
+            for (int i = lane; i < P; i += 32) acc += hw.pass_w[o * P + i] * spint[i];
+            acc = warp_sum(acc);
+            if (lane == 0) pass5[(size_t)b * 5 + o] = acc + hw.pass_b[o];
+        } else {
+            const int om = o - 5;
+            float acc = 0.f;
+            for (int i = lane; i < 3 * V; i += 32) acc += hw.misc_w[om * 3 * V + i] * svint[i];
+            acc = warp_sum(acc);
+            if (lane == 0) misc15[(size_t)b * 15 + om] = acc + hw.misc_b[om];
+        }
+    }
+}
+
+// Per-sample output record handed back through the C ABI (sb_output in include/sayuri_b200.h).
+constexpr int kOutFloats = 2 * kMaxIntersections + 8;
+
+// head_out: policy_conv += intermediate (blas_forward_pipe.cc:483-484), the P->5 and V->1 1x1 convs
+// (:487-499,535-547) and FillOutputs (:597-618): only the requested policy channel `offset` is
+// evaluated, outputs are written in the sample's NATIVE n x n order (the crop of
+// batch_forward_pipe.cc:48-67) and zero-filled up to 361, misc values are gathered to
+// {pass[offset], wdl0..2, stm(3), final_score(8), q_error(13), score_error(14)}.
+__global__ void __launch_bounds__(384)
+head_out_kernel(const float* __restrict__ pv, const int* __restrict__ board_sizes,
+                const int* __restrict__ offsets, Geom g, int P, int V, HeadWeights hw,
+                const float* __restrict__ pint, const float* __restrict__ pass5,
+                const float* __restrict__ misc15, float* __restrict__ out) {
+    const int b = blockIdx.x, i = threadIdx.x;
+    const int bs = board_sizes[b], off = offsets[b];
+    const int PV = P + V;
+    float* o = out + (size_t)b * kOutFloats;
+    if (i < kMaxIntersections) {
+        float prob = 0.f, own = 0.f;
+        if (i < bs * bs) {
+            const int y = i / bs, x = i - y * bs;
+            const float* row = pv + (size_t)g.row(b, y, x) * PV;
+            prob = hw.prob_b[off];
+            for (int c = 0; c < P; ++c) prob += hw.prob_w[off * P + c] * (row[c] + pint[(size_t)b * P + c]);
+            own = hw.own_b[0];
+            for (int c = 0; c < V; ++c) own += hw.own_w[c] * row[P + c];
+        }
+        o[i] = prob;
+        o[kMaxIntersections + i] = own;
+    } else if (i < kMaxIntersections + 8) {
+        const int k = i - kMaxIntersections;
+        const float* m = misc15 + (size_t)b * 15;
+        float v;
+        switch (k) {
+            case 0: v = pass5[(size_t)b * 5 + off]; break;
+            case 1: v = m[0]; break;
+            case 2: v = m[1]; break;
+            case 3: v = m[2]; break;
+            case 4: v = m[3]; break;
+            case 5: v = m[8]; break;
+            case 6: v = m[13]; break;
+            default: v = m[14]; break;
+        }
+        o[2 * kMaxIntersections + k] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv3x3_simt: fp32 CUDA-core evaluation of the SAME convolution on the SAME canvas buffers.  It is
+// the on-device cross-check for conv3x3_tc (tests compare the two layer by layer) and never the
+// default; selected only with precision = SB_PRECISION_SIMT_DEBUG.
+// wT: fp32 [9*CINp][cout] (k-major rows, cout contiguous).  One thread per (row, cout).
+__global__ void __launch_bounds__(256)
+conv3x3_simt_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, bool split, int cinp,
+                    const float* __restrict__ wT, const float* __restrict__ bias,
+                    const __half* __restrict__ res_hi, const __half* __restrict__ res_lo,
+                    const uint8_t* __restrict__ mask, int cout, int n_rows, int pitch, int act,
+                    __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_pitch) {
+    const int co = blockIdx.y * 32 + threadIdx.x;
+    const int r = blockIdx.x * 8 + threadIdx.y;
+    if (r >= n_rows || co >= cout) return;
+    const int row = kGuardRows + r;
+    const size_t off = (size_t)row * out_pitch + co;
+    float v = 0.f;
+    if (mask[row]) {
+        float acc = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int src = row + (tap / 3 - 1) * pitch + (tap % 3 - 1);
+            const __half* ah = in_hi + (size_t)src * cinp;
+            const __half* al = in_lo + (size_t)src * cinp;
+            const float* w = wT + (size_t)tap * cinp * cout + co;
+            for (int c = 0; c < cinp; ++c) {
+                float a = __half2float(ah[c]);
+                if (split) a += __half2float(al[c]);
+                acc += a * w[(size_t)c * cout];
+            }
+        }
+        acc += bias[co];
+        if (res_hi) {
+            acc += __half2float(res_hi[off]);
+            if (split) acc += __half2float(res_lo[off]);
+        }
+        v = activate(acc, act);
+    }
+    __half h, l;
+    split_f16(v, h, l);
+    out_hi[off] = h;
+    if (split) out_lo[off] = l;
+}
+
+}  // namespace sb

@@ -1,0 +1,66 @@
+// Shared definitions: canvas geometry, activations, fp16 hi/lo split helpers.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+// ---- Canvas layout (DESIGN.md "Data layout in HBM") -------------------------------------------
+// Activations are NHWC matrices [rows][C] of fp16 (a `hi` tensor and, in split precision, a `lo`
+// tensor with x ~= hi + lo).  Sample b, board cell (y, x) of an N x N canvas lives at row
+//     kGuardRows + b * SS + y * P + x,     P = N + 1,  SS = (N + 1) * (N + 1)
+// i.e. every board row carries ONE trailing halo cell and every sample ONE trailing halo row; the
+// halo cell right of row y doubles as the halo left of row y+1, the halo row below sample b doubles
+// as the halo above sample b+1.  All halo cells are kept at zero by the epilogues, so a 3x3 tap
+// (ky, kx) of the convolution is the constant row shift (ky-1)*P + (kx-1): the implicit GEMM needs no
+// im2col, only shifted views of one resident tile (19x19: 400 rows per sample for 361 real cells).
+constexpr int kGuardRows = 32;   // zero rows in front of sample 0 (top halo of sample 0, TMA coords stay >= 0)
+constexpr int kSuperRows = 256;  // rows per CTA work item: two UMMA M=128 tiles
+constexpr int kSlabMargin = 24;  // slab rows loaded before/after the super tile (>= P + 1, multiple of 8)
+constexpr int kSlabRows = kSuperRows + 2 * kSlabMargin;  // 304
+constexpr int kMaxBoard = 19;    // /root/reference/src/game/types.h:5-7 (MAX_BOARD_SIZE)
+constexpr int kMaxIntersections = kMaxBoard * kMaxBoard;
+constexpr int kInputChannels = 43;   // /root/reference/src/neural/network_basic.h:10
+constexpr int kInputChannelsPadded = 64;
+
+struct Geom {
+    int N, P, SS;
+    __host__ __device__ Geom() : N(0), P(0), SS(0) {}
+    __host__ __device__ explicit Geom(int n) : N(n), P(n + 1), SS((n + 1) * (n + 1)) {}
+    __host__ __device__ int row(int b, int y, int x) const { return kGuardRows + b * SS + y * P + x; }
+    __host__ __device__ int rows_used(int batch) const { return kGuardRows + batch * SS; }
+    __host__ __device__ int n_super(int batch) const { return (batch * SS + kSuperRows - 1) / kSuperRows; }
+    __host__ __device__ int rows_alloc(int max_batch) const { return kGuardRows + n_super(max_batch) * kSuperRows + 64; }
+};
+
+// ---- Activations: same ints and formulas as /root/reference/src/neural/activation.h:8-17,43-59 --
+enum Act : int { kIdentity = 0, kReLU = 1, kELU = 2, kSELU = 3, kGELU = 4, kMISH = 5, kSwish = 6, kHardSwish = 7 };
+
+__device__ __forceinline__ float activate(float x, int act) {
+    switch (act) {
+        case kReLU: return x > 0.f ? x : 0.f;
+        case kELU: return x > 0.f ? x : (expf(x) - 1.f);
+        case kSELU: return x > 0.f ? (1.05070098f * x) : (1.05070098f * 1.67326324f * (expf(x) - 1.0f));
+        case kGELU: return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+        case kMISH: {
+            // x * tanh(log(1 + e^x)) == x * n / (n + 2), n = e^x (e^x + 2): no cancellation, one expf.
+            if (x > 20.f) return x;
+            const float w = expf(x);
+            const float n = w * (w + 2.f);
+            return x * (n / (n + 2.f));
+        }
+        case kSwish: return x / (1.0f + expf(-x));
+        case kHardSwish: return x >= 3.f ? x : x <= -3.f ? 0.f : (x * (x + 3.0f) / 6.0f);
+        default: return x;
+    }
+}
+
+// ---- fp16 hi/lo split: v ~= hi + lo with ~22 significant bits ---------------------------------
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+    v = fminf(fmaxf(v, -60000.f), 60000.f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+}  // namespace sb

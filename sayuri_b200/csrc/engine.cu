@@ -1,0 +1,1042 @@
+// Engine + C ABI (include/sayuri_b200.h).  One Replica per GPU (weights blob, tensor maps), a few
+// independent Slots per replica (stream, pinned staging, activations) so that H2D / compute / D2H of
+// consecutive batches overlap.  Mirrors the lifetime and semantics of the reference GPU pipe
+//   CudaForwardPipe / NNGraph      /root/reference/src/neural/cuda/cuda_forward_pipe.cc:14-131,133-613,684-1136
+// but none of its structure: NHWC canvas activations, one fused tensor-core conv kernel per layer,
+// device-side canvas placement / crop / policy-channel gather.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sayuri_b200.h"
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "conv3x3_tc.cuh"
+#include "host_net.h"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------
+struct CudaError {
+    std::string msg;
+};
+#define SB_CUDA(call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            throw CudaError{std::string("CUDA Error: ") + cudaGetErrorString(e__) + " at " + #call + " (" + \
+                            __FILE__ + ":" + std::to_string(__LINE__) + ")"};                             \
+        }                                                                                                 \
+    } while (0)
+
+static inline int RoundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency,
+// so the library also loads on a box without a driver (the "symbols exported" CPU test).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn GetEncodeTiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+    });
+    if (!fn) throw CudaError{"cuTensorMapEncodeTiled is unavailable (driver too old?)"};
+    return fn;
+}
+
+// 2-D fp16 row-major tensor [rows][cols], box = [box_rows][64 cols], 128-byte swizzle, zero OOB fill.
+static CUtensorMap MakeMap2D(const void* base, int rows, int cols, int box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = GetEncodeTiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)};
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight blob: every device-resident parameter of one replica, packed once on the host.
+struct ConvLayout {
+    int cin = 0, cinp = 0, cout = 0, kh = 0, bn = 0, ntiles = 0;
+    size_t w_hi = 0, w_lo = 0, bias = 0;  // byte offsets into the blob
+};
+struct FcLayout {
+    int in = 0, out = 0;
+    size_t w = 0, b = 0;
+};
+struct BlobLayout {
+    ConvLayout input;
+    std::vector<ConvLayout> conv1, conv2;
+    std::vector<FcLayout> squeeze, excite;  // per block (unused entries when se_size == 0)
+    size_t head_wT = 0, head_b = 0;         // [C][P+V], [P+V]
+    FcLayout p_inter, pass, v_inter, misc;
+    size_t prob_w = 0, prob_b = 0, own_w = 0, own_b = 0;
+    size_t bytes = 0;
+};
+
+static size_t Take(size_t& cursor, size_t bytes) {
+    const size_t at = cursor;
+    cursor = (cursor + bytes + 255) & ~(size_t)255;
+    return at;
+}
+
+static ConvLayout LayConv(size_t& cur, int cin, int cout) {
+    ConvLayout c;
+    c.cin = cin;
+    c.cinp = RoundUp(cin, 64);
+    c.cout = cout;
+    c.kh = c.cinp / 64;
+    c.bn = cout <= 128 ? cout : cout / 2;
+    c.ntiles = cout / c.bn;
+    const size_t mat = (size_t)cout * 9 * c.cinp * sizeof(__half);
+    c.w_hi = Take(cur, mat);
+    c.w_lo = Take(cur, mat);
+    c.bias = Take(cur, (size_t)cout * sizeof(float));
+    return c;
+}
+static FcLayout LayFc(size_t& cur, int in, int out) {
+    FcLayout f;
+    f.in = in;
+    f.out = out;
+    f.w = Take(cur, (size_t)in * out * sizeof(float));
+    f.b = Take(cur, (size_t)out * sizeof(float));
+    return f;
+}
+
+static BlobLayout ComputeLayout(int blocks, int C, int P, int V, const std::vector<int>& se) {
+    BlobLayout L;
+    size_t cur = 0;
+    L.input = LayConv(cur, SB_INPUT_CHANNELS, C);
+    L.conv1.resize(blocks);
+    L.conv2.resize(blocks);
+    L.squeeze.resize(blocks);
+    L.excite.resize(blocks);
+    for (int b = 0; b < blocks; ++b) {
+        L.conv1[b] = LayConv(cur, C, C);
+        L.conv2[b] = LayConv(cur, C, C);
+        if (se[b] > 0) {
+            L.squeeze[b] = LayFc(cur, 3 * C, se[b]);
+            L.excite[b] = LayFc(cur, se[b], 2 * C);
+        }
+    }
+    L.head_wT = Take(cur, (size_t)C * (P + V) * sizeof(float));
+    L.head_b = Take(cur, (size_t)(P + V) * sizeof(float));
+    L.p_inter = LayFc(cur, 3 * P, P);
+    L.pass = LayFc(cur, P, 5);
+    L.v_inter = LayFc(cur, 3 * V, 3 * V);
+    L.misc = LayFc(cur, 3 * V, 15);
+    L.prob_w = Take(cur, (size_t)5 * P * sizeof(float));
+    L.prob_b = Take(cur, 5 * sizeof(float));
+    L.own_w = Take(cur, (size_t)V * sizeof(float));
+    L.own_b = Take(cur, sizeof(float));
+    L.bytes = cur;
+    return L;
+}
+
+// OIHW fp32 -> K-major [cout][tap * cinp + c] fp16 hi / lo (the B operand of the implicit GEMM).
+static void PackConv(const HostConv& hc, const ConvLayout& L, uint8_t* blob) {
+    __half* hi = reinterpret_cast<__half*>(blob + L.w_hi);
+    __half* lo = reinterpret_cast<__half*>(blob + L.w_lo);
+    const size_t K = (size_t)9 * L.cinp;
+    for (int o = 0; o < L.cout; ++o) {
+        for (int tap = 0; tap < 9; ++tap) {
+            for (int c = 0; c < L.cinp; ++c) {
+                float w = 0.f;
+                if (c < L.cin) w = hc.w[((size_t)o * L.cin + c) * 9 + tap];
+                const __half h = __float2half_rn(w);
+                const __half l = __float2half_rn(w - __half2float(h));
+                hi[(size_t)o * K + (size_t)tap * L.cinp + c] = h;
+                lo[(size_t)o * K + (size_t)tap * L.cinp + c] = l;
+            }
+        }
+    }
+    std::memcpy(blob + L.bias, hc.b.data(), (size_t)L.cout * sizeof(float));
+}
+static void PackFc(const HostFC& f, const FcLayout& L, uint8_t* blob) {
+    std::memcpy(blob + L.w, f.w.data(), f.w.size() * sizeof(float));
+    std::memcpy(blob + L.b, f.b.data(), f.b.size() * sizeof(float));
+}
+
+static std::vector<uint8_t> PackBlob(const HostNet& n, const BlobLayout& L) {
+    std::vector<uint8_t> blob(L.bytes, 0);
+    uint8_t* p = blob.data();
+    PackConv(n.input_conv, L.input, p);
+    for (int b = 0; b < n.blocks; ++b) {
+        PackConv(n.tower[b].conv1, L.conv1[b], p);
+        PackConv(n.tower[b].conv2, L.conv2[b], p);
+        if (n.tower[b].se_size > 0) {
+            PackFc(n.tower[b].squeeze, L.squeeze[b], p);
+            PackFc(n.tower[b].excite, L.excite[b], p);
+        }
+    }
+    const int C = n.channels, P = n.P, V = n.V, PV = P + V;
+    float* wT = reinterpret_cast<float*>(p + L.head_wT);
+    float* hb = reinterpret_cast<float*>(p + L.head_b);
+    for (int c = 0; c < C; ++c) {
+        for (int j = 0; j < P; ++j) wT[(size_t)c * PV + j] = n.p_hd_conv.w[(size_t)j * C + c];
+        for (int j = 0; j < V; ++j) wT[(size_t)c * PV + P + j] = n.v_hd_conv.w[(size_t)j * C + c];
+    }
+    for (int j = 0; j < P; ++j) hb[j] = n.p_hd_conv.b[j];
+    for (int j = 0; j < V; ++j) hb[P + j] = n.v_hd_conv.b[j];
+    PackFc(n.p_inter_fc, L.p_inter, p);
+    PackFc(n.pass_fc, L.pass, p);
+    PackFc(n.v_inter_fc, L.v_inter, p);
+    PackFc(n.v_misc, L.misc, p);
+    std::memcpy(p + L.prob_w, n.prob_conv.w.data(), (size_t)5 * P * sizeof(float));
+    std::memcpy(p + L.prob_b, n.prob_conv.b.data(), 5 * sizeof(float));
+    std::memcpy(p + L.own_w, n.v_ownership.w.data(), (size_t)V * sizeof(float));
+    std::memcpy(p + L.own_b, n.v_ownership.b.data(), sizeof(float));
+    return blob;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct ActBuf {
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    int pitch = 0;
+    CUtensorMap tm_hi, tm_lo;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    float* h_in = nullptr;     // pinned [max_batch][SB_PLANE_FLOATS]
+    float* d_in = nullptr;
+    int* h_meta = nullptr;     // pinned [2][max_batch]: board sizes, policy offsets
+    int* d_meta = nullptr;
+    float* d_out = nullptr;    // [max_batch][kOutFloats]
+    float* h_out = nullptr;    // pinned
+    ActBuf in, x, t, u;
+    ActBuf* trunk = nullptr;   // which buffer holds the tower output after the last forward
+    uint8_t* mask = nullptr;
+    float* gb = nullptr;       // [max_batch][2C]
+    float* pv = nullptr;       // [rows][P+V]
+    float* pint = nullptr;
+    float* pass5 = nullptr;
+    float* misc15 = nullptr;
+    int* h_err = nullptr;      // mapped pinned: barrier-timeout site code survives a trapped context
+    int* d_err = nullptr;
+    int n = 0;                 // samples of the batch in flight / last uploaded
+    bool busy = false;
+    std::vector<int> sizes, offsets;
+};
+
+struct DevConv {
+    ConvLayout L;
+    CUtensorMap tm_hi, tm_lo;
+    float* wT = nullptr;  // fp32 [9*cinp][cout], SIMT debug only
+};
+
+struct Replica {
+    int device = -1;
+    uint8_t* blob = nullptr;
+    DevConv input;
+    std::vector<DevConv> conv1, conv2;
+    std::vector<Slot> slots;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    int sm_count = 0;
+};
+
+}  // namespace sb
+
+using namespace sb;
+
+struct sb_engine {
+    HostNet net_shape;  // scalar fields + se sizes only (tensors dropped after packing)
+    std::vector<int> se_sizes;
+    BlobLayout layout;
+    std::vector<Replica> replicas;
+    Geom geom;
+    int max_batch = 0;
+    int rows_alloc = 0;
+    int precision = SB_PRECISION_FP32_SPLIT;
+    int bo_mode = 0;
+    int n_slots = 2;
+    bool weights_ready = false;
+    std::atomic<long long> launches{0};
+    std::string last_error;
+    std::vector<float> host_wT_scratch;
+};
+
+static std::string g_create_error;
+
+namespace sb {
+
+static bool Split(const sb_engine* e) { return e->precision != SB_PRECISION_FP16; }
+
+static void FreeSlot(Slot& s) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.ev_a) cudaEventDestroy(s.ev_a);
+    if (s.ev_b) cudaEventDestroy(s.ev_b);
+    cudaFreeHost(s.h_in);
+    cudaFree(s.d_in);
+    cudaFreeHost(s.h_meta);
+    cudaFree(s.d_meta);
+    cudaFree(s.d_out);
+    cudaFreeHost(s.h_out);
+    for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u}) {
+        cudaFree(a->hi);
+        cudaFree(a->lo);
+    }
+    cudaFree(s.mask);
+    cudaFree(s.gb);
+    cudaFree(s.pv);
+    cudaFree(s.pint);
+    cudaFree(s.pass5);
+    cudaFree(s.misc15);
+    cudaFreeHost(s.h_err);
+    s = Slot{};
+}
+
+static void AllocAct(ActBuf& a, int rows, int pitch, bool split) {
+    a.pitch = pitch;
+    const size_t bytes = (size_t)rows * pitch * sizeof(__half);
+    SB_CUDA(cudaMalloc(&a.hi, bytes));
+    SB_CUDA(cudaMemset(a.hi, 0, bytes));
+    a.tm_hi = MakeMap2D(a.hi, rows, pitch, kSlabRows / 2);
+    if (split) {
+        SB_CUDA(cudaMalloc(&a.lo, bytes));
+        SB_CUDA(cudaMemset(a.lo, 0, bytes));
+        a.tm_lo = MakeMap2D(a.lo, rows, pitch, kSlabRows / 2);
+    } else {
+        a.lo = a.hi;
+        a.tm_lo = a.tm_hi;
+    }
+}
+
+static void AllocSlots(sb_engine* e, Replica& r) {
+    SB_CUDA(cudaSetDevice(r.device));
+    const int C = e->net_shape.channels, P = e->net_shape.P, V = e->net_shape.V;
+    const int Cp = RoundUp(C, 64);
+    const int rows = e->rows_alloc;
+    const bool split = Split(e);
+    r.slots.resize(e->n_slots);
+    for (Slot& s : r.slots) {
+        SB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreate(&s.ev_a));
+        SB_CUDA(cudaEventCreate(&s.ev_b));
+        const size_t in_bytes = (size_t)e->max_batch * SB_PLANE_FLOATS * sizeof(float);
+        SB_CUDA(cudaHostAlloc(&s.h_in, in_bytes, cudaHostAllocDefault));
+        SB_CUDA(cudaMalloc(&s.d_in, in_bytes));
+        SB_CUDA(cudaHostAlloc(&s.h_meta, (size_t)2 * e->max_batch * sizeof(int), cudaHostAllocDefault));
+        SB_CUDA(cudaMalloc(&s.d_meta, (size_t)2 * e->max_batch * sizeof(int)));
+        const size_t out_bytes = (size_t)e->max_batch * kOutFloats * sizeof(float);
+        SB_CUDA(cudaMalloc(&s.d_out, out_bytes));
+        SB_CUDA(cudaHostAlloc(&s.h_out, out_bytes, cudaHostAllocDefault));
+        AllocAct(s.in, rows, kInputChannelsPadded, split);
+        AllocAct(s.x, rows, Cp, split);
+        AllocAct(s.t, rows, Cp, split);
+        AllocAct(s.u, rows, Cp, split);
+        SB_CUDA(cudaMalloc(&s.mask, (size_t)rows));
+        SB_CUDA(cudaMemset(s.mask, 0, (size_t)rows));
+        SB_CUDA(cudaMalloc(&s.gb, (size_t)e->max_batch * 2 * C * sizeof(float)));
+        SB_CUDA(cudaMalloc(&s.pv, (size_t)rows * (P + V) * sizeof(float)));
+        SB_CUDA(cudaMemset(s.pv, 0, (size_t)rows * (P + V) * sizeof(float)));
+        SB_CUDA(cudaMalloc(&s.pint, (size_t)e->max_batch * P * sizeof(float)));
+        SB_CUDA(cudaMalloc(&s.pass5, (size_t)e->max_batch * 5 * sizeof(float)));
+        SB_CUDA(cudaMalloc(&s.misc15, (size_t)e->max_batch * 15 * sizeof(float)));
+        SB_CUDA(cudaHostAlloc(&s.h_err, sizeof(int), cudaHostAllocMapped));
+        *s.h_err = 0;
+        SB_CUDA(cudaHostGetDevicePointer(&s.d_err, s.h_err, 0));
+        s.sizes.assign(e->max_batch, 0);
+        s.offsets.assign(e->max_batch, 0);
+    }
+}
+
+static void MakeConvMaps(const Replica& r, DevConv& c) {
+    c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, 9 * c.L.cinp, c.L.bn);
+    c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, 9 * c.L.cinp, c.L.bn);
+}
+
+// fp32 transposed weights for the SIMT cross-check kernel, derived from the packed hi/lo matrices.
+static void MakeSimtWeights(sb_engine* e, Replica& r, DevConv& c, const std::vector<uint8_t>& blob) {
+    const size_t K = (size_t)9 * c.L.cinp;
+    std::vector<float> wT(K * c.L.cout);
+    const __half* hi = reinterpret_cast<const __half*>(blob.data() + c.L.w_hi);
+    const __half* lo = reinterpret_cast<const __half*>(blob.data() + c.L.w_lo);
+    for (int o = 0; o < c.L.cout; ++o)
+        for (size_t k = 0; k < K; ++k) wT[k * c.L.cout + o] = __half2float(hi[o * K + k]) + __half2float(lo[o * K + k]);
+    if (!c.wT) SB_CUDA(cudaMalloc(&c.wT, wT.size() * sizeof(float)));
+    SB_CUDA(cudaMemcpy(c.wT, wT.data(), wT.size() * sizeof(float), cudaMemcpyHostToDevice));
+    (void)e;
+    (void)r;
+}
+
+static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* blob) {
+    SB_CUDA(cudaSetDevice(r.device));
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, r.device));
+    if (prop.major != 10) {
+        throw CudaError{"sayuri_b200 requires a Blackwell sm_100 device; device " + std::to_string(r.device) + " is sm_" +
+                        std::to_string(prop.major) + std::to_string(prop.minor)};
+    }
+    r.sm_count = prop.multiProcessorCount;
+    if (!r.blob) SB_CUDA(cudaMalloc(&r.blob, e->layout.bytes));
+    if (blob) SB_CUDA(cudaMemcpy(r.blob, blob->data(), e->layout.bytes, cudaMemcpyHostToDevice));
+    const int blocks = e->net_shape.blocks;
+    r.input.L = e->layout.input;
+    MakeConvMaps(r, r.input);
+    r.conv1.resize(blocks);
+    r.conv2.resize(blocks);
+    for (int b = 0; b < blocks; ++b) {
+        r.conv1[b].L = e->layout.conv1[b];
+        r.conv2[b].L = e->layout.conv2[b];
+        MakeConvMaps(r, r.conv1[b]);
+        MakeConvMaps(r, r.conv2[b]);
+    }
+    if (blob && e->precision == SB_PRECISION_SIMT_DEBUG) {
+        MakeSimtWeights(e, r, r.input, *blob);
+        for (int b = 0; b < blocks; ++b) {
+            MakeSimtWeights(e, r, r.conv1[b], *blob);
+            MakeSimtWeights(e, r, r.conv2[b], *blob);
+        }
+    }
+    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::kSmemBytes));
+    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::kSmemBytes));
+}
+
+static void DestroyReplica(Replica& r) {
+    if (r.device >= 0) cudaSetDevice(r.device);
+    for (Slot& s : r.slots) FreeSlot(s);
+    r.slots.clear();
+    auto free_conv = [](DevConv& c) {
+        cudaFree(c.wT);
+        c.wT = nullptr;
+    };
+    free_conv(r.input);
+    for (auto& c : r.conv1) free_conv(c);
+    for (auto& c : r.conv2) free_conv(c);
+    cudaFree(r.blob);
+    r.blob = nullptr;
+    cudaFree(r.flush_buf);
+    r.flush_buf = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward orchestration
+struct ConvTimer {
+    std::vector<cudaEvent_t> ev;  // pairs
+    bool on = false;
+};
+
+static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, const ActBuf& in, ActBuf& out,
+                       const ActBuf* res, int act, int n, ConvTimer* tm) {
+    const int n_super = e->geom.n_super(n);
+    if (tm && tm->on) {
+        cudaEvent_t a;
+        SB_CUDA(cudaEventCreate(&a));
+        SB_CUDA(cudaEventRecord(a, s.stream));
+        tm->ev.push_back(a);
+    }
+    if (e->precision == SB_PRECISION_SIMT_DEBUG) {
+        dim3 grid((n_super * kSuperRows + 7) / 8, (c.L.cout + 31) / 32), block(32, 8);
+        conv3x3_simt_kernel<<<grid, block, 0, s.stream>>>(in.hi, in.lo, true, c.L.cinp, c.wT,
+                                                          reinterpret_cast<const float*>(r.blob + c.L.bias),
+                                                          res ? res->hi : nullptr, res ? res->lo : nullptr, s.mask,
+                                                          c.L.cout, n_super * kSuperRows, e->geom.P, act, out.hi, out.lo,
+                                                          out.pitch);
+    } else {
+        ConvParams p;
+        p.out_hi = out.hi;
+        p.out_lo = out.lo;
+        p.res_hi = res ? res->hi : nullptr;
+        p.res_lo = res ? res->lo : nullptr;
+        p.bias = reinterpret_cast<const float*>(r.blob + c.L.bias);
+        p.mask = s.mask;
+        p.cout = c.L.cout;
+        p.out_pitch = out.pitch;
+        p.kh = c.L.kh;
+        p.bn = c.L.bn;
+        p.n_super = n_super;
+        p.n_ntiles = c.L.ntiles;
+        p.pitch = e->geom.P;
+        p.act = act;
+        p.bo_mode = e->bo_mode;
+        p.err = s.d_err;
+        const int items = n_super * c.L.ntiles;
+        const int grid = std::min(items, r.sm_count);
+        if (Split(e)) {
+            conv3x3_tc_kernel<true><<<grid, 384, ConvCfg<true>::kSmemBytes, s.stream>>>(in.tm_hi, in.tm_lo, c.tm_hi, c.tm_lo, p);
+        } else {
+            conv3x3_tc_kernel<false><<<grid, 384, ConvCfg<false>::kSmemBytes, s.stream>>>(in.tm_hi, in.tm_hi, c.tm_hi, c.tm_hi, p);
+        }
+    }
+    SB_CUDA(cudaGetLastError());
+    e->launches++;
+    if (tm && tm->on) {
+        cudaEvent_t b;
+        SB_CUDA(cudaEventCreate(&b));
+        SB_CUDA(cudaEventRecord(b, s.stream));
+        tm->ev.push_back(b);
+    }
+}
+
+template <int PV>
+static void LaunchHeadConv(sb_engine* e, Replica& r, Slot& s, const ActBuf& x, int n_rows) {
+    const int C = e->net_shape.channels;
+    const size_t smem = ((size_t)C * PV + PV) * sizeof(float);
+    static thread_local bool attr_set[16] = {false};
+    if (smem > 48 * 1024 && !attr_set[r.device & 15]) {
+        SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[r.device & 15] = true;
+    }
+    head_conv_kernel<PV><<<(n_rows + 127) / 128, 128, smem, s.stream>>>(
+        x.hi, x.lo, Split(e), s.mask, reinterpret_cast<const float*>(r.blob + e->layout.head_wT),
+        reinterpret_cast<const float*>(r.blob + e->layout.head_b), C, x.pitch, n_rows, e->net_shape.act, s.pv);
+}
+
+// Everything between "inputs are in d_in / d_meta" and "outputs are in d_out", on the slot's stream.
+static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* tm = nullptr) {
+    const HostNet& ns = e->net_shape;
+    const Geom g = e->geom;
+    const int C = ns.channels, P = ns.P, V = ns.V, act = ns.act;
+    const bool split = Split(e);
+    const int n_rows = g.n_super(n) * kSuperRows;
+    const int* d_sizes = s.d_meta;
+    const int* d_offsets = s.d_meta + e->max_batch;
+    const BlobLayout& L = e->layout;
+    auto F = [&](size_t off) { return reinterpret_cast<const float*>(r.blob + off); };
+
+    {   // input planes -> canvas
+        const int threads = n_rows * 8;
+        unpack_planes_kernel<<<(threads + 255) / 256, 256, 0, s.stream>>>(s.d_in, (size_t)SB_PLANE_FLOATS, d_sizes, g, n,
+                                                                          n_rows, s.in.hi, s.in.lo, split, s.mask);
+        SB_CUDA(cudaGetLastError());
+        e->launches++;
+    }
+    ActBuf* x = &s.x;
+    ActBuf* t = &s.t;
+    ActBuf* u = &s.u;
+    LaunchConv(e, r, s, r.input, s.in, *x, nullptr, act, n, tm);
+    for (int b = 0; b < ns.blocks; ++b) {
+        LaunchConv(e, r, s, r.conv1[b], *x, *t, nullptr, act, n, tm);
+        const int se = e->se_sizes[b];
+        if (se > 0) {
+            LaunchConv(e, r, s, r.conv2[b], *t, *u, nullptr, kIdentity, n, tm);
+            const int n_rg = 256 / (C / 2);
+            const size_t smem = ((size_t)2 * n_rg * C + 3 * C + se) * sizeof(float);
+            se_pool_fc_kernel<<<n, 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->pitch, se,
+                                                          F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
+                                                          F(L.excite[b].b), act, s.gb);
+            SB_CUDA(cudaGetLastError());
+            const size_t total = (size_t)n_rows * (C / 8);
+            se_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(u->hi, u->lo, x->hi, x->lo, split, s.mask,
+                                                                                   s.gb, g, C, u->pitch, n_rows, act);
+            SB_CUDA(cudaGetLastError());
+            e->launches += 2;
+        } else {
+            LaunchConv(e, r, s, r.conv2[b], *t, *u, x, act, n, tm);
+        }
+        std::swap(x, u);
+    }
+    s.trunk = x;
+    // heads
+    switch (P + V) {
+        case 16: LaunchHeadConv<16>(e, r, s, *x, n_rows); break;
+        case 32: LaunchHeadConv<32>(e, r, s, *x, n_rows); break;
+        case 48: LaunchHeadConv<48>(e, r, s, *x, n_rows); break;
+        case 64: LaunchHeadConv<64>(e, r, s, *x, n_rows); break;
+        default: throw CudaError{"unsupported policy+value head width " + std::to_string(P + V) + " (16/32/48/64)"};
+    }
+    SB_CUDA(cudaGetLastError());
+    HeadWeights hw;
+    hw.p_inter_w = F(L.p_inter.w);
+    hw.p_inter_b = F(L.p_inter.b);
+    hw.pass_w = F(L.pass.w);
+    hw.pass_b = F(L.pass.b);
+    hw.v_inter_w = F(L.v_inter.w);
+    hw.v_inter_b = F(L.v_inter.b);
+    hw.misc_w = F(L.misc.w);
+    hw.misc_b = F(L.misc.b);
+    hw.prob_w = F(L.prob_w);
+    hw.prob_b = F(L.prob_b);
+    hw.own_w = F(L.own_w);
+    hw.own_b = F(L.own_b);
+    {
+        const int PV = P + V, n_rg = 256 / PV;
+        const size_t smem = ((size_t)2 * n_rg * PV + 3 * P + 3 * V + P + 3 * V) * sizeof(float);
+        head_pool_fc_kernel<<<n, 256, smem, s.stream>>>(s.pv, s.mask, d_sizes, g, P, V, hw, act, s.pint, s.pass5, s.misc15);
+        SB_CUDA(cudaGetLastError());
+        head_out_kernel<<<n, 384, 0, s.stream>>>(s.pv, d_sizes, d_offsets, g, P, V, hw, s.pint, s.pass5, s.misc15, s.d_out);
+        SB_CUDA(cudaGetLastError());
+    }
+    e->launches += 3;
+}
+
+static void CheckSlotError(Slot& s, cudaError_t err, const char* what) {
+    if (err == cudaSuccess) return;
+    std::string msg = std::string("CUDA Error: ") + cudaGetErrorString(err) + " in " + what;
+    if (s.h_err && *s.h_err != 0) msg += " (pipeline barrier timeout at site " + std::to_string(*s.h_err) + ")";
+    throw CudaError{msg};
+}
+
+static void Configure(sb_engine* e, int board, int max_batch) {
+    e->geom = Geom(board);
+    e->max_batch = max_batch;
+    e->rows_alloc = e->geom.rows_alloc(max_batch);
+    for (Replica& r : e->replicas) {
+        SB_CUDA(cudaSetDevice(r.device));
+        for (Slot& s : r.slots) FreeSlot(s);
+        r.slots.clear();
+        AllocSlots(e, r);
+    }
+}
+
+static int Fail(sb_engine* e, int code, const std::string& msg) {
+    if (e) e->last_error = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_only, const int* gpu_ids, int n_gpus,
+                      int board, int max_batch, int precision) {
+    if (!out) return Fail(nullptr, SB_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    if (board < 2 || board > SB_MAX_BOARD_SIZE) return Fail(nullptr, SB_ERR_INVALID, "NN board size should be in [2, 19]");
+    if (max_batch < 1) return Fail(nullptr, SB_ERR_INVALID, "NN batch size should be larger than zero");
+    if (precision < 0 || precision > 2) return Fail(nullptr, SB_ERR_INVALID, "unknown precision");
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        cudaGetLastError();
+        return Fail(nullptr, SB_ERR_CUDA, "No executable GPU device!");   // cuda_forward_pipe.cc:105-107
+    }
+    std::vector<int> gpus;
+    for (int i = 0; i < n_gpus; ++i) {
+        if (gpu_ids && gpu_ids[i] >= 0 && gpu_ids[i] < dev_count) gpus.push_back(gpu_ids[i]);
+    }
+    if (gpus.empty()) {   // reference: assign all devices automatically (cuda_forward_pipe.cc:98-104)
+        if (n_gpus > 0 && gpu_ids) return Fail(nullptr, SB_ERR_INVALID, "Not found the requested GPU device(s)");
+        for (int i = 0; i < dev_count; ++i) gpus.push_back(i);
+    }
+    std::unique_ptr<sb_engine> e(new sb_engine);
+    e->precision = precision;
+    if (net) {
+        e->net_shape.version = net->version;
+        e->net_shape.input_channels = net->input_channels;
+        e->net_shape.blocks = net->blocks;
+        e->net_shape.channels = net->channels;
+        e->net_shape.P = net->P;
+        e->net_shape.V = net->V;
+        e->net_shape.act = net->act;
+        e->se_sizes = net->se_sizes();
+    } else {
+        e->net_shape.version = shape_only->version;
+        e->net_shape.input_channels = shape_only->input_channels;
+        e->net_shape.blocks = shape_only->blocks;
+        e->net_shape.channels = shape_only->channels;
+        e->net_shape.P = shape_only->policy_channels;
+        e->net_shape.V = shape_only->value_channels;
+        e->net_shape.act = shape_only->activation;
+        e->se_sizes.assign(shape_only->se_sizes, shape_only->se_sizes + shape_only->blocks);
+        const int C = e->net_shape.channels, PV = e->net_shape.P + e->net_shape.V;
+        if (C < 16 || C > 256 || C % 16 || (C > 128 && C % 32) || PV % 4 || PV > 64 || e->net_shape.input_channels != SB_INPUT_CHANNELS)
+            return Fail(nullptr, SB_ERR_INVALID, "unsupported network shape");
+    }
+    {
+        const int PV = e->net_shape.P + e->net_shape.V;
+        if (PV != 16 && PV != 32 && PV != 48 && PV != 64)
+            return Fail(nullptr, SB_ERR_INVALID, "policy+value head channels must sum to 16, 32, 48 or 64");
+        if (e->net_shape.channels % 8) return Fail(nullptr, SB_ERR_INVALID, "channels must be a multiple of 8");
+    }
+    e->layout = ComputeLayout(e->net_shape.blocks, e->net_shape.channels, e->net_shape.P, e->net_shape.V, e->se_sizes);
+    try {
+        std::vector<uint8_t> blob;
+        if (net) blob = PackBlob(*net, e->layout);
+        e->replicas.resize(gpus.size());
+        for (size_t i = 0; i < gpus.size(); ++i) {
+            e->replicas[i].device = gpus[i];
+            BuildReplica(e.get(), e->replicas[i], net ? &blob : nullptr);
+        }
+        e->weights_ready = net != nullptr;
+        Configure(e.get(), board, max_batch);
+    } catch (const CudaError& ce) {
+        for (Replica& r : e->replicas) DestroyReplica(r);
+        return Fail(nullptr, SB_ERR_CUDA, ce.msg);
+    }
+    *out = e.release();
+    return SB_OK;
+}
+
+static int SubmitImpl(sb_engine* e, int gpu, int slot, int n, const float* planes, long long stride,
+                      const float* const* plane_ptrs, const int* sizes, const int* offsets) {
+    if (!e) return SB_ERR_INVALID;
+    if (gpu < 0 || gpu >= (int)e->replicas.size()) return Fail(e, SB_ERR_INVALID, "gpu index out of range");
+    if (slot < 0 || slot >= e->n_slots) return Fail(e, SB_ERR_INVALID, "slot index out of range");
+    if (n < 1 || n > e->max_batch) return Fail(e, SB_ERR_INVALID, "batch size out of range [1, max_batch]");
+    if ((!planes && !plane_ptrs) || !sizes || !offsets) return Fail(e, SB_ERR_INVALID, "null input pointer");
+    if (!e->weights_ready) return Fail(e, SB_ERR_STATE, "weights have not been loaded");
+    Replica& r = e->replicas[gpu];
+    Slot& s = r.slots[slot];
+    if (s.busy) return Fail(e, SB_ERR_STATE, "slot is busy: call sb_wait first");
+    for (int i = 0; i < n; ++i) {
+        if (sizes[i] < 2 || sizes[i] > e->geom.N) return Fail(e, SB_ERR_INVALID, "board size of a sample exceeds the NN canvas");
+        if (offsets[i] < 0 || offsets[i] > 4) return Fail(e, SB_ERR_INVALID, "policy offset must be in [0, 4]");
+    }
+    try {
+        SB_CUDA(cudaSetDevice(r.device));
+        for (int i = 0; i < n; ++i) {
+            s.h_meta[i] = sizes[i];
+            s.h_meta[e->max_batch + i] = offsets[i];
+            s.sizes[i] = sizes[i];
+            s.offsets[i] = offsets[i];
+        }
+        SB_CUDA(cudaMemcpyAsync(s.d_meta, s.h_meta, (size_t)2 * e->max_batch * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        bool direct = false;
+        if (planes) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, planes) == cudaSuccess && attr.type == cudaMemoryTypeHost) direct = true;
+            cudaGetLastError();
+        }
+        if (direct) {
+            const size_t width = (size_t)std::min<long long>(stride, SB_PLANE_FLOATS) * sizeof(float);
+            SB_CUDA(cudaMemcpy2DAsync(s.d_in, (size_t)SB_PLANE_FLOATS * sizeof(float), planes, (size_t)stride * sizeof(float),
+                                      width, n, cudaMemcpyHostToDevice, s.stream));
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const float* src = plane_ptrs ? plane_ptrs[i] : planes + (size_t)i * stride;
+                std::memcpy(s.h_in + (size_t)i * SB_PLANE_FLOATS, src, (size_t)SB_INPUT_CHANNELS * sizes[i] * sizes[i] * sizeof(float));
+            }
+            SB_CUDA(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)n * SB_PLANE_FLOATS * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        }
+        s.n = n;
+        EnqueueForward(e, r, s, n);
+        SB_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * kOutFloats * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        s.busy = true;
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    return SB_OK;
+}
+
+static int WaitImpl(sb_engine* e, int gpu, int slot, sb_output* out) {
+    if (!e) return SB_ERR_INVALID;
+    if (gpu < 0 || gpu >= (int)e->replicas.size()) return Fail(e, SB_ERR_INVALID, "gpu index out of range");
+    if (slot < 0 || slot >= e->n_slots) return Fail(e, SB_ERR_INVALID, "slot index out of range");
+    Replica& r = e->replicas[gpu];
+    Slot& s = r.slots[slot];
+    if (!s.busy) return Fail(e, SB_ERR_STATE, "slot is idle: nothing was submitted");
+    try {
+        SB_CUDA(cudaSetDevice(r.device));
+        s.busy = false;
+        CheckSlotError(s, cudaStreamSynchronize(s.stream), "forward");
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    if (out) {
+        for (int i = 0; i < s.n; ++i) {
+            const float* src = s.h_out + (size_t)i * kOutFloats;
+            sb_output& o = out[i];
+            std::memcpy(o.probabilities, src, sizeof(float) * SB_MAX_INTERSECTIONS);
+            std::memcpy(o.ownership, src + SB_MAX_INTERSECTIONS, sizeof(float) * SB_MAX_INTERSECTIONS);
+            const float* m = src + 2 * SB_MAX_INTERSECTIONS;
+            o.pass_probability = m[0];
+            o.wdl[0] = m[1];
+            o.wdl[1] = m[2];
+            o.wdl[2] = m[3];
+            o.stm_winrate = m[4];
+            o.final_score = m[5];
+            o.q_error = m[6];
+            o.score_error = m[7];
+            o.board_size = s.sizes[i];
+            o.offset = s.offsets[i];
+            o.fp16 = e->precision == SB_PRECISION_FP16 ? 1 : 0;
+        }
+    }
+    return SB_OK;
+}
+
+}  // namespace sb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int sb_create(sb_engine** out, const sb_net_desc* desc, const sb_weights* w, const int* gpu_ids, int n_gpus,
+              int board_size, int max_batch, int precision) {
+    if (!desc) return Fail(nullptr, SB_ERR_INVALID, "null net description");
+    if (!w) {
+        if (desc->blocks < 0 || (desc->blocks > 0 && !desc->se_sizes)) return Fail(nullptr, SB_ERR_INVALID, "bad block count / se_sizes");
+        return CreateImpl(out, nullptr, desc, gpu_ids, n_gpus, board_size, max_batch, precision);
+    }
+    HostNet net;
+    std::string err;
+    if (!NetFromAbi(desc, w, net, err)) return Fail(nullptr, SB_ERR_INVALID, err);
+    return CreateImpl(out, &net, nullptr, gpu_ids, n_gpus, board_size, max_batch, precision);
+}
+
+int sb_create_from_file(sb_engine** out, const char* weights_path, const int* gpu_ids, int n_gpus, int board_size,
+                        int max_batch, int precision) {
+    if (!weights_path) return Fail(nullptr, SB_ERR_INVALID, "null weights path");
+    HostNet net;
+    std::string err;
+    if (!LoadWeightsFile(weights_path, net, err)) return Fail(nullptr, SB_ERR_IO, err);
+    return CreateImpl(out, &net, nullptr, gpu_ids, n_gpus, board_size, max_batch, precision);
+}
+
+int sb_reconfigure(sb_engine* e, int board_size, int max_batch) {
+    if (!e) return SB_ERR_INVALID;
+    // CudaForwardPipe::Construct semantics (cuda_forward_pipe.cc:56-77): non-positive values keep the
+    // current setting; no rebuild if the board is unchanged and the batch fits.
+    const int board = board_size > 0 ? board_size : e->geom.N;
+    const int batch = max_batch > 0 ? max_batch : e->max_batch;
+    if (board < 2 || board > SB_MAX_BOARD_SIZE) return Fail(e, SB_ERR_INVALID, "NN board size should be in [2, 19]");
+    if (board == e->geom.N && batch <= e->max_batch) return SB_OK;
+    for (Replica& r : e->replicas)
+        for (Slot& s : r.slots)
+            if (s.busy) return Fail(e, SB_ERR_STATE, "cannot reconfigure while a batch is in flight");
+    try {
+        Configure(e, board, std::max(batch, board == e->geom.N ? e->max_batch : batch));
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    return SB_OK;
+}
+
+static int ReloadImpl(sb_engine* e, HostNet& net) {
+    if (net.blocks != e->net_shape.blocks || net.channels != e->net_shape.channels || net.P != e->net_shape.P ||
+        net.V != e->net_shape.V || net.se_sizes() != e->se_sizes)
+        return Fail(e, SB_ERR_INVALID, "reload requires the same architecture; destroy and create for a new one");
+    try {
+        e->net_shape.act = net.act;
+        e->net_shape.version = net.version;
+        std::vector<uint8_t> blob = PackBlob(net, e->layout);
+        for (Replica& r : e->replicas) {
+            SB_CUDA(cudaSetDevice(r.device));
+            SB_CUDA(cudaDeviceSynchronize());
+            BuildReplica(e, r, &blob);
+        }
+        e->weights_ready = true;
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    return SB_OK;
+}
+
+int sb_reload_weights(sb_engine* e, const sb_net_desc* desc, const sb_weights* w) {
+    if (!e) return SB_ERR_INVALID;
+    HostNet net;
+    std::string err;
+    if (!NetFromAbi(desc, w, net, err)) return Fail(e, SB_ERR_INVALID, err);
+    return ReloadImpl(e, net);
+}
+
+int sb_reload_weights_from_file(sb_engine* e, const char* weights_path) {
+    if (!e || !weights_path) return SB_ERR_INVALID;
+    HostNet net;
+    std::string err;
+    if (!LoadWeightsFile(weights_path, net, err)) return Fail(e, SB_ERR_IO, err);
+    return ReloadImpl(e, net);
+}
+
+void sb_destroy(sb_engine* e) {
+    if (!e) return;
+    for (Replica& r : e->replicas) {
+        if (r.device >= 0) {
+            cudaSetDevice(r.device);
+            cudaDeviceSynchronize();
+        }
+        DestroyReplica(r);
+    }
+    delete e;
+}
+
+const char* sb_last_error(const sb_engine* e) { return e ? e->last_error.c_str() : g_create_error.c_str(); }
+int sb_num_gpus(const sb_engine* e) { return e ? (int)e->replicas.size() : 0; }
+int sb_num_slots(const sb_engine* e) { return e ? e->n_slots : 0; }
+int sb_max_batch(const sb_engine* e) { return e ? e->max_batch : 0; }
+int sb_board_size(const sb_engine* e) { return e ? e->geom.N : 0; }
+
+int sb_get_net_desc(const sb_engine* e, sb_net_desc* d, int* se_sizes, int se_capacity) {
+    if (!e || !d) return SB_ERR_INVALID;
+    d->version = e->net_shape.version;
+    d->input_channels = e->net_shape.input_channels;
+    d->blocks = e->net_shape.blocks;
+    d->channels = e->net_shape.channels;
+    d->policy_channels = e->net_shape.P;
+    d->value_channels = e->net_shape.V;
+    d->activation = e->net_shape.act;
+    d->se_sizes = se_sizes;
+    if (se_sizes) {
+        if (se_capacity < e->net_shape.blocks) return SB_ERR_INVALID;
+        for (int b = 0; b < e->net_shape.blocks; ++b) se_sizes[b] = e->se_sizes[b];
+    }
+    return SB_OK;
+}
+
+int sb_forward_batch(sb_engine* e, int gpu, int n, const float* const* planes, const int* board_sizes,
+                     const int* policy_offsets, sb_output* out) {
+    int rc = SubmitImpl(e, gpu, 0, n, nullptr, 0, planes, board_sizes, policy_offsets);
+    if (rc) return rc;
+    return WaitImpl(e, gpu, 0, out);
+}
+
+int sb_submit(sb_engine* e, int gpu, int slot, int n, const float* planes, long long plane_stride,
+              const int* board_sizes, const int* policy_offsets) {
+    if (plane_stride <= 0) return Fail(e, SB_ERR_INVALID, "plane_stride must be positive");
+    return SubmitImpl(e, gpu, slot, n, planes, plane_stride, nullptr, board_sizes, policy_offsets);
+}
+
+int sb_wait(sb_engine* e, int gpu, int slot, sb_output* out) { return WaitImpl(e, gpu, slot, out); }
+
+void* sb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void sb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int sb_weights_blob(sb_engine* e, int gpu, void** device_ptr, size_t* bytes) {
+    if (!e || gpu < 0 || gpu >= (int)e->replicas.size() || !device_ptr || !bytes) return SB_ERR_INVALID;
+    *device_ptr = e->replicas[gpu].blob;
+    *bytes = e->layout.bytes;
+    return SB_OK;
+}
+
+static int BlobCopy(sb_engine* e, int gpu, void* dst, const void* src, size_t bytes, bool import) {
+    if (!e || gpu < 0 || gpu >= (int)e->replicas.size() || !dst || !src) return SB_ERR_INVALID;
+    if (bytes != e->layout.bytes) return Fail(e, SB_ERR_INVALID, "blob size mismatch: expected " + std::to_string(e->layout.bytes));
+    try {
+        SB_CUDA(cudaSetDevice(e->replicas[gpu].device));
+        SB_CUDA(cudaDeviceSynchronize());
+        SB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+        SB_CUDA(cudaDeviceSynchronize());
+        if (import) e->weights_ready = true;
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    return SB_OK;
+}
+
+int sb_weights_export(sb_engine* e, int gpu, void* device_dst, size_t bytes) {
+    if (!e || gpu < 0 || gpu >= (int)e->replicas.size()) return SB_ERR_INVALID;
+    return BlobCopy(e, gpu, device_dst, e->replicas[gpu].blob, bytes, false);
+}
+
+int sb_weights_import(sb_engine* e, int gpu, const void* device_src, size_t bytes) {
+    if (!e || gpu < 0 || gpu >= (int)e->replicas.size()) return SB_ERR_INVALID;
+    return BlobCopy(e, gpu, e->replicas[gpu].blob, device_src, bytes, true);
+}
+
+uint64_t sb_weights_checksum(sb_engine* e, int gpu) {
+    if (!e || gpu < 0 || gpu >= (int)e->replicas.size()) return 0;
+    std::vector<uint8_t> host(e->layout.bytes);
+    cudaSetDevice(e->replicas[gpu].device);
+    if (cudaMemcpy(host.data(), e->replicas[gpu].blob, host.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    uint64_t h = 1469598103934665603ull;
+    for (uint8_t b : host) {
+        h ^= b;
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+int sb_time_forward(sb_engine* e, int gpu, int slot, int iters, int flush_l2, float* ms_each, float* conv_ms,
+                    int* conv_launches) {
+    if (!e || gpu < 0 || gpu >= (int)e->replicas.size() || slot < 0 || slot >= e->n_slots || iters < 0) return SB_ERR_INVALID;
+    Replica& r = e->replicas[gpu];
+    Slot& s = r.slots[slot];
+    if (s.busy) return Fail(e, SB_ERR_STATE, "slot is busy");
+    if (s.n < 1) return Fail(e, SB_ERR_STATE, "no batch has been uploaded to this slot yet");
+    try {
+        SB_CUDA(cudaSetDevice(r.device));
+        if (flush_l2 && !r.flush_buf) {
+            r.flush_bytes = (size_t)256 << 20;   // > 126 MB L2
+            SB_CUDA(cudaMalloc(&r.flush_buf, r.flush_bytes));
+        }
+        for (int i = 0; i < iters; ++i) {
+            if (flush_l2) SB_CUDA(cudaMemsetAsync(r.flush_buf, i & 0xff, r.flush_bytes, s.stream));
+            SB_CUDA(cudaEventRecord(s.ev_a, s.stream));
+            EnqueueForward(e, r, s, s.n);
+            SB_CUDA(cudaEventRecord(s.ev_b, s.stream));
+            CheckSlotError(s, cudaEventSynchronize(s.ev_b), "timed forward");
+            float ms = 0.f;
+            SB_CUDA(cudaEventElapsedTime(&ms, s.ev_a, s.ev_b));
+            if (ms_each) ms_each[i] = ms;
+        }
+        if (conv_ms || conv_launches) {
+            ConvTimer tm;
+            tm.on = true;
+            EnqueueForward(e, r, s, s.n, &tm);
+            CheckSlotError(s, cudaStreamSynchronize(s.stream), "profiled forward");
+            float total = 0.f;
+            for (size_t i = 0; i + 1 < tm.ev.size(); i += 2) {
+                float ms = 0.f;
+                SB_CUDA(cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]));
+                total += ms;
+            }
+            if (conv_ms) *conv_ms = total;
+            if (conv_launches) *conv_launches = (int)(tm.ev.size() / 2);
+            for (cudaEvent_t ev : tm.ev) cudaEventDestroy(ev);
+        }
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    return SB_OK;
+}
+
+long long sb_launch_count(const sb_engine* e) { return e ? e->launches.load() : 0; }
+
+int sb_debug_read_trunk(sb_engine* e, int gpu, int slot, int sample, float* out) {
+    if (!e || gpu < 0 || gpu >= (int)e->replicas.size() || slot < 0 || slot >= e->n_slots || !out) return SB_ERR_INVALID;
+    Replica& r = e->replicas[gpu];
+    Slot& s = r.slots[slot];
+    if (!s.trunk || sample < 0 || sample >= s.n) return Fail(e, SB_ERR_STATE, "no forward has run on this slot / bad sample");
+    try {
+        SB_CUDA(cudaSetDevice(r.device));
+        SB_CUDA(cudaStreamSynchronize(s.stream));
+        const Geom g = e->geom;
+        const int C = e->net_shape.channels, pitch = s.trunk->pitch, bs = s.sizes[sample];
+        std::vector<__half> hi((size_t)g.SS * pitch), lo((size_t)g.SS * pitch);
+        const size_t off = (size_t)g.row(sample, 0, 0) * pitch;
+        SB_CUDA(cudaMemcpy(hi.data(), s.trunk->hi + off, hi.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+        SB_CUDA(cudaMemcpy(lo.data(), s.trunk->lo + off, lo.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+        const bool split = Split(e);
+        for (int c = 0; c < C; ++c)
+            for (int y = 0; y < bs; ++y)
+                for (int x = 0; x < bs; ++x) {
+                    const size_t i = (size_t)(y * g.P + x) * pitch + c;
+                    out[(size_t)c * bs * bs + y * bs + x] = __half2float(hi[i]) + (split ? __half2float(lo[i]) : 0.f);
+                }
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    return SB_OK;
+}
+
+int sb_set_option(sb_engine* e, const char* key, int value) {
+    if (!e || !key) return SB_ERR_INVALID;
+    if (!std::strcmp(key, "bo_mode")) {
+        e->bo_mode = value ? 1 : 0;
+        return SB_OK;
+    }
+    return Fail(e, SB_ERR_INVALID, std::string("unknown option ") + key);
+}
+
+}  // extern "C"

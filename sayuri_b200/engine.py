@@ -1,0 +1,292 @@
+"""ctypes host mirror of the C ABI (include/sayuri_b200.h) — what tests/ and bench.py drive.
+
+The class mirrors the reference plugin interface for this path,
+    NetworkForwardPipe / BatchForwardPipe   /root/reference/src/neural/network_basic.h:132-161,
+                                            /root/reference/src/neural/batch_forward_pipe.h:13-62
+    CudaForwardPipe                         /root/reference/src/neural/cuda/cuda_forward_pipe.h:20-36
+(Initialize / Construct / Forward / BatchForward / Release / Destroy / Valid / GetNumWorkers), with the
+same argument meaning and error behaviour (errors raise RuntimeError, as the C++ shim throws
+std::runtime_error).  There is no CPU fallback: if libsayuri_b200.so is missing, or no B200 is present,
+construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsayuri_b200.so")
+
+MAX_INTERSECTIONS = 361
+INPUT_CHANNELS = 43
+PLANE_FLOATS = INPUT_CHANNELS * MAX_INTERSECTIONS
+
+PRECISION_FP32_SPLIT = 0
+PRECISION_FP16 = 1
+PRECISION_SIMT_DEBUG = 2
+
+_F = ctypes.POINTER(ctypes.c_float)
+_I = ctypes.POINTER(ctypes.c_int)
+
+
+class SbNetDesc(ctypes.Structure):
+    _fields_ = [("version", ctypes.c_int), ("input_channels", ctypes.c_int), ("blocks", ctypes.c_int),
+                ("channels", ctypes.c_int), ("policy_channels", ctypes.c_int), ("value_channels", ctypes.c_int),
+                ("activation", ctypes.c_int), ("se_sizes", _I)]
+
+
+class SbTensor(ctypes.Structure):
+    _fields_ = [("data", _F), ("count", ctypes.c_longlong)]
+
+
+class SbWeights(ctypes.Structure):
+    _fields_ = [("tensors", ctypes.POINTER(SbTensor)), ("n_tensors", ctypes.c_int)]
+
+
+class SbOutput(ctypes.Structure):
+    _fields_ = [("probabilities", ctypes.c_float * MAX_INTERSECTIONS),
+                ("ownership", ctypes.c_float * MAX_INTERSECTIONS),
+                ("pass_probability", ctypes.c_float), ("wdl", ctypes.c_float * 3),
+                ("stm_winrate", ctypes.c_float), ("final_score", ctypes.c_float), ("q_error", ctypes.c_float),
+                ("score_error", ctypes.c_float), ("board_size", ctypes.c_int), ("offset", ctypes.c_int),
+                ("fp16", ctypes.c_int)]
+
+
+OUTPUT_DTYPE = np.dtype([("probabilities", np.float32, MAX_INTERSECTIONS), ("ownership", np.float32, MAX_INTERSECTIONS),
+                         ("pass_probability", np.float32), ("wdl", np.float32, 3), ("stm_winrate", np.float32),
+                         ("final_score", np.float32), ("q_error", np.float32), ("score_error", np.float32),
+                         ("board_size", np.int32), ("offset", np.int32), ("fp16", np.int32)])
+assert OUTPUT_DTYPE.itemsize == ctypes.sizeof(SbOutput)
+
+# Every symbol include/sayuri_b200.h declares (checked by tests/test_abi.py).
+ABI_SYMBOLS = [
+    "sb_create", "sb_create_from_file", "sb_reconfigure", "sb_reload_weights", "sb_reload_weights_from_file",
+    "sb_destroy", "sb_last_error", "sb_num_gpus", "sb_num_slots", "sb_max_batch", "sb_board_size", "sb_get_net_desc",
+    "sb_forward_batch", "sb_submit", "sb_wait", "sb_host_alloc", "sb_host_free", "sb_weights_blob",
+    "sb_weights_export", "sb_weights_import",
+    "sb_weights_checksum", "sb_time_forward", "sb_launch_count", "sb_debug_read_trunk", "sb_set_option",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libsayuri_b200.so (built in-tree by __graft_entry__.build / sayuri_b200/csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("sayuri_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp = ctypes.c_void_p
+    lib.sb_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(SbNetDesc), ctypes.POINTER(SbWeights), _I, ctypes.c_int,
+                              ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.sb_create_from_file.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, _I, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.sb_reconfigure.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.sb_reload_weights.argtypes = [vp, ctypes.POINTER(SbNetDesc), ctypes.POINTER(SbWeights)]
+    lib.sb_reload_weights_from_file.argtypes = [vp, ctypes.c_char_p]
+    lib.sb_destroy.argtypes = [vp]
+    lib.sb_destroy.restype = None
+    lib.sb_last_error.argtypes = [vp]
+    lib.sb_last_error.restype = ctypes.c_char_p
+    for name in ("sb_num_gpus", "sb_num_slots", "sb_max_batch", "sb_board_size"):
+        getattr(lib, name).argtypes = [vp]
+    lib.sb_get_net_desc.argtypes = [vp, ctypes.POINTER(SbNetDesc), _I, ctypes.c_int]
+    lib.sb_forward_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_F), _I, _I, ctypes.c_void_p]
+    lib.sb_submit.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, _I, _I]
+    lib.sb_wait.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.sb_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.sb_host_alloc.restype = ctypes.c_void_p
+    lib.sb_host_free.argtypes = [ctypes.c_void_p]
+    lib.sb_host_free.restype = None
+    lib.sb_weights_blob.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
+    lib.sb_weights_export.argtypes = [vp, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+    lib.sb_weights_import.argtypes = [vp, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+    lib.sb_weights_checksum.argtypes = [vp, ctypes.c_int]
+    lib.sb_weights_checksum.restype = ctypes.c_uint64
+    lib.sb_time_forward.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F, _F, _I]
+    lib.sb_launch_count.argtypes = [vp]
+    lib.sb_launch_count.restype = ctypes.c_longlong
+    lib.sb_debug_read_trunk.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F]
+    lib.sb_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    _lib = lib
+    return lib
+
+
+class PinnedArray:
+    """float32 numpy view over pinned host memory from sb_host_alloc (DMA'd in place by sb_submit)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        lib = load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib.sb_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise RuntimeError("sb_host_alloc(%d) failed" % self.nbytes)
+        buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load_library().sb_host_free(self.ptr)
+            self.ptr = None
+
+
+class B200ForwardPipe:
+    """Drop-in for the backend behind NetworkForwardPipe (see module docstring)."""
+
+    def __init__(self):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p(None)
+
+    # ---- NetworkForwardPipe::Initialize / CudaForwardPipe::Construct ----------------------------
+    def initialize(self, weights_path, board_size=19, batch_size=256, gpus=None, precision=PRECISION_FP32_SPLIT):
+        self.destroy()
+        ids = list(gpus) if gpus else []
+        arr = (ctypes.c_int * max(len(ids), 1))(*ids)
+        rc = self._lib.sb_create_from_file(ctypes.byref(self._h), str(weights_path).encode(), arr, len(ids), board_size,
+                                           batch_size, precision)
+        if rc:
+            self._h = ctypes.c_void_p(None)
+            raise RuntimeError(self._lib.sb_last_error(None).decode())
+        return self
+
+    def initialize_from_tensors(self, desc, tensors, board_size=19, batch_size=256, gpus=None,
+                                precision=PRECISION_FP32_SPLIT):
+        """desc: dict(version, blocks, channels, P, V, activation, se_sizes); tensors: list of float32 arrays in
+        loader order with BN folded, or None to leave the weight blob to a later broadcast (weights_blob())."""
+        self.destroy()
+        se = (ctypes.c_int * max(len(desc["se_sizes"]), 1))(*desc["se_sizes"])
+        d = SbNetDesc(desc.get("version", 5), INPUT_CHANNELS, desc["blocks"], desc["channels"], desc["P"], desc["V"],
+                      desc["activation"], se)
+        wptr = None
+        keep = []
+        if tensors is not None:
+            ts = (SbTensor * len(tensors))()
+            for i, t in enumerate(tensors):
+                a = np.ascontiguousarray(t, dtype=np.float32).ravel()
+                keep.append(a)
+                ts[i].data = a.ctypes.data_as(_F)
+                ts[i].count = a.size
+            w = SbWeights(ts, len(tensors))
+            wptr = ctypes.byref(w)
+        ids = list(gpus) if gpus else []
+        arr = (ctypes.c_int * max(len(ids), 1))(*ids)
+        rc = self._lib.sb_create(ctypes.byref(self._h), ctypes.byref(d), wptr, arr, len(ids), board_size, batch_size, precision)
+        if rc:
+            self._h = ctypes.c_void_p(None)
+            raise RuntimeError(self._lib.sb_last_error(None).decode())
+        return self
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError(self._lib.sb_last_error(self._h).decode())
+
+    def construct(self, board_size=-1, batch_size=-1):
+        """CudaForwardPipe::Construct(option, nullptr): non-positive keeps the current value."""
+        self._check(self._lib.sb_reconfigure(self._h, board_size, batch_size))
+
+    def reload(self, weights_path):
+        self._check(self._lib.sb_reload_weights_from_file(self._h, str(weights_path).encode()))
+
+    def valid(self):
+        return bool(self._h)
+
+    def get_num_workers(self):
+        return self._lib.sb_num_gpus(self._h)
+
+    num_slots = property(lambda self: self._lib.sb_num_slots(self._h))
+    max_batch = property(lambda self: self._lib.sb_max_batch(self._h))
+    board_size = property(lambda self: self._lib.sb_board_size(self._h))
+
+    def net_desc(self):
+        d = SbNetDesc()
+        se = (ctypes.c_int * 1024)()
+        self._check(self._lib.sb_get_net_desc(self._h, ctypes.byref(d), se, 1024))
+        return dict(version=d.version, blocks=d.blocks, channels=d.channels, P=d.policy_channels, V=d.value_channels,
+                    activation=d.activation, se_sizes=[se[i] for i in range(d.blocks)])
+
+    def release(self):
+        self.destroy()
+
+    def destroy(self):
+        if getattr(self, "_h", None):
+            self._lib.sb_destroy(self._h)
+            self._h = ctypes.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # ---- BatchForwardPipe::BatchForward -------------------------------------------------------
+    def batch_forward(self, gpu, planes_list, board_sizes, offsets=None):
+        """planes_list[i]: float32 array with 43*bs_i*bs_i values (InputData.planes at native size).
+        Returns a structured array of OutputResult mirrors."""
+        n = len(planes_list)
+        offsets = [0] * n if offsets is None else list(offsets)
+        keep = [np.ascontiguousarray(p, dtype=np.float32).ravel() for p in planes_list]
+        for a, bs in zip(keep, board_sizes):
+            if a.size < INPUT_CHANNELS * bs * bs:
+                raise ValueError("planes array smaller than 43*bs*bs")
+        ptrs = (_F * n)(*[a.ctypes.data_as(_F) for a in keep])
+        sizes = (ctypes.c_int * n)(*[int(b) for b in board_sizes])
+        offs = (ctypes.c_int * n)(*[int(o) for o in offsets])
+        out = np.zeros(n, dtype=OUTPUT_DTYPE)
+        self._check(self._lib.sb_forward_batch(self._h, gpu, n, ptrs, sizes, offs, out.ctypes.data))
+        return out
+
+    def forward(self, planes, board_size, offset=0, gpu=0):
+        """NetworkForwardPipe::Forward for one InputData."""
+        return self.batch_forward(gpu, [planes], [board_size], [offset])[0]
+
+    def submit(self, gpu, slot, planes, board_sizes, offsets, plane_stride=PLANE_FLOATS):
+        """planes: contiguous float32 array (ideally a PinnedArray.array) of n records plane_stride apart."""
+        n = len(board_sizes)
+        sizes = np.ascontiguousarray(board_sizes, dtype=np.int32)
+        offs = np.ascontiguousarray(offsets, dtype=np.int32)
+        self._check(self._lib.sb_submit(self._h, gpu, slot, n, planes.ctypes.data, plane_stride,
+                                        sizes.ctypes.data_as(_I), offs.ctypes.data_as(_I)))
+
+    def wait(self, gpu, slot, out=None):
+        self._check(self._lib.sb_wait(self._h, gpu, slot, out.ctypes.data if out is not None else None))
+        return out
+
+    # ---- weights blob / measurement / debug ---------------------------------------------------
+    def weights_blob(self, gpu=0):
+        p = ctypes.c_void_p()
+        n = ctypes.c_size_t()
+        self._check(self._lib.sb_weights_blob(self._h, gpu, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def weights_export(self, device_ptr, nbytes, gpu=0):
+        self._check(self._lib.sb_weights_export(self._h, gpu, ctypes.c_void_p(device_ptr), nbytes))
+
+    def weights_import(self, device_ptr, nbytes, gpu=0):
+        self._check(self._lib.sb_weights_import(self._h, gpu, ctypes.c_void_p(device_ptr), nbytes))
+
+    def weights_checksum(self, gpu=0):
+        return int(self._lib.sb_weights_checksum(self._h, gpu))
+
+    def time_forward(self, gpu, slot, iters, flush_l2=True, profile_conv=False):
+        ms = np.zeros(max(iters, 1), dtype=np.float32)
+        conv_ms = ctypes.c_float(0)
+        conv_n = ctypes.c_int(0)
+        self._check(self._lib.sb_time_forward(self._h, gpu, slot, iters, int(flush_l2), ms.ctypes.data_as(_F),
+                                              ctypes.byref(conv_ms) if profile_conv else None,
+                                              ctypes.byref(conv_n) if profile_conv else None))
+        return ms[:iters], conv_ms.value, conv_n.value
+
+    def launch_count(self):
+        return int(self._lib.sb_launch_count(self._h))
+
+    def debug_read_trunk(self, gpu, slot, sample, board_size):
+        c = self.net_desc()["channels"]
+        out = np.zeros(c * board_size * board_size, dtype=np.float32)
+        self._check(self._lib.sb_debug_read_trunk(self._h, gpu, slot, sample, out.ctypes.data_as(_F)))
+        return out.reshape(c, board_size * board_size)
+
+    def set_option(self, key, value):
+        self._check(self._lib.sb_set_option(self._h, key.encode(), int(value)))

@@ -1,0 +1,285 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle and the committed
+golden vectors of the reference.  Needs a B200: run with `pytest -m gpu`.
+
+Tolerances (written here, per BASELINE.json's north star):
+  * default precision (fp16 hi/lo split, fp32 accumulate): 1e-4 absolute on every raw output
+    (policy logits, ownership, pass, wdl, stm, score, errors) vs the reference Eigen forward;
+  * index work (canvas placement / crop, policy-plane select, zero fill): bit-exact;
+  * batch invariance: bit-exact (a position's result never depends on its batch neighbours);
+  * SB_PRECISION_FP16 (the reference's own --fp16 trade, SELF_CHECK tolerance 0.2 L2,
+    network.cc:333-359): 5e-2 absolute, reported not asserted tight.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-4
+SIZES = (9, 13, 19)
+
+
+def _misc(o):
+    return np.array([o["pass_probability"], *o["wdl"], o["stm_winrate"], o["final_score"], o["q_error"], o["score_error"]],
+                    dtype=np.float32)
+
+
+def _check(out, ref, bs, atol=ATOL):
+    s = bs * bs
+    np.testing.assert_allclose(out["probabilities"][:s], ref["prob"], rtol=0, atol=atol)
+    np.testing.assert_allclose(out["ownership"][:s], ref["own"], rtol=0, atol=atol)
+    np.testing.assert_allclose(_misc(out), ref["misc"], rtol=0, atol=atol)
+    assert not np.any(out["probabilities"][s:]) and not np.any(out["ownership"][s:])  # zero fill, exact
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from sayuri_b200 import engine
+    engine.load_library()   # raises if the CUDA library is missing: no fallback
+    return engine
+
+
+@pytest.fixture(scope="module")
+def golden_pipe(eng, golden_weights_bin):
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 16, gpus=[0])
+    yield pipe
+    pipe.destroy()
+
+
+def test_matches_reference_golden_vectors(golden_pipe, golden):
+    """Outputs of the UNMODIFIED reference (tests/golden/make_golden.py) for 9/13/19 boards, every policy offset."""
+    planes, sizes, offsets, refs = [], [], [], []
+    for bs in SIZES:
+        for i in range(2):
+            planes.append(golden["planes_%d" % bs][i].ravel())
+            sizes.append(bs)
+            offsets.append(int(golden["offset_%d_%d" % (bs, i)]))
+            v = golden["ref_%d_%d" % (bs, i)]
+            s = bs * bs
+            refs.append({"prob": v[:s], "own": v[s:2 * s], "misc": v[2 * s:]})
+    out = golden_pipe.batch_forward(0, planes, sizes, offsets)
+    for o, r, bs, off in zip(out, refs, sizes, offsets):
+        _check(o, r, bs)
+        assert o["board_size"] == bs and o["offset"] == off and o["fp16"] == 0
+
+
+def test_all_policy_planes_match_pytorch_reference(golden_pipe, golden):
+    """Policy-plane select (FillOutputs): plane k of the reference PyTorch forward for k = 0..4."""
+    bs = 19
+    x = golden["planes_19"][0].ravel()
+    out = golden_pipe.batch_forward(0, [x] * 5, [bs] * 5, list(range(5)))
+    for k in range(5):
+        np.testing.assert_allclose(out[k]["probabilities"], golden["torch_prob5_19"][0, k], rtol=0, atol=ATOL)
+        np.testing.assert_allclose(out[k]["pass_probability"], golden["torch_pass5_19"][0, k], rtol=0, atol=ATOL)
+        # everything that does not depend on the offset is bit-identical across the five copies
+        assert np.array_equal(out[k]["ownership"], out[0]["ownership"])
+        assert np.array_equal(out[k]["wdl"], out[0]["wdl"])
+
+
+def test_matches_reference_so_live_when_shipped(golden_pipe, golden_weights_bin, oracle_lib):
+    if not oracle_lib.Reference.available():
+        pytest.skip("oracle/_ref not shipped")
+    from sayuri_b200 import synth
+    ref = oracle_lib.Reference(golden_weights_bin, winograd=False)
+    sizes = [19, 9, 13, 19]
+    planes = [synth.synth_positions(1, bs, seed=900 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    out = golden_pipe.batch_forward(0, planes, sizes, [0, 1, 2, 3])
+    for i, bs in enumerate(sizes):
+        _check(out[i], ref.forward(planes[i], bs, offset=i), bs)
+
+
+def test_batch_invariance_and_canvas_index_work_bit_exact(golden_pipe):
+    """A position's outputs are bit-identical alone, duplicated, and buried in a mixed 9/13/19 batch at any slot:
+    canvas placement/crop and per-sample reductions do not depend on the neighbours."""
+    from sayuri_b200 import synth
+    probe = {bs: synth.synth_positions(1, bs, seed=77)[0].ravel() for bs in SIZES}
+    alone = {bs: golden_pipe.batch_forward(0, [probe[bs]], [bs], [2])[0] for bs in SIZES}
+    filler = [synth.synth_positions(1, bs, seed=500 + i)[0].ravel() for i, bs in enumerate((19, 9, 13, 19, 9, 13, 19, 19, 13))]
+    fsizes = [19, 9, 13, 19, 9, 13, 19, 19, 13]
+    for pos in (0, 4, 9):
+        for bs in SIZES:
+            planes = filler[:pos] + [probe[bs]] + filler[pos:]
+            sizes = fsizes[:pos] + [bs] + fsizes[pos:]
+            out = golden_pipe.batch_forward(0, planes, sizes, [2] * len(sizes))
+            for f in ("probabilities", "ownership", "pass_probability", "wdl", "stm_winrate", "final_score", "q_error", "score_error"):
+                assert np.array_equal(out[pos][f], alone[bs][f]), (pos, bs, f)
+
+
+def test_small_canvas_matches_large_canvas(eng, golden_weights_bin, oracle_lib):
+    """CudaForwardPipe::Construct on a board change: a 9x9 net canvas gives the same results as 9x9 on the 19x19 canvas."""
+    from sayuri_b200 import synth
+    orc = oracle_lib.Oracle(golden_weights_bin)
+    planes = [synth.synth_positions(1, 9, seed=300 + i)[0].ravel() for i in range(3)]
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 9, 4, gpus=[0])
+    try:
+        out9 = pipe.batch_forward(0, planes, [9] * 3, [0, 1, 4])
+        for i in range(3):
+            _check(out9[i], orc.forward(planes[i], 9, [0, 1, 4][i]), 9)
+        with pytest.raises(RuntimeError, match="exceeds the NN canvas"):
+            pipe.batch_forward(0, [synth.synth_positions(1, 13)[0].ravel()], [13], [0])
+        pipe.construct(board_size=19, batch_size=-1)   # Reconstruct, network.cc:494-498
+        assert pipe.board_size == 19
+        out19 = pipe.batch_forward(0, planes, [9] * 3, [0, 1, 4])
+        for i in range(3):
+            _check(out19[i], orc.forward(planes[i], 9, [0, 1, 4][i]), 9)
+        pipe.construct(batch_size=64)                   # grow the batch only
+        assert pipe.max_batch == 64 and pipe.board_size == 19
+        with pytest.raises(RuntimeError, match="batch size out of range"):
+            pipe.batch_forward(0, planes * 30, [9] * 90, [0] * 90)
+    finally:
+        pipe.destroy()
+
+
+@pytest.mark.parametrize("shape,stack", [
+    ((2, 64, 8, 8), ["ResidualBlock-SE", "ResidualBlock"]),
+    ((2, 96, 24, 24), ["ResidualBlock", "ResidualBlock-SE"]),
+    ((3, 128, 24, 24), ["ResidualBlock", "ResidualBlock", "ResidualBlock-SE"]),
+    ((2, 192, 32, 32), ["ResidualBlock", "ResidualBlock-SE"]),
+    ((2, 256, 32, 32), ["ResidualBlock-SE", "ResidualBlock"]),
+])
+def test_channel_widths_of_all_baseline_nets(eng, oracle_lib, shape, stack):
+    """Every tower width BASELINE.json names (96/128/192/256) through its own tile configuration, mixed board sizes."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_%dx%d.bin" % (shape[0], shape[1]))
+    synth.write_synth_net(path, shape, seed=shape[1], stack=stack)
+    orc = oracle_lib.Oracle(path)
+    sizes = [19, 13, 9, 19, 19, 9, 13]
+    planes = [synth.synth_positions(1, bs, seed=10 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    offsets = [i % 5 for i in range(len(sizes))]
+    pipe = eng.B200ForwardPipe().initialize(path, 19, 8, gpus=[0])
+    try:
+        out = pipe.batch_forward(0, planes, sizes, offsets)
+        for i, bs in enumerate(sizes):
+            _check(out[i], orc.forward(planes[i], bs, offsets[i]), bs)
+    finally:
+        pipe.destroy()
+
+
+@pytest.mark.parametrize("act", ["relu", "swish", "gelu", "hardswish", "elu", "selu", "identity"])
+def test_every_activation(eng, oracle_lib, act):
+    """activation.h:8-17,43-59."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_act_%s.bin" % act)
+    synth.write_synth_net(path, (2, 32, 8, 8), seed=3, activation=act, stack=["ResidualBlock-SE", "ResidualBlock"])
+    orc = oracle_lib.Oracle(path)
+    sizes = [19, 9]
+    planes = [synth.synth_positions(1, bs, seed=60 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    pipe = eng.B200ForwardPipe().initialize(path, 19, 4, gpus=[0])
+    try:
+        out = pipe.batch_forward(0, planes, sizes, [0, 3])
+        for i, bs in enumerate(sizes):
+            _check(out[i], orc.forward(planes[i], bs, [0, 3][i]), bs, atol=2e-4 if act in ("identity", "selu") else ATOL)
+    finally:
+        pipe.destroy()
+
+
+def test_tensor_core_kernel_agrees_with_simt_cross_check(eng, golden_weights_bin):
+    """conv3x3_tc vs conv3x3_simt (fp32 CUDA cores) on the same canvas buffers, trunk level."""
+    from sayuri_b200 import synth
+    sizes = [19, 13, 9, 19]
+    planes = [synth.synth_positions(1, bs, seed=700 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    trunks = {}
+    for prec in (eng.PRECISION_FP32_SPLIT, eng.PRECISION_SIMT_DEBUG):
+        pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 4, gpus=[0], precision=prec)
+        try:
+            pipe.batch_forward(0, planes, sizes, [0] * 4)
+            trunks[prec] = [pipe.debug_read_trunk(0, 0, i, bs) for i, bs in enumerate(sizes)]
+        finally:
+            pipe.destroy()
+    for a, b in zip(trunks[eng.PRECISION_FP32_SPLIT], trunks[eng.PRECISION_SIMT_DEBUG]):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_fp16_rung_is_close_and_flagged(eng, golden_weights_bin, oracle_lib):
+    from sayuri_b200 import synth
+    orc = oracle_lib.Oracle(golden_weights_bin)
+    sizes = [19, 9, 13]
+    planes = [synth.synth_positions(1, bs, seed=800 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 4, gpus=[0], precision=eng.PRECISION_FP16)
+    try:
+        out = pipe.batch_forward(0, planes, sizes, [0, 0, 0])
+        for i, bs in enumerate(sizes):
+            assert out[i]["fp16"] == 1
+            _check(out[i], orc.forward(planes[i], bs, 0), bs, atol=5e-2)
+    finally:
+        pipe.destroy()
+
+
+def test_async_pinned_submit_wait_equals_blocking_call(golden_pipe, eng):
+    from sayuri_b200 import synth
+    n = 6
+    sizes = [19] * n
+    x = synth.synth_positions(n, 19, seed=123).reshape(n, -1)
+    blocking = golden_pipe.batch_forward(0, list(x), sizes, [1] * n)
+    pinned = eng.PinnedArray((2, n, eng.PLANE_FLOATS))
+    try:
+        pinned.array[0] = x
+        pinned.array[1] = x[::-1]
+        outs = [np.zeros(n, dtype=eng.OUTPUT_DTYPE) for _ in range(2)]
+        golden_pipe.submit(0, 0, pinned.array[0], sizes, [1] * n)
+        golden_pipe.submit(0, 1, pinned.array[1], sizes, [1] * n)
+        with pytest.raises(RuntimeError, match="slot is busy"):
+            golden_pipe.submit(0, 1, pinned.array[1], sizes, [1] * n)
+        golden_pipe.wait(0, 0, outs[0])
+        golden_pipe.wait(0, 1, outs[1])
+        with pytest.raises(RuntimeError, match="slot is idle"):
+            golden_pipe.wait(0, 1, outs[1])
+        for i in range(n):
+            assert np.array_equal(outs[0][i]["probabilities"], blocking[i]["probabilities"])
+            assert np.array_equal(outs[1][n - 1 - i]["probabilities"], blocking[i]["probabilities"])
+            assert np.array_equal(outs[1][n - 1 - i]["ownership"], blocking[i]["ownership"])
+    finally:
+        pinned.free()
+
+
+def test_reload_weights_hot_swap(eng, oracle_lib):
+    from sayuri_b200 import synth
+    d = tempfile.gettempdir()
+    a, b = os.path.join(d, "sb_reload_a.bin"), os.path.join(d, "sb_reload_b.bin")
+    synth.write_synth_net(a, (2, 32, 8, 8), seed=1, stack=["ResidualBlock", "ResidualBlock-SE"])
+    synth.write_synth_net(b, (2, 32, 8, 8), seed=2, stack=["ResidualBlock", "ResidualBlock-SE"])
+    x = synth.synth_positions(1, 19, seed=5)[0].ravel()
+    pipe = eng.B200ForwardPipe().initialize(a, 19, 4, gpus=[0])
+    try:
+        ca = pipe.weights_checksum()
+        _check(pipe.forward(x, 19), oracle_lib.Oracle(a).forward(x, 19), 19)
+        pipe.reload(b)
+        assert pipe.weights_checksum() != ca
+        _check(pipe.forward(x, 19), oracle_lib.Oracle(b).forward(x, 19), 19)
+        c = os.path.join(d, "sb_reload_c.bin")
+        synth.write_synth_net(c, (3, 32, 8, 8), seed=2)
+        with pytest.raises(RuntimeError, match="same architecture"):
+            pipe.reload(c)
+    finally:
+        pipe.destroy()
+
+
+def test_full_size_config2_properties(eng, oracle_lib):
+    """BASELINE config 2 at full size (10bx128, 19x19, batch 256): size-independent properties plus a sampled
+    oracle comparison.  (i) duplicates inside the batch are bit-identical, (ii) a permutation of the batch
+    permutes the outputs bit-exactly, (iii) 6 sampled positions match the CPU oracle within 1e-4."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_10bx128.bin")
+    synth.write_synth_net(path, "10bx128", seed=20260417)
+    n = 256
+    x = synth.synth_positions(n, 19, seed=20260419).reshape(n, -1)
+    x[200] = x[3]
+    x[255] = x[3]
+    pipe = eng.B200ForwardPipe().initialize(path, 19, n, gpus=[0])
+    try:
+        out = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
+        for f in ("probabilities", "ownership", "wdl"):
+            assert np.array_equal(out[200][f], out[3][f]) and np.array_equal(out[255][f], out[3][f])
+        perm = np.random.default_rng(0).permutation(n)
+        outp = pipe.batch_forward(0, list(x[perm]), [19] * n, [0] * n)
+        assert np.array_equal(outp["probabilities"], out["probabilities"][perm])
+        assert np.array_equal(outp["ownership"], out["ownership"][perm])
+        assert np.array_equal(outp["pass_probability"], out["pass_probability"][perm])
+        orc = oracle_lib.Oracle(path)
+        for i in (0, 1, 100, 128, 254, 255):
+            _check(out[i], orc.forward(x[i], 19, 0), 19)
+        assert np.isfinite(out["probabilities"]).all()
+    finally:
+        pipe.destroy()
