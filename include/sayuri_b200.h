@@ -168,7 +168,11 @@ long long sb_launch_count(const sb_engine* e);  /* kernels launched by this engi
 /* ---- debugging / tests -------------------------------------------------------------------------- */
 /* Tower output of sample `sample` of the last batch on (gpu, slot) as fp32 NCHW [channels][n*n]. */
 int sb_debug_read_trunk(sb_engine* e, int gpu, int slot, int sample, float* out);
-/* Named integer knobs: "bo_mode" (UMMA descriptor base-offset mode 0/1). */
+/* Cycle counters of the LAST conv3x3 launch on (gpu, slot), 8 int64 per CTA: {mma loop total, wait for free TMEM,
+ * wait for activation slab, wait for weight stage, epilogue wait for accumulators, epilogue total, items, -}.
+ * Filled only while option "stats" = 1.  Returns the number of int64 written (<= capacity) or a negative status. */
+int sb_conv_stats(sb_engine* e, int gpu, int slot, long long* out, int capacity);
+/* Named integer knobs: "stats" (collect conv kernel cycle counters, default 0). */
 int sb_set_option(sb_engine* e, const char* key, int value);
 
 #ifdef __cplusplus

@@ -139,10 +139,11 @@ se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_
 
 // se_apply: x' = act(sigmoid(gamma) * u + beta + skip) on board cells, 0 elsewhere
 // (SEUnit::SEProcess, se_unit.cc:92-128; GPU twin se_scale_kernel cuda_kernels.cu:391-440).  In place on u.
+template <int ACT>
 __global__ void se_apply_kernel(__half* __restrict__ u_hi, __half* __restrict__ u_lo,
                                 const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, bool split,
                                 const uint8_t* __restrict__ mask, const float* __restrict__ gb, Geom g, int C,
-                                int pitch, int n_rows, int act) {
+                                int pitch, int n_rows) {
     const int groups = C >> 3;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = (int)(idx / groups), cg = (int)(idx - (size_t)r * groups);
@@ -157,7 +158,7 @@ __global__ void se_apply_kernel(__half* __restrict__ u_hi, __half* __restrict__ 
         load8(x_hi + off, x_lo + off, split, x);
         const float* ga = gb + (size_t)b * 2 * C + cg * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = activate(ga[i] * u[i] + ga[C + i] + x[i], act);
+        for (int i = 0; i < 8; ++i) o[i] = activate_t<ACT>(ga[i] * u[i] + ga[C + i] + x[i]);
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -170,11 +171,11 @@ __global__ void se_apply_kernel(__half* __restrict__ u_hi, __half* __restrict__ 
 //   pv[row][0:P]   = act(Wp x + bp)   (policy, blas_forward_pipe.cc:430-442)
 //   pv[row][P:P+V] = act(Wv x + bv)   (value,  blas_forward_pipe.cc:513-522)
 // fp32 out, zero on non-board rows.  One thread per canvas row; W^T [C][PV] broadcast from shared memory.
-template <int PV>
+template <int PV, int ACT>
 __global__ void __launch_bounds__(128)
 head_conv_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, bool split,
                  const uint8_t* __restrict__ mask, const float* __restrict__ wT, const float* __restrict__ bias,
-                 int C, int pitch, int n_rows, int act, float* __restrict__ pv) {
+                 int C, int pitch, int n_rows, float* __restrict__ pv) {
     extern __shared__ float sw[];   // [C][PV] + [PV]
     for (int i = threadIdx.x; i < C * PV; i += blockDim.x) sw[i] = wT[i];
     float* sb_ = sw + C * PV;
@@ -206,7 +207,7 @@ head_conv_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_l
             }
         }
 #pragma unroll
-        for (int j = 0; j < PV; ++j) acc[j] = activate(acc[j], act);
+        for (int j = 0; j < PV; ++j) acc[j] = activate_t<ACT>(acc[j]);
     } else {
 #pragma unroll
         for (int j = 0; j < PV; ++j) acc[j] = 0.f;

@@ -37,24 +37,60 @@ struct Geom {
 // ---- Activations: same ints and formulas as /root/reference/src/neural/activation.h:8-17,43-59 --
 enum Act : int { kIdentity = 0, kReLU = 1, kELU = 2, kSELU = 3, kGELU = 4, kMISH = 5, kSwish = 6, kHardSwish = 7 };
 
-__device__ __forceinline__ float activate(float x, int act) {
+// Compile-time activation: ONE formula is inlined per kernel instantiation (an 8-way runtime switch per
+// element made the conv epilogue 25K instructions long and instruction-fetch bound).
+// exp() goes through ex2.approx (rel. error ~2^-22) and the mish/swish quotients through rcp.approx: unbiased
+// ~1e-7 relative perturbations, far below the 1e-4 parity bar.
+__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * 1.4426950408889634f); }
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <int ACT>
+__device__ __forceinline__ float activate_t(float x) {
+    if (ACT == kReLU) return fmaxf(x, 0.f);
+    if (ACT == kELU) return x > 0.f ? x : (expf(x) - 1.f);
+    if (ACT == kSELU) return x > 0.f ? (1.05070098f * x) : (1.05070098f * 1.67326324f * (expf(x) - 1.0f));
+    if (ACT == kGELU) return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+    if (ACT == kMISH) {
+        // x * tanh(log(1 + e^x)) == x * n / (n + 2), n = e^x (e^x + 2): no cancellation, one ex2 + one rcp.
+        const float w = fast_exp(fminf(x, 20.f));
+        const float n = w * (w + 2.f);
+        return x * n * fast_rcp(n + 2.f);
+    }
+    if (ACT == kSwish) return x * fast_rcp(1.0f + fast_exp(-x));
+    if (ACT == kHardSwish) return x >= 3.f ? x : x <= -3.f ? 0.f : (x * (x + 3.0f) * (1.0f / 6.0f));
+    return x;
+}
+
+// Runtime-dispatched form for the tiny per-sample FC kernels (executed a handful of times per sample).
+__device__ __noinline__ float activate(float x, int act) {
     switch (act) {
-        case kReLU: return x > 0.f ? x : 0.f;
-        case kELU: return x > 0.f ? x : (expf(x) - 1.f);
-        case kSELU: return x > 0.f ? (1.05070098f * x) : (1.05070098f * 1.67326324f * (expf(x) - 1.0f));
-        case kGELU: return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
-        case kMISH: {
-            // x * tanh(log(1 + e^x)) == x * n / (n + 2), n = e^x (e^x + 2): no cancellation, one expf.
-            if (x > 20.f) return x;
-            const float w = expf(x);
-            const float n = w * (w + 2.f);
-            return x * (n / (n + 2.f));
-        }
-        case kSwish: return x / (1.0f + expf(-x));
-        case kHardSwish: return x >= 3.f ? x : x <= -3.f ? 0.f : (x * (x + 3.0f) / 6.0f);
+        case kReLU: return activate_t<kReLU>(x);
+        case kELU: return activate_t<kELU>(x);
+        case kSELU: return activate_t<kSELU>(x);
+        case kGELU: return activate_t<kGELU>(x);
+        case kMISH: return activate_t<kMISH>(x);
+        case kSwish: return activate_t<kSwish>(x);
+        case kHardSwish: return activate_t<kHardSwish>(x);
         default: return x;
     }
 }
+
+// Host-side dispatch of a kernel template over the activation enum.
+#define SB_DISPATCH_ACT(act, ACT, ...)                                  \
+    switch (act) {                                                      \
+        case sb::kReLU: { constexpr int ACT = sb::kReLU; __VA_ARGS__; } break;           \
+        case sb::kELU: { constexpr int ACT = sb::kELU; __VA_ARGS__; } break;             \
+        case sb::kSELU: { constexpr int ACT = sb::kSELU; __VA_ARGS__; } break;           \
+        case sb::kGELU: { constexpr int ACT = sb::kGELU; __VA_ARGS__; } break;           \
+        case sb::kMISH: { constexpr int ACT = sb::kMISH; __VA_ARGS__; } break;           \
+        case sb::kSwish: { constexpr int ACT = sb::kSwish; __VA_ARGS__; } break;         \
+        case sb::kHardSwish: { constexpr int ACT = sb::kHardSwish; __VA_ARGS__; } break; \
+        default: { constexpr int ACT = sb::kIdentity; __VA_ARGS__; } break;              \
+    }
 
 // ---- fp16 hi/lo split: v ~= hi + lo with ~22 significant bits ---------------------------------
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {

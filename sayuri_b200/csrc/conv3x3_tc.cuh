@@ -20,8 +20,8 @@
 // parity bar.  SPLIT=false uses the hi parts only (the reference's own --fp16 trade).
 //
 // Warp roles (384 threads, 1 CTA/SM, persistent over work items):
-//   warp 0 lane 0 : TMA producer for weight stages      warp 1 lane 0 : tcgen05.mma issuer
-//   warp 2        : TMEM allocator                      warp 3 lane 0 : TMA producer for activation slabs
+//   warp 0 : TMA producer for weight stages      warp 1 : tcgen05.mma issuer   (converged, elected lane issues)
+//   warp 2 : TMEM allocator                      warp 3 : TMA producer for activation slabs
 //   warps 4..11   : epilogue (warp%4 = TMEM lane quadrant, (warp-4)/4 = which M=128 tile of the item)
 #pragma once
 #include "common.cuh"
@@ -43,9 +43,8 @@ struct ConvParams {
     int n_super;             // number of 256-row work items along M
     int n_ntiles;            // cout / bn
     int pitch;               // P = N + 1
-    int act;                 // sb::Act applied after bias (+residual)
-    int bo_mode;             // 0: descriptor base_offset = 0 ; 1: base_offset = (start_addr >> 7) & 7
     int* err;                // device int, receives a site code if a barrier wait times out
+    long long* stats;        // optional [grid][8] cycle counters (see sb_conv_stats), nullptr = off
 };
 
 template <bool SPLIT>
@@ -65,7 +64,7 @@ struct ConvCfg {
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <bool SPLIT>
+template <bool SPLIT, int ACT>
 __global__ void __launch_bounds__(384, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -120,7 +119,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 3 && lane == 0) {
+    // Role warps stay CONVERGED (all 32 lanes run the loops, one elected lane issues the PTX): loop state is
+    // then warp-uniform and lives in uniform registers, which is what UTMALDG / UTCHMMA take as operands.
+    // (A `lane == 0` branch forces R2UR moves and an ELECT/BRA loop around every MMA: 4x slower issue.)
+    if (warp == 3) {
         // ===================== activation-slab producer =====================
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -129,17 +131,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             for (int h = 0; h < KH; ++h, ++it) {
                 const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
                 mbar_wait(slab_empty + 8 * s, ph ^ 1u, p.err, 1);
-                mbar_arrive_expect_tx(slab_full + 8 * s, Cfg::kSlabBytes);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(slab_full + 8 * s, Cfg::kSlabBytes);
 #pragma unroll
-                for (int part = 0; part < Cfg::kParts; ++part) {
-                    const CUtensorMap* tm = part ? &tmA_lo : &tmA_hi;
-                    const uint32_t dst = slab_addr + s * Cfg::kSlabBytes + part * Cfg::kSlabPartBytes;
-                    tma_load_2d(dst, tm, h * 64, row_lo, slab_full + 8 * s);
-                    tma_load_2d(dst + (kSlabRows / 2) * 128, tm, h * 64, row_lo + kSlabRows / 2, slab_full + 8 * s);
+                    for (int part = 0; part < Cfg::kParts; ++part) {
+                        const CUtensorMap* tm = part ? &tmA_lo : &tmA_hi;
+                        const uint32_t dst = slab_addr + s * Cfg::kSlabBytes + part * Cfg::kSlabPartBytes;
+                        tma_load_2d(dst, tm, h * 64, row_lo, slab_full + 8 * s);
+                        tma_load_2d(dst + (kSlabRows / 2) * 128, tm, h * 64, row_lo + kSlabRows / 2, slab_full + 8 * s);
+                    }
                 }
+                __syncwarp();
             }
         }
-    } else if (warp == 0 && lane == 0) {
+    } else if (warp == 0) {
         // ===================== weight-stage producer =====================
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -150,140 +155,206 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     for (int part = 0; part < Cfg::kParts; ++part, ++it) {
                         const uint32_t s = it & 3u, ph = (it >> 2) & 1u;
                         mbar_wait(b_empty + 8 * s, ph ^ 1u, p.err, 2);
-                        mbar_arrive_expect_tx(b_full + 8 * s, (uint32_t)BN * 128u);
-                        tma_load_2d(bst_addr + s * Cfg::kBStageBytes, part ? &tmW_lo : &tmW_hi,
-                                    tap * (KH * 64) + h * 64, nt * BN, b_full + 8 * s);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(b_full + 8 * s, (uint32_t)BN * 128u);
+                            tma_load_2d(bst_addr + s * Cfg::kBStageBytes, part ? &tmW_lo : &tmW_hi,
+                                        tap * (KH * 64) + h * 64, nt * BN, b_full + 8 * s);
+                        }
+                        __syncwarp();
                     }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // TMEM columns: main accumulator of (stage as, tile t) at (as*2 + t)*BN; with SPLIT there is one stage
+        // and the low-order products (a_lo*w_hi + a_hi*w_lo) go to their OWN accumulator at (2 + t)*BN.
+        // The tensor core accumulates with truncation (RZ): every MMA into a large accumulator costs ~0.5 ulp
+        // of bias, so the 2/3 of the MMAs that only carry 2^-11-sized terms must not touch the main sum.
         const uint32_t idesc = umma_idesc_f16(128, BN);
+        const bool stats = p.stats != nullptr;
         uint32_t a_it = 0, b_it = 0, j = 0;
+        long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0, t0 = 0;
+        const long long t_begin = stats ? clock64() : 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
-            const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+            const uint32_t as = SPLIT ? 0u : (j & 1u);
+            const uint32_t aph = SPLIT ? (j & 1u) : ((j >> 1) & 1u);
+            if (stats) t0 = clock64();
             mbar_wait(tmem_empty + 8 * as, aph ^ 1u, p.err, 3);
+            if (stats) t_wait_tmem += clock64() - t0;
             tc_fence_after();
             for (int h = 0; h < KH; ++h, ++a_it) {
                 const uint32_t s = a_it & 1u, sph = (a_it >> 1) & 1u;
+                if (stats) t0 = clock64();
                 mbar_wait(slab_full + 8 * s, sph, p.err, 4);
+                if (stats) t_wait_slab += clock64() - t0;
                 tc_fence_after();
                 const uint32_t a_hi = slab_addr + s * Cfg::kSlabBytes;
-                const uint32_t a_lo = a_hi + Cfg::kSlabPartBytes;
                 for (int tap = 0; tap < 9; ++tap) {
                     const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
-                    {   // weights hi  x  (activations hi [+ lo])
+                    const uint32_t first = (h | tap) == 0 ? 0u : 1u;
+                    const uint64_t ad_t0 = umma_desc_sw128(a_hi + (uint32_t)(kSlabMargin + shift) * 128u);
+                    {   // weights hi  x  activations hi -> main ; x activations lo -> lo accumulator
                         const uint32_t bs = b_it & 3u, bph = (b_it >> 2) & 1u;
+                        if (stats) t0 = clock64();
                         mbar_wait(b_full + 8 * bs, bph, p.err, 5);
+                        if (stats) t_wait_b += clock64() - t0;
                         tc_fence_after();
-                        const uint32_t b_addr = bst_addr + bs * Cfg::kBStageBytes;
+                        const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            const uint32_t d = tmem_base + (as * 2 + t) * BN;
-                            const uint32_t roff = (uint32_t)(kSlabMargin + t * 128 + shift) * 128u;
+                            for (int t = 0; t < 2; ++t) {
+                                const uint32_t d_main = tmem_base + (as * 2 + t) * BN;
+                                const uint32_t d_lo = tmem_base + (2 + t) * BN;
+                                const uint64_t ad0 = ad_t0 + (uint64_t)(t * 128 * 128 / 16);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t aa = a_hi + roff + k * 32;
-                                const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 0);
-                                umma_f16(d, umma_desc_sw128(aa, p.bo_mode ? (aa >> 7) : 0u), bd, idesc,
-                                         (h | tap | k) != 0 ? 1u : 0u);
-                                if (SPLIT) {
-                                    const uint32_t al = a_lo + roff + k * 32;
-                                    umma_f16(d, umma_desc_sw128(al, p.bo_mode ? (al >> 7) : 0u), bd, idesc, 1u);
+                                for (int k = 0; k < 4; ++k) {
+                                    // +2 in the start-address field == +32 bytes == one K=16 step inside the swizzle row
+                                    umma_f16(d_main, ad0 + 2 * k, bd0 + 2 * k, idesc, (k == 0) ? first : 1u);
+                                    if (SPLIT)
+                                        umma_f16(d_lo, ad0 + (Cfg::kSlabPartBytes >> 4) + 2 * k, bd0 + 2 * k, idesc,
+                                                 (k == 0) ? first : 1u);
                                 }
                             }
+                            umma_commit(b_empty + 8 * bs);
                         }
-                        umma_commit(b_empty + 8 * bs);
+                        __syncwarp();
                         ++b_it;
                     }
-                    if (SPLIT) {   // weights lo  x  activations hi
+                    if (SPLIT) {   // weights lo  x  activations hi -> lo accumulator
                         const uint32_t bs = b_it & 3u, bph = (b_it >> 2) & 1u;
+                        if (stats) t0 = clock64();
                         mbar_wait(b_full + 8 * bs, bph, p.err, 6);
+                        if (stats) t_wait_b += clock64() - t0;
                         tc_fence_after();
-                        const uint32_t b_addr = bst_addr + bs * Cfg::kBStageBytes;
+                        const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            const uint32_t d = tmem_base + (as * 2 + t) * BN;
-                            const uint32_t roff = (uint32_t)(kSlabMargin + t * 128 + shift) * 128u;
+                            for (int t = 0; t < 2; ++t) {
+                                const uint32_t d_lo = tmem_base + (2 + t) * BN;
+                                const uint64_t ad0 = ad_t0 + (uint64_t)(t * 128 * 128 / 16);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t aa = a_hi + roff + k * 32;
-                                umma_f16(d, umma_desc_sw128(aa, p.bo_mode ? (aa >> 7) : 0u),
-                                         umma_desc_sw128(b_addr + k * 32, 0), idesc, 1u);
+                                for (int k = 0; k < 4; ++k) umma_f16(d_lo, ad0 + 2 * k, bd0 + 2 * k, idesc, 1u);
                             }
+                            umma_commit(b_empty + 8 * bs);
                         }
-                        umma_commit(b_empty + 8 * bs);
+                        __syncwarp();
                         ++b_it;
                     }
                 }
-                umma_commit(slab_empty + 8 * s);   // slab reusable once every MMA reading it has retired
+                if (elect_one()) umma_commit(slab_empty + 8 * s);   // slab reusable once every MMA reading it has retired
+                __syncwarp();
             }
-            umma_commit(tmem_full + 8 * as);       // accumulators of this item are complete
+            if (elect_one()) umma_commit(tmem_full + 8 * as);       // accumulators of this item are complete
+            __syncwarp();
+        }
+        if (stats && lane == 0) {
+            long long* st = p.stats + (size_t)blockIdx.x * 8;
+            st[0] = clock64() - t_begin;
+            st[1] = t_wait_tmem;
+            st[2] = t_wait_slab;
+            st[3] = t_wait_b;
+            st[6] = j;
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
+        // Drain first, compute later: the accumulators are pulled into registers (main + lo added with
+        // round-to-nearest), TMEM is handed back to the MMA warp at once, and bias / residual / activation /
+        // fp16 split / stores run from registers while the next item's MMAs are already in flight.
         const int t = (warp - 4) >> 2;
         const int q = warp & 3;
         uint32_t j = 0;
+        const bool stats = p.stats != nullptr;
+        long long t_wait_full = 0;
+        const long long t_begin = stats ? clock64() : 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int st = item / p.n_ntiles, nt = item % p.n_ntiles;
-            const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+            const uint32_t as = SPLIT ? 0u : (j & 1u);
+            const uint32_t aph = SPLIT ? (j & 1u) : ((j >> 1) & 1u);
+            const long long t0 = stats ? clock64() : 0;
             mbar_wait(tmem_full + 8 * as, aph, p.err, 7);
+            if (stats) t_wait_full += clock64() - t0;
             tc_fence_after();
-            const int row = kGuardRows + st * kSuperRows + t * 128 + q * 32 + lane;
-            const bool live = p.mask[row] != 0;
-            const size_t off = (size_t)row * p.out_pitch + (size_t)nt * BN;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + t) * BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + c0, r);
-                tmem_ld_wait();
-                float v[16];
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_main = lane_base + (as * 2 + t) * BN;
+            const uint32_t t_lo = lane_base + (2 + t) * BN;
+            float acc[128];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sbias[nt * BN + c0 + i];
-                if (live && p.res_hi != nullptr) {
-                    const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + off + c0);
-                    uint4 a0 = rh[0], a1 = rh[1];
-                    const __half* hh0 = reinterpret_cast<const __half*>(&a0);
-                    const __half* hh1 = reinterpret_cast<const __half*>(&a1);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        v[i] += __half2float(hh0[i]);
-                        v[8 + i] += __half2float(hh1[i]);
-                    }
+            for (int g = 0; g < 8; ++g) {
+                if (g * 16 < BN) {
+                    uint32_t r[16];
+                    tmem_ld16(t_main + g * 16, r);
                     if (SPLIT) {
-                        const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + off + c0);
-                        uint4 b0 = rl[0], b1 = rl[1];
-                        const __half* ll0 = reinterpret_cast<const __half*>(&b0);
-                        const __half* ll1 = reinterpret_cast<const __half*>(&b1);
+                        uint32_t r2[16];
+                        tmem_ld16(t_lo + g * 16, r2);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            v[i] += __half2float(ll0[i]);
-                            v[8 + i] += __half2float(ll1[i]);
-                        }
+                        for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]);
                     }
-                }
-                __align__(16) __half oh[16];
-                __align__(16) __half ol[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a = live ? activate(v[i], p.act) : 0.f;   // select, not multiply: garbage rows may hold NaN
-                    split_f16(a, oh[i], ol[i]);
-                }
-                uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off + c0);
-                dh[0] = reinterpret_cast<const uint4*>(oh)[0];
-                dh[1] = reinterpret_cast<const uint4*>(oh)[1];
-                if (SPLIT) {
-                    uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off + c0);
-                    dl[0] = reinterpret_cast<const uint4*>(ol)[0];
-                    dl[1] = reinterpret_cast<const uint4*>(ol)[1];
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * as);   // TMEM free: the next item's MMAs may start
+
+            const int row = kGuardRows + st * kSuperRows + t * 128 + q * 32 + lane;
+            const bool live = p.mask[row] != 0;
+            const size_t off = (size_t)row * p.out_pitch + (size_t)nt * BN;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                if (g * 16 < BN) {
+                    const int c0 = g * 16;
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[nt * BN + c0 + i];
+                    if (live && p.res_hi != nullptr) {
+                        const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + off + c0);
+                        uint4 a0 = rh[0], a1 = rh[1];
+                        const __half* hh0 = reinterpret_cast<const __half*>(&a0);
+                        const __half* hh1 = reinterpret_cast<const __half*>(&a1);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            v[i] += __half2float(hh0[i]);
+                            v[8 + i] += __half2float(hh1[i]);
+                        }
+                        if (SPLIT) {
+                            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + off + c0);
+                            uint4 b0 = rl[0], b1 = rl[1];
+                            const __half* ll0 = reinterpret_cast<const __half*>(&b0);
+                            const __half* ll1 = reinterpret_cast<const __half*>(&b1);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                v[i] += __half2float(ll0[i]);
+                                v[8 + i] += __half2float(ll1[i]);
+                            }
+                        }
+                    }
+                    __align__(16) __half oh[16];
+                    __align__(16) __half ol[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float a = live ? activate_t<ACT>(v[i]) : 0.f;   // select, not multiply: garbage rows may hold NaN
+                        split_f16(a, oh[i], ol[i]);
+                    }
+                    uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off + c0);
+                    dh[0] = reinterpret_cast<const uint4*>(oh)[0];
+                    dh[1] = reinterpret_cast<const uint4*>(oh)[1];
+                    if (SPLIT) {
+                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off + c0);
+                        dl[0] = reinterpret_cast<const uint4*>(ol)[0];
+                        dl[1] = reinterpret_cast<const uint4*>(ol)[1];
+                    }
+                }
+            }
+        }
+        if (stats && warp == 4 && lane == 0) {
+            long long* st = p.stats + (size_t)blockIdx.x * 8;
+            st[4] = t_wait_full;
+            st[5] = clock64() - t_begin;
         }
     }
 

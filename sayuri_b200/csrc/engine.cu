@@ -234,6 +234,7 @@ struct Slot {
     float* pint = nullptr;
     float* pass5 = nullptr;
     float* misc15 = nullptr;
+    long long* d_stats = nullptr;  // [sm_count][8] cycle counters of the last conv launch (option "stats")
     int* h_err = nullptr;      // mapped pinned: barrier-timeout site code survives a trapped context
     int* d_err = nullptr;
     int n = 0;                 // samples of the batch in flight / last uploaded
@@ -271,7 +272,7 @@ struct sb_engine {
     int max_batch = 0;
     int rows_alloc = 0;
     int precision = SB_PRECISION_FP32_SPLIT;
-    int bo_mode = 0;
+    int collect_stats = 0;
     int n_slots = 2;
     bool weights_ready = false;
     std::atomic<long long> launches{0};
@@ -296,8 +297,8 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.d_out);
     cudaFreeHost(s.h_out);
     for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u}) {
+        if (a->lo != a->hi) cudaFree(a->lo);   // single-pass fp16 mode aliases lo to hi
         cudaFree(a->hi);
-        cudaFree(a->lo);
     }
     cudaFree(s.mask);
     cudaFree(s.gb);
@@ -305,6 +306,7 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.pint);
     cudaFree(s.pass5);
     cudaFree(s.misc15);
+    cudaFree(s.d_stats);
     cudaFreeHost(s.h_err);
     s = Slot{};
 }
@@ -356,6 +358,8 @@ static void AllocSlots(sb_engine* e, Replica& r) {
         SB_CUDA(cudaMalloc(&s.pint, (size_t)e->max_batch * P * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.pass5, (size_t)e->max_batch * 5 * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.misc15, (size_t)e->max_batch * 15 * sizeof(float)));
+        SB_CUDA(cudaMalloc(&s.d_stats, (size_t)r.sm_count * 8 * sizeof(long long)));
+        SB_CUDA(cudaMemset(s.d_stats, 0, (size_t)r.sm_count * 8 * sizeof(long long)));
         SB_CUDA(cudaHostAlloc(&s.h_err, sizeof(int), cudaHostAllocMapped));
         *s.h_err = 0;
         SB_CUDA(cudaHostGetDevicePointer(&s.d_err, s.h_err, 0));
@@ -412,8 +416,17 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
             MakeSimtWeights(e, r, r.conv2[b], *blob);
         }
     }
-    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::kSmemBytes));
-    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::kSmemBytes));
+    // dynamic shared memory opt-in, sized for the widest supported net (C = 256) so that engines of different
+    // widths can coexist in one process
+    for (int act = 0; act < 8; ++act) {
+        SB_DISPATCH_ACT(act, ACT,
+            SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<16, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 16 + 16) * 4));
+            SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<32, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 32 + 32) * 4));
+            SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<48, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 48 + 48) * 4));
+            SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<64, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 64 + 64) * 4));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::kSmemBytes));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::kSmemBytes)));
+    }
 }
 
 static void DestroyReplica(Replica& r) {
@@ -471,15 +484,16 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.n_super = n_super;
         p.n_ntiles = c.L.ntiles;
         p.pitch = e->geom.P;
-        p.act = act;
-        p.bo_mode = e->bo_mode;
         p.err = s.d_err;
+        p.stats = e->collect_stats ? s.d_stats : nullptr;
         const int items = n_super * c.L.ntiles;
         const int grid = std::min(items, r.sm_count);
         if (Split(e)) {
-            conv3x3_tc_kernel<true><<<grid, 384, ConvCfg<true>::kSmemBytes, s.stream>>>(in.tm_hi, in.tm_lo, c.tm_hi, c.tm_lo, p);
+            SB_DISPATCH_ACT(act, ACT, (conv3x3_tc_kernel<true, ACT><<<grid, 384, ConvCfg<true>::kSmemBytes, s.stream>>>(
+                                          in.tm_hi, in.tm_lo, c.tm_hi, c.tm_lo, p)));
         } else {
-            conv3x3_tc_kernel<false><<<grid, 384, ConvCfg<false>::kSmemBytes, s.stream>>>(in.tm_hi, in.tm_hi, c.tm_hi, c.tm_hi, p);
+            SB_DISPATCH_ACT(act, ACT, (conv3x3_tc_kernel<false, ACT><<<grid, 384, ConvCfg<false>::kSmemBytes, s.stream>>>(
+                                          in.tm_hi, in.tm_hi, c.tm_hi, c.tm_hi, p)));
         }
     }
     SB_CUDA(cudaGetLastError());
@@ -495,15 +509,10 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
 template <int PV>
 static void LaunchHeadConv(sb_engine* e, Replica& r, Slot& s, const ActBuf& x, int n_rows) {
     const int C = e->net_shape.channels;
-    const size_t smem = ((size_t)C * PV + PV) * sizeof(float);
-    static thread_local bool attr_set[16] = {false};
-    if (smem > 48 * 1024 && !attr_set[r.device & 15]) {
-        SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[r.device & 15] = true;
-    }
-    head_conv_kernel<PV><<<(n_rows + 127) / 128, 128, smem, s.stream>>>(
+    const size_t smem = ((size_t)C * PV + PV) * sizeof(float);   // opt-in size set once in BuildReplica
+    SB_DISPATCH_ACT(e->net_shape.act, ACT, (head_conv_kernel<PV, ACT><<<(n_rows + 127) / 128, 128, smem, s.stream>>>(
         x.hi, x.lo, Split(e), s.mask, reinterpret_cast<const float*>(r.blob + e->layout.head_wT),
-        reinterpret_cast<const float*>(r.blob + e->layout.head_b), C, x.pitch, n_rows, e->net_shape.act, s.pv);
+        reinterpret_cast<const float*>(r.blob + e->layout.head_b), C, x.pitch, n_rows, s.pv)));
 }
 
 // Everything between "inputs are in d_in / d_meta" and "outputs are in d_out", on the slot's stream.
@@ -541,8 +550,8 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
                                                           F(L.excite[b].b), act, s.gb);
             SB_CUDA(cudaGetLastError());
             const size_t total = (size_t)n_rows * (C / 8);
-            se_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(u->hi, u->lo, x->hi, x->lo, split, s.mask,
-                                                                                   s.gb, g, C, u->pitch, n_rows, act);
+            SB_DISPATCH_ACT(act, ACT, (se_apply_kernel<ACT><<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(
+                                          u->hi, u->lo, x->hi, x->lo, split, s.mask, s.gb, g, C, u->pitch, n_rows)));
             SB_CUDA(cudaGetLastError());
             e->launches += 2;
         } else {
@@ -695,6 +704,7 @@ static int SubmitImpl(sb_engine* e, int gpu, int slot, int n, const float* plane
     }
     try {
         SB_CUDA(cudaSetDevice(r.device));
+        cudaGetLastError();   // drop any stale non-sticky error of an unrelated earlier call
         for (int i = 0; i < n; ++i) {
             s.h_meta[i] = sizes[i];
             s.h_meta[e->max_batch + i] = offsets[i];
@@ -1030,10 +1040,25 @@ int sb_debug_read_trunk(sb_engine* e, int gpu, int slot, int sample, float* out)
     return SB_OK;
 }
 
+int sb_conv_stats(sb_engine* e, int gpu, int slot, long long* out, int capacity) {
+    if (!e || gpu < 0 || gpu >= (int)e->replicas.size() || slot < 0 || slot >= e->n_slots || !out) return SB_ERR_INVALID;
+    Replica& r = e->replicas[gpu];
+    Slot& s = r.slots[slot];
+    const int n = std::min(capacity, r.sm_count * 8);
+    try {
+        SB_CUDA(cudaSetDevice(r.device));
+        SB_CUDA(cudaStreamSynchronize(s.stream));
+        SB_CUDA(cudaMemcpy(out, s.d_stats, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    return n;
+}
+
 int sb_set_option(sb_engine* e, const char* key, int value) {
     if (!e || !key) return SB_ERR_INVALID;
-    if (!std::strcmp(key, "bo_mode")) {
-        e->bo_mode = value ? 1 : 0;
+    if (!std::strcmp(key, "stats")) {
+        e->collect_stats = value ? 1 : 0;
         return SB_OK;
     }
     return Fail(e, SB_ERR_INVALID, std::string("unknown option ") + key);

@@ -58,6 +58,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 // `err` (global) receives a site code before the trap so the host can report where it stalled.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int site) {
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         if (mbar_try_wait(bar, parity)) return;
     }
@@ -129,16 +130,15 @@ __device__ __forceinline__ void tmem_ld_wait() {
 
 // UMMA shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, rows of 64 fp16 (=128 B),
 // 8-row groups 1024 B apart (SBO).  Field layout: cute/arch/mma_sm100_desc.hpp:109-140.
-//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base_offset | [61,64) layout=2
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t base_offset) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major), CUTLASS writes 1
-    d |= (uint64_t)(1024u >> 4) << 32;  // SBO
-    d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
-    d |= (uint64_t)(base_offset & 7u) << 49;
-    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
-    return d;
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base_offset=0 | [61,64) layout=2
+// Measured on B200 (tools/gpu_probe.py, profiles/r01_bringup.md): the swizzle XOR is applied to the ABSOLUTE
+// shared-memory address, so a start address shifted by any number of 128-byte rows (not only multiples of
+// 8) reads rows consistently with what TMA wrote, with base_offset = 0.  (base_offset = (addr>>7)&7 is wrong.)
+// Advancing the start field by n adds 16*n bytes: K steps (+32 B) and row shifts are plain integer adds.
+constexpr uint64_t kUmmaDescSw128 = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) |
+                                    ((uint64_t)2 << 61);
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return kUmmaDescSw128 | (uint64_t)((saddr & 0x3FFFFu) >> 4);
 }
 
 // Instruction descriptor for kind::f16, A=B=fp16, D=fp32, both K-major, dense.

@@ -1,0 +1,236 @@
+// B200ForwardPipe: the C++ host side of the drop-in boundary.  Implements the reference's
+// CudaForwardPipe interface (src/neural/cuda/cuda_forward_pipe.h:20-36, semantics of
+// cuda_forward_pipe.cc:14-131) on top of the sayuri_b200 C ABI (include/sayuri_b200.h).
+// Compiled only together with the reference front-end; it is not part of
+// libsayuri_b200.so.
+#ifdef USE_CUDA
+
+#include "neural/cuda/cuda_forward_pipe.h"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "sayuri_b200.h"
+#include "utils/format.h"
+#include "utils/log.h"
+#include "utils/option.h"
+
+namespace {
+
+void Check(int rc, const sb_engine* e) {
+    // Same convention as ReportCUDAErrors (src/neural/cuda/cuda_common.cc:55-62): throw, the front-end
+    // catches at mode level (src/main.cc:17-39).
+    if (rc != SB_OK) throw std::runtime_error(std::string("sayuri_b200: ") + sb_last_error(e));
+}
+
+void PushConv(std::vector<sb_tensor>& t, ConvLayer& c) {
+    // BN is already folded by DNNLoader::ProcessWeights (loader.cc:775-831); never GetTransformF().
+    t.push_back({c.GetWeights().data(), (long long)c.GetWeights().size()});
+    t.push_back({c.GetBiases().data(), (long long)c.GetBiases().size()});
+}
+void PushFc(std::vector<sb_tensor>& t, LinearLayer& l) {
+    t.push_back({l.GetWeights().data(), (long long)l.GetWeights().size()});
+    t.push_back({l.GetBiases().data(), (long long)l.GetBiases().size()});
+}
+
+}  // namespace
+
+CudaForwardPipe::~CudaForwardPipe() {
+    if (engine_) {
+        sb_destroy(engine_);
+        engine_ = nullptr;
+    }
+}
+
+void CudaForwardPipe::Initialize(std::shared_ptr<DNNWeights> weights) {
+    LOGGING << "Backend: sayuri_b200 (sm_100a tcgen05/TMA implicit-GEMM engine)\n";
+    dump_gpu_info_ = true;
+    auto option = ForwardPipeOption::Get()
+                      .SetBoardSize(GetOption<int>("defualt_boardsize"))
+                      .SetBatchSize(GetOption<int>("batch_size"));
+    Construct(option, weights);
+    BatchForwardPipe::AssignWorkers(num_gpus_);
+}
+
+OutputResult CudaForwardPipe::Forward(const InputData& input) {
+    return BatchForwardPipe::SendQueryAndWait(input);
+}
+
+bool CudaForwardPipe::Valid() const {
+    return weights_ != nullptr;
+}
+
+int CudaForwardPipe::GetNumWorkers() const {
+    return num_gpus_;
+}
+
+void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWeights> weights) {
+    // cuda_forward_pipe.cc:44-119
+    if (weights) {
+        weights_ = weights;
+    }
+    if (weights_ == nullptr) {
+        return;   // dummy backend
+    }
+    int board_size = option.IsValidBoardSize() ? option.board_size : board_size_;
+    int batch_size = option.IsValidBatchSize() ? option.batch_size : max_batch_per_nn_;
+    board_size = std::max(board_size, GetOption<int>("fixed_nn_boardsize"));
+    if (board_size == 0 || batch_size == 0) {
+        LOGGING << "NN board size/batch size should be larger than zero.\n";
+        return;
+    }
+    BatchForwardPipe::SetForwardingSize(batch_size);
+    if (engine_ && !weights && board_size_ == board_size && batch_size <= max_batch_per_nn_) {
+        return;   // current engine already supports this configuration
+    }
+    if (engine_ && !weights) {
+        // Reconstruct (network.cc:494-498): keep the weights, re-allocate activations.
+        Check(sb_reconfigure(engine_, board_size, batch_size), engine_);
+        board_size_ = board_size;
+        max_batch_per_nn_ = std::max(batch_size, max_batch_per_nn_);
+        BatchForwardPipe::SetBoardSize(board_size);
+        return;
+    }
+    Release();
+    board_size_ = board_size;
+    max_batch_per_nn_ = batch_size;
+    BatchForwardPipe::SetBoardSize(board_size);
+
+    // user-specified GPUs first, else all devices (cuda_forward_pipe.cc:82-107; the engine validates ids)
+    std::vector<int> gpus;
+    const int specific = GetOptionCount("gpus");
+    for (int i = 0; i < specific; ++i) {
+        const int id = GetOption<int>("gpus", i);
+        if (id >= 0) gpus.push_back(id);
+    }
+
+    DNNWeights& w = *weights_;
+    if (w.policy_head_type != PolicyHeadType::kNormal) {
+        throw std::runtime_error("sayuri_b200: RepLK policy head is not supported");
+    }
+    std::vector<int> se(w.residual_blocks, 0);
+    std::vector<sb_tensor> t;
+    PushConv(t, w.input_conv);
+    for (int b = 0; b < w.residual_blocks; ++b) {
+        BlockBasic* blk = w.tower[b].get();
+        if (!blk->IsResidualBlock()) {
+            throw std::runtime_error("sayuri_b200: only ResidualBlock[-SE] towers are supported");
+        }
+        PushConv(t, blk->conv1);
+        PushConv(t, blk->conv2);
+        if (blk->apply_se) {
+            se[b] = blk->se_size;
+            PushFc(t, blk->squeeze);
+            PushFc(t, blk->excite);
+        }
+    }
+    PushConv(t, w.p_hd_conv);
+    PushFc(t, w.p_inter_fc);
+    PushConv(t, w.prob_conv);
+    PushFc(t, w.pass_fc);
+    PushConv(t, w.v_hd_conv);
+    PushFc(t, w.v_inter_fc);
+    PushConv(t, w.v_ownership);
+    PushFc(t, w.v_misc);
+
+    sb_net_desc d;
+    d.version = w.version;
+    d.input_channels = w.input_channels;
+    d.blocks = w.residual_blocks;
+    d.channels = w.residual_channels;
+    d.policy_channels = w.policy_head_channels;
+    d.value_channels = w.value_head_channels;
+    d.activation = static_cast<int>(w.default_act);
+    d.se_sizes = se.data();
+    sb_weights sw{t.data(), (int)t.size()};
+    const int precision = GetOption<bool>("fp16") ? SB_PRECISION_FP16 : SB_PRECISION_FP32_SPLIT;
+    int rc = sb_create(&engine_, &d, &sw, gpus.empty() ? nullptr : gpus.data(), (int)gpus.size(), board_size_,
+                       max_batch_per_nn_, precision);
+    if (rc != SB_OK) {
+        engine_ = nullptr;
+        throw std::runtime_error(std::string("sayuri_b200: ") + sb_last_error(nullptr));
+    }
+    num_gpus_ = sb_num_gpus(engine_);
+    if (dump_gpu_info_) {
+        LOGGING << Format("sayuri_b200: %d GPU replica(s), NN board %d, max batch %d, precision %s\n", num_gpus_,
+                          board_size_, max_batch_per_nn_, precision == SB_PRECISION_FP16 ? "fp16" : "fp32-split");
+    }
+    dump_gpu_info_ = false;
+}
+
+void CudaForwardPipe::Release() {
+    if (engine_) {
+        sb_destroy(engine_);
+        engine_ = nullptr;
+    }
+}
+
+void CudaForwardPipe::Destroy() {
+    BatchForwardPipe::QuitWorkers();
+    Release();
+}
+
+std::vector<OutputResult> CudaForwardPipe::BatchForward(int gpu, const std::vector<InputData>& inputs) {
+    // Called by exactly one worker thread per GPU (batch_forward_pipe.cc:93-96).
+    const int n = static_cast<int>(inputs.size());
+    const int N = board_size_, NS = N * N;
+    std::vector<const float*> planes(n);
+    std::vector<int> sizes(n), offsets(n);
+    // SendQueryAndWait (batch_forward_pipe.cc:15-33) has already re-laid smaller boards onto the N x N
+    // canvas on the host; the C ABI takes native packed planes and does the placement on the device, so
+    // undo that host re-layout for the (rare) mixed-size samples.
+    std::vector<std::vector<float>> repacked;
+    repacked.reserve(n);
+    for (int i = 0; i < n; ++i) {
+        const InputData& in = inputs[i];
+        sizes[i] = in.board_size;
+        offsets[i] = in.offset == PolicyBufferOffset::kDefault ? 0 : static_cast<int>(in.offset);
+        if (in.board_size == N) {
+            planes[i] = in.planes.data();
+        } else {
+            const int bs = in.board_size;
+            repacked.emplace_back((size_t)kInputChannels * bs * bs);
+            std::vector<float>& dst = repacked.back();
+            for (int c = 0; c < kInputChannels; ++c)
+                for (int y = 0; y < bs; ++y)
+                    std::memcpy(&dst[((size_t)c * bs + y) * bs], &in.planes[(size_t)c * NS + (size_t)y * N], sizeof(float) * bs);
+            planes[i] = dst.data();
+        }
+    }
+    std::vector<sb_output> raw(n);
+    Check(sb_forward_batch(engine_, gpu, n, planes.data(), sizes.data(), offsets.data(), raw.data()), engine_);
+    std::vector<OutputResult> results(n);
+    for (int i = 0; i < n; ++i) {
+        OutputResult& r = results[i];
+        const sb_output& o = raw[i];
+        const int bs = sizes[i];
+        if (bs == N) {
+            std::memcpy(r.probabilities.data(), o.probabilities, sizeof(float) * NS);
+            std::memcpy(r.ownership.data(), o.ownership, sizeof(float) * NS);
+        } else {
+            // back to canvas order; SendQueryAndWait crops it again (batch_forward_pipe.cc:48-67)
+            for (int y = 0; y < bs; ++y)
+                for (int x = 0; x < bs; ++x) {
+                    r.probabilities[(size_t)y * N + x] = o.probabilities[y * bs + x];
+                    r.ownership[(size_t)y * N + x] = o.ownership[y * bs + x];
+                }
+        }
+        r.pass_probability = o.pass_probability;
+        r.wdl[0] = o.wdl[0];
+        r.wdl[1] = o.wdl[1];
+        r.wdl[2] = o.wdl[2];
+        r.stm_winrate = o.stm_winrate;
+        r.final_score = o.final_score;
+        r.q_error = o.q_error;
+        r.score_error = o.score_error;
+        r.offset = inputs[i].offset;
+        r.board_size = bs;
+        r.komi = inputs[i].komi;
+        r.fp16 = o.fp16 != 0;
+    }
+    return results;
+}
+
+#endif

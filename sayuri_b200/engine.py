@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "sb_destroy", "sb_last_error", "sb_num_gpus", "sb_num_slots", "sb_max_batch", "sb_board_size", "sb_get_net_desc",
     "sb_forward_batch", "sb_submit", "sb_wait", "sb_host_alloc", "sb_host_free", "sb_weights_blob",
     "sb_weights_export", "sb_weights_import",
-    "sb_weights_checksum", "sb_time_forward", "sb_launch_count", "sb_debug_read_trunk", "sb_set_option",
+    "sb_weights_checksum", "sb_time_forward", "sb_launch_count", "sb_debug_read_trunk", "sb_conv_stats", "sb_set_option",
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def load_library():
     lib.sb_launch_count.argtypes = [vp]
     lib.sb_launch_count.restype = ctypes.c_longlong
     lib.sb_debug_read_trunk.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F]
+    lib.sb_conv_stats.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     lib.sb_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
     _lib = lib
     return lib
@@ -287,6 +288,14 @@ class B200ForwardPipe:
         out = np.zeros(c * board_size * board_size, dtype=np.float32)
         self._check(self._lib.sb_debug_read_trunk(self._h, gpu, slot, sample, out.ctypes.data_as(_F)))
         return out.reshape(c, board_size * board_size)
+
+    def conv_stats(self, gpu=0, slot=0):
+        """[n_ctas, 8] int64 cycle counters of the last conv3x3 launch (needs set_option("stats", 1))."""
+        buf = np.zeros(8 * 1024, dtype=np.int64)
+        n = self._lib.sb_conv_stats(self._h, gpu, slot, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), buf.size)
+        if n < 0:
+            self._check(n)
+        return buf[:n].reshape(-1, 8)
 
     def set_option(self, key, value):
         self._check(self._lib.sb_set_option(self._h, key.encode(), int(value)))

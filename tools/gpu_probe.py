@@ -28,7 +28,7 @@ SHAPES = {
     "20bx256": (20, 256, 32, 32, None),
     "golden": None,
 }
-MODES = {"simt": (2, 0), "split_bo0": (0, 0), "split_bo1": (0, 1), "fp16_bo0": (1, 0), "fp16_bo1": (1, 1)}
+MODES = {"simt": (2, 0), "split": (0, 0), "fp16": (1, 0)}
 
 
 def run_case(shape, mode, n, seed):
@@ -47,7 +47,6 @@ def run_case(shape, mode, n, seed):
     planes = [synth.synth_positions(1, bs, seed=seed + i)[0].ravel() for i, bs in enumerate(sizes)]
     offsets = [i % 5 for i in range(n)]
     pipe = engine.B200ForwardPipe().initialize(path, 19, max(n, 4), gpus=[0], precision=prec)
-    pipe.set_option("bo_mode", bo)
     out = pipe.batch_forward(0, planes, sizes, offsets)
     orc = Oracle(path)
     res = {"shape": shape, "mode": mode, "n": n, "trunk": 0.0, "prob": 0.0, "own": 0.0, "misc": 0.0, "scale": 0.0}
@@ -87,7 +86,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default=None, help="internal: shape:mode:n")
     ap.add_argument("--shapes", default="in32,b1c64,b1c128,golden")
-    ap.add_argument("--modes", default="simt,split_bo0,split_bo1,fp16_bo0")
+    ap.add_argument("--modes", default="simt,split,fp16")
     ap.add_argument("--n", default="5,16")
     args = ap.parse_args()
     if args.case:
