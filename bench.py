@@ -178,22 +178,8 @@ def run_ours(args, rank, local_rank, world):
                     se_sizes=[C // 4 if s.endswith("-SE") else 0 for s in stack])
         pipe.initialize_from_tensors(desc, None, 19, B, gpus=[local_rank], precision=precision)
     if world > 1:
-        _, nbytes = pipe.weights_blob(0)
-        buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            pipe.weights_export(buf.data_ptr(), nbytes)
-        torch.cuda.synchronize()
-        dist.broadcast(buf, src=0)            # the path's only collective (NVLink/NVSwitch)
-        torch.cuda.synchronize()
-        if rank != 0:
-            pipe.weights_import(buf.data_ptr(), nbytes)
-        cs = torch.tensor([pipe.weights_checksum(0) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
-        lo, hi = cs.clone(), cs.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        if int(lo) != int(hi):
-            raise RuntimeError("weight replicas differ after broadcast")
-        del buf
+        from sayuri_b200.dist import replicate_weights
+        replicate_weights(pipe, dist, rank, torch.device("cuda", local_rank))   # the path's only collective
 
     # ---- inputs: synthetic positions in pinned host memory (two alternating batches) ----------------
     pinned = engine.PinnedArray((2, B, engine.PLANE_FLOATS))

@@ -41,12 +41,12 @@ __device__ __forceinline__ void store8(__half* hi, __half* lo, bool split, const
 // BatchForwardPipe::SendQueryAndWait, batch_forward_pipe.cc:15-33), fp16 hi/lo split, and the per-row
 // board mask (ApplyMask, cuda_forward_pipe.cc:636-682).  One thread per (canvas row, 8-channel group).
 __global__ void unpack_planes_kernel(const float* __restrict__ planes, size_t sample_stride,
-                                     const int* __restrict__ board_sizes, Geom g, int n, int n_rows,
+                                     const int* __restrict__ board_sizes, Geom g, int n, int n_rows, int R,
                                      __half* __restrict__ hi, __half* __restrict__ lo, bool split,
                                      uint8_t* __restrict__ mask) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = idx >> 3, cg = idx & 7;
-    if (r >= n_rows) return;
+    const int cg = idx / n_rows, r = idx - cg * n_rows;   // rows fastest: coalesced 16-byte pieces
+    if (cg >= 8) return;
     const int b = r / g.SS, rem = r - b * g.SS;
     const int y = rem / g.P, x = rem - y * g.P;
     int bs = 0;
@@ -58,7 +58,7 @@ __global__ void unpack_planes_kernel(const float* __restrict__ planes, size_t sa
         const int c = cg * 8 + i;
         v[i] = (live && c < kInputChannels) ? planes[(size_t)b * sample_stride + (size_t)c * bs * bs + y * bs + x] : 0.f;
     }
-    const size_t off = (size_t)(kGuardRows + r) * kInputChannelsPadded + cg * 8;
+    const size_t off = act_index(kGuardRows + r, cg * 8, R);
     store8(hi + off, lo + off, split, v);
     if (cg == 0) mask[kGuardRows + r] = live ? 1 : 0;
 }
@@ -70,7 +70,7 @@ __global__ void unpack_planes_kernel(const float* __restrict__ planes, size_t sa
 // beta, [n][2C].  Mean divides by the sample's own n^2, (n-14)/10 uses the sample's own n.
 __global__ void __launch_bounds__(256)
 se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_lo, bool split,
-                  const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int C, int pitch,
+                  const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int C, int R,
                   int se, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                   const float* __restrict__ b2, int act, float* __restrict__ gb) {
     extern __shared__ float sm[];
@@ -89,7 +89,7 @@ se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_
         const int row0 = kGuardRows + b * g.SS;
         for (int r = rg; r < g.SS; r += n_rg) {
             if (!mask[row0 + r]) continue;
-            const size_t off = (size_t)(row0 + r) * pitch + 2 * c2;
+            const size_t off = act_index(row0 + r, 2 * c2, R);
             float2 v = __half22float2(*reinterpret_cast<const __half2*>(u_hi + off));
             if (split) {
                 const float2 l = __half22float2(*reinterpret_cast<const __half2*>(u_lo + off));
@@ -143,13 +143,13 @@ template <int ACT>
 __global__ void se_apply_kernel(__half* __restrict__ u_hi, __half* __restrict__ u_lo,
                                 const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, bool split,
                                 const uint8_t* __restrict__ mask, const float* __restrict__ gb, Geom g, int C,
-                                int pitch, int n_rows) {
+                                int R, int n_rows) {
     const int groups = C >> 3;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = (int)(idx / groups), cg = (int)(idx - (size_t)r * groups);
-    if (r >= n_rows) return;
+    const int cg = (int)(idx / n_rows), r = (int)(idx - (size_t)cg * n_rows);   // rows fastest
+    if (cg >= groups) return;
     const int row = kGuardRows + r;
-    const size_t off = (size_t)row * pitch + cg * 8;
+    const size_t off = act_index(row, cg * 8, R);
     float o[8];
     if (mask[row]) {
         const int b = r / g.SS;
@@ -175,7 +175,7 @@ template <int PV, int ACT>
 __global__ void __launch_bounds__(128)
 head_conv_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, bool split,
                  const uint8_t* __restrict__ mask, const float* __restrict__ wT, const float* __restrict__ bias,
-                 int C, int pitch, int n_rows, float* __restrict__ pv) {
+                 int C, int R, int n_rows, float* __restrict__ pv) {
     extern __shared__ float sw[];   // [C][PV] + [PV]
     for (int i = threadIdx.x; i < C * PV; i += blockDim.x) sw[i] = wT[i];
     float* sb_ = sw + C * PV;
@@ -191,7 +191,7 @@ head_conv_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_l
         for (int j = 0; j < PV; ++j) acc[j] = sb_[j];
         for (int c0 = 0; c0 < C; c0 += 8) {
             float x[8];
-            const size_t off = (size_t)row * pitch + c0;
+            const size_t off = act_index(row, c0, R);
             load8(x_hi + off, x_lo + off, split, x);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -377,23 +377,22 @@ conv3x3_simt_kernel(const __half* __restrict__ in_hi, const __half* __restrict__
                     const float* __restrict__ wT, const float* __restrict__ bias,
                     const __half* __restrict__ res_hi, const __half* __restrict__ res_lo,
                     const uint8_t* __restrict__ mask, int cout, int n_rows, int pitch, int act,
-                    __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_pitch) {
+                    __half* __restrict__ out_hi, __half* __restrict__ out_lo, int R) {
     const int co = blockIdx.y * 32 + threadIdx.x;
     const int r = blockIdx.x * 8 + threadIdx.y;
     if (r >= n_rows || co >= cout) return;
     const int row = kGuardRows + r;
-    const size_t off = (size_t)row * out_pitch + co;
+    const size_t off = act_index(row, co, R);
     float v = 0.f;
     if (mask[row]) {
         float acc = 0.f;
         for (int tap = 0; tap < 9; ++tap) {
             const int src = row + (tap / 3 - 1) * pitch + (tap % 3 - 1);
-            const __half* ah = in_hi + (size_t)src * cinp;
-            const __half* al = in_lo + (size_t)src * cinp;
             const float* w = wT + (size_t)tap * cinp * cout + co;
             for (int c = 0; c < cinp; ++c) {
-                float a = __half2float(ah[c]);
-                if (split) a += __half2float(al[c]);
+                const size_t ai = act_index(src, c, R);
+                float a = __half2float(in_hi[ai]);
+                if (split) a += __half2float(in_lo[ai]);
                 acc += a * w[(size_t)c * cout];
             }
         }

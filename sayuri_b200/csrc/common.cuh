@@ -7,8 +7,15 @@
 namespace sb {
 
 // ---- Canvas layout (DESIGN.md "Data layout in HBM") -------------------------------------------
-// Activations are NHWC matrices [rows][C] of fp16 (a `hi` tensor and, in split precision, a `lo`
-// tensor with x ~= hi + lo).  Sample b, board cell (y, x) of an N x N canvas lives at row
+// Activations are [rows] x [C] fp16 matrices (a `hi` tensor and, in split precision, a `lo` tensor with
+// x ~= hi + lo) stored CHANNEL-BLOCKED ("C8"): element (row, c) sits at ((c / 8) * R + row) * 8 + c % 8, i.e.
+// [C/8 chunks][R rows][8 channels = 16 bytes].  Consequences:
+//   * a thread that owns one row (the TMEM epilogue: lane <-> row) and its 31 neighbours touch 32 consecutive
+//     16-byte pieces: every global load/store of the epilogues is fully coalesced without staging;
+//   * one 4-D TMA box [8 chunks][304 rows][16 B] lands in shared memory exactly as the UMMA no-swizzle K-major
+//     "core matrix" layout (8 rows x 16 B contiguous, SBO = 128 B between row groups, LBO = 304*16 B between the
+//     two K chunks of an MMA), where a shift by s rows is a plain +16*s bytes on the descriptor start address.
+// Sample b, board cell (y, x) of an N x N canvas lives at row
 //     kGuardRows + b * SS + y * P + x,     P = N + 1,  SS = (N + 1) * (N + 1)
 // i.e. every board row carries ONE trailing halo cell and every sample ONE trailing halo row; the
 // halo cell right of row y doubles as the halo left of row y+1, the halo row below sample b doubles
@@ -23,6 +30,11 @@ constexpr int kMaxBoard = 19;    // /root/reference/src/game/types.h:5-7 (MAX_BO
 constexpr int kMaxIntersections = kMaxBoard * kMaxBoard;
 constexpr int kInputChannels = 43;   // /root/reference/src/neural/network_basic.h:10
 constexpr int kInputChannelsPadded = 64;
+
+// element (row, c) of a C8 tensor with R rows
+__host__ __device__ inline size_t act_index(int row, int c, int R) {
+    return ((size_t)(c >> 3) * (size_t)R + (size_t)row) * 8 + (size_t)(c & 7);
+}
 
 struct Geom {
     int N, P, SS;
@@ -91,6 +103,55 @@ __device__ __noinline__ float activate(float x, int act) {
         case sb::kHardSwish: { constexpr int ACT = sb::kHardSwish; __VA_ARGS__; } break; \
         default: { constexpr int ACT = sb::kIdentity; __VA_ARGS__; } break;              \
     }
+
+// Stage-wise (structure-of-arrays) activation of 16 values: every MUFU / FMA stage is issued for all 16
+// elements before the next stage starts, so the ~100-cycle ex2 -> rcp dependency chain of one element is
+// overlapped with its 15 neighbours (an element-by-element loop ran latency-bound: 110 cycles per element).
+template <int ACT>
+__device__ __forceinline__ void activate16(float (&v)[16]) {
+    if (ACT == kMISH) {
+        float w[16], n[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = fast_exp(fminf(v[i], 20.f));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) n[i] = w[i] * (w[i] + 2.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = fast_rcp(n[i] + 2.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] * n[i] * w[i];
+    } else if (ACT == kSwish) {
+        float w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = fast_exp(-v[i]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = fast_rcp(1.0f + w[i]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] * w[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = activate_t<ACT>(v[i]);
+    }
+}
+
+// 16 floats -> 16 fp16 `hi` (+ 16 fp16 `lo` residues), packed two per register, stage-wise.
+__device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8], bool want_lo) {
+    __half2 h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float a = fminf(fmaxf(v[2 * i], -60000.f), 60000.f);
+        const float b = fminf(fmaxf(v[2 * i + 1], -60000.f), 60000.f);
+        h[i] = __floats2half2_rn(a, b);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h[i]);
+    }
+    if (want_lo) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 f = __half22float2(h[i]);
+            const __half2 l = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+    }
+}
 
 // ---- fp16 hi/lo split: v ~= hi + lo with ~22 significant bits ---------------------------------
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {

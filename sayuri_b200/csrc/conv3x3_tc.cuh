@@ -1,5 +1,5 @@
 // conv3x3_tc — 3x3 same-pad convolution (+bias, +residual, *mask, activation) as an implicit GEMM on the
-// 5th-gen tensor cores: TMA-staged NHWC tiles in 128B-swizzled shared memory -> tcgen05.mma (M=128,
+// 5th-gen tensor cores: TMA-staged channel-blocked NHWC tiles in shared memory -> tcgen05.mma (M=128,
 // N=BN, K=16 per instruction, fp16 operands, fp32 accumulation in TMEM) -> tcgen05.ld epilogue.
 //
 // Replaces, for the tower and input convolutions, the reference's
@@ -37,12 +37,14 @@ struct ConvParams {
     const float* bias;       // [cout]
     const uint8_t* mask;     // [rows]: 1 = real board cell of its sample, 0 = halo / off-board / padding
     int cout;                // real output channels (bias length)
-    int out_pitch;           // row pitch (elements) of out/res: cout rounded up to 64
+    int rows;                // R: rows per channel chunk of the C8 activation tensors (out/res)
     int kh;                  // number of 64-channel K blocks per tap = padded Cin / 64
     int bn;                  // UMMA N = output channels per work item (multiple of 16, <= 128)
     int n_super;             // number of 256-row work items along M
     int n_ntiles;            // cout / bn
     int pitch;               // P = N + 1
+    int dbg;                 // ablation bits for profiling only: 1 skip stores, 2 skip activation+split math, 4 skip drain
+    int a_lbo, a_sbo;        // A-operand descriptor strides in bytes (K-adjacent / row-group-adjacent core matrices)
     int* err;                // device int, receives a site code if a barrier wait times out
     long long* stats;        // optional [grid][8] cycle counters (see sb_conv_stats), nullptr = off
 };
@@ -54,7 +56,7 @@ struct ConvCfg {
     static constexpr int kSlabBytes = kParts * kSlabPartBytes;
     static constexpr int kNumSlabs = 2;
     static constexpr int kBStageBytes = 128 * 128;                    // up to 128 rows x 64 fp16
-    static constexpr int kNumBStages = 4;
+    static constexpr int kNumBStages = SPLIT ? 4 : 8;                 // whatever shared memory is left
     static constexpr int kOffB = kNumSlabs * kSlabBytes;
     static constexpr int kOffBar = kOffB + kNumBStages * kBStageBytes;
     static constexpr int kOffBias = kOffBar + 256;
@@ -80,9 +82,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const uint32_t bar_addr = smem_base + Cfg::kOffBar;
     // barrier slots (8 B each)
     const uint32_t slab_full = bar_addr + 0, slab_empty = bar_addr + 16;          // [2] each
-    const uint32_t b_full = bar_addr + 32, b_empty = bar_addr + 64;               // [4] each
-    const uint32_t tmem_full = bar_addr + 96, tmem_empty = bar_addr + 112;        // [2] each
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 128);
+    const uint32_t tmem_full = bar_addr + 32, tmem_empty = bar_addr + 48;         // [2] each
+    const uint32_t b_full = bar_addr + 64, b_empty = bar_addr + 128;              // [kNumBStages <= 8] each
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 192);
+    constexpr uint32_t kNB = Cfg::kNumBStages;
     float* sbias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
 
     const int warp = threadIdx.x >> 5;
@@ -98,7 +101,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             mbar_init(tmem_full + 8 * i, 1);
             mbar_init(tmem_empty + 8 * i, 8);   // one arrive per epilogue warp
         }
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < Cfg::kNumBStages; ++i) {
             mbar_init(b_full + 8 * i, 1);
             mbar_init(b_empty + 8 * i, 1);
         }
@@ -119,9 +122,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // Register re-balancing: the epilogue threads hold a full 128-column accumulator row in registers and need
+    // working registers on top for instruction-level parallelism; the producer / MMA warps need very few.
+    // (setmaxnreg sits at the top of each warpgroup's own branch so that ptxas can scope the two limits.)
+
     // Role warps stay CONVERGED (all 32 lanes run the loops, one elected lane issues the PTX): loop state is
     // then warp-uniform and lives in uniform registers, which is what UTMALDG / UTCHMMA take as operands.
     // (A `lane == 0` branch forces R2UR moves and an ELECT/BRA loop around every MMA: 4x slower issue.)
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 3) {
         // ===================== activation-slab producer =====================
         uint32_t it = 0;
@@ -135,10 +144,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     mbar_arrive_expect_tx(slab_full + 8 * s, Cfg::kSlabBytes);
 #pragma unroll
                     for (int part = 0; part < Cfg::kParts; ++part) {
-                        const CUtensorMap* tm = part ? &tmA_lo : &tmA_hi;
-                        const uint32_t dst = slab_addr + s * Cfg::kSlabBytes + part * Cfg::kSlabPartBytes;
-                        tma_load_2d(dst, tm, h * 64, row_lo, slab_full + 8 * s);
-                        tma_load_2d(dst + (kSlabRows / 2) * 128, tm, h * 64, row_lo + kSlabRows / 2, slab_full + 8 * s);
+                        // one 4-D box = [8 chunks][2 x 152 rows][8 ch]: lands as [chunk][304 rows][16 B]
+                        tma_load_4d(slab_addr + s * Cfg::kSlabBytes + part * Cfg::kSlabPartBytes, part ? &tmA_lo : &tmA_hi,
+                                    0, row_lo, 0, h * 8, slab_full + 8 * s);
                     }
                 }
                 __syncwarp();
@@ -153,7 +161,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
                     for (int part = 0; part < Cfg::kParts; ++part, ++it) {
-                        const uint32_t s = it & 3u, ph = (it >> 2) & 1u;
+                        const uint32_t s = it % kNB, ph = (it / kNB) & 1u;
                         mbar_wait(b_empty + 8 * s, ph ^ 1u, p.err, 2);
                         if (elect_one()) {
                             mbar_arrive_expect_tx(b_full + 8 * s, (uint32_t)BN * 128u);
@@ -172,6 +180,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         // The tensor core accumulates with truncation (RZ): every MMA into a large accumulator costs ~0.5 ulp
         // of bias, so the 2/3 of the MMAs that only carry 2^-11-sized terms must not touch the main sum.
         const uint32_t idesc = umma_idesc_f16(128, BN);
+        constexpr uint64_t kAStep = 2 * kSlabRows * 16 / 16;   // two K chunks, in 16-byte units
         const bool stats = p.stats != nullptr;
         uint32_t a_it = 0, b_it = 0, j = 0;
         long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0, t0 = 0;
@@ -193,9 +202,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 for (int tap = 0; tap < 9; ++tap) {
                     const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
                     const uint32_t first = (h | tap) == 0 ? 0u : 1u;
-                    const uint64_t ad_t0 = umma_desc_sw128(a_hi + (uint32_t)(kSlabMargin + shift) * 128u);
+                    // A: no-swizzle core matrices, row r of chunk j at j*304*16 + r*16; a tap is a +16*shift byte offset
+                    const uint64_t ad_t0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, (uint32_t)p.a_lbo, (uint32_t)p.a_sbo);
                     {   // weights hi  x  activations hi -> main ; x activations lo -> lo accumulator
-                        const uint32_t bs = b_it & 3u, bph = (b_it >> 2) & 1u;
+                        const uint32_t bs = b_it % kNB, bph = (b_it / kNB) & 1u;
                         if (stats) t0 = clock64();
                         mbar_wait(b_full + 8 * bs, bph, p.err, 5);
                         if (stats) t_wait_b += clock64() - t0;
@@ -206,13 +216,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             for (int t = 0; t < 2; ++t) {
                                 const uint32_t d_main = tmem_base + (as * 2 + t) * BN;
                                 const uint32_t d_lo = tmem_base + (2 + t) * BN;
-                                const uint64_t ad0 = ad_t0 + (uint64_t)(t * 128 * 128 / 16);
+                                const uint64_t ad0 = ad_t0 + (uint64_t)(t * 128 * 16 / 16);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    // +2 in the start-address field == +32 bytes == one K=16 step inside the swizzle row
-                                    umma_f16(d_main, ad0 + 2 * k, bd0 + 2 * k, idesc, (k == 0) ? first : 1u);
+                                    // K=16 step: A advances two chunks (2*304*16 B), B 32 B inside its swizzle row
+                                    // (descriptor start field counts 16-byte units)
+                                    umma_f16(d_main, ad0 + kAStep * k, bd0 + 2 * k, idesc, (k == 0) ? first : 1u);
                                     if (SPLIT)
-                                        umma_f16(d_lo, ad0 + (Cfg::kSlabPartBytes >> 4) + 2 * k, bd0 + 2 * k, idesc,
+                                        umma_f16(d_lo, ad0 + (Cfg::kSlabPartBytes >> 4) + kAStep * k, bd0 + 2 * k, idesc,
                                                  (k == 0) ? first : 1u);
                                 }
                             }
@@ -222,7 +233,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         ++b_it;
                     }
                     if (SPLIT) {   // weights lo  x  activations hi -> lo accumulator
-                        const uint32_t bs = b_it & 3u, bph = (b_it >> 2) & 1u;
+                        const uint32_t bs = b_it % kNB, bph = (b_it / kNB) & 1u;
                         if (stats) t0 = clock64();
                         mbar_wait(b_full + 8 * bs, bph, p.err, 6);
                         if (stats) t_wait_b += clock64() - t0;
@@ -232,9 +243,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                             for (int t = 0; t < 2; ++t) {
                                 const uint32_t d_lo = tmem_base + (2 + t) * BN;
-                                const uint64_t ad0 = ad_t0 + (uint64_t)(t * 128 * 128 / 16);
+                                const uint64_t ad0 = ad_t0 + (uint64_t)(t * 128 * 16 / 16);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_f16(d_lo, ad0 + 2 * k, bd0 + 2 * k, idesc, 1u);
+                                for (int k = 0; k < 4; ++k) umma_f16(d_lo, ad0 + kAStep * k, bd0 + 2 * k, idesc, 1u);
                             }
                             umma_commit(b_empty + 8 * bs);
                         }
@@ -256,7 +267,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             st[3] = t_wait_b;
             st[6] = j;
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================== epilogue =====================
         // Drain first, compute later: the accumulators are pulled into registers (main + lo added with
         // round-to-nearest), TMEM is handed back to the MMA warp at once, and bias / residual / activation /
@@ -265,7 +278,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const int q = warp & 3;
         uint32_t j = 0;
         const bool stats = p.stats != nullptr;
-        long long t_wait_full = 0;
+        long long t_wait_full = 0, t_drain = 0;
         const long long t_begin = stats ? clock64() : 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int st = item / p.n_ntiles, nt = item % p.n_ntiles;
@@ -279,9 +292,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             const uint32_t t_main = lane_base + (as * 2 + t) * BN;
             const uint32_t t_lo = lane_base + (2 + t) * BN;
             float acc[128];
+            const long long t_d0 = stats ? clock64() : 0;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                if (g * 16 < BN) {
+                if (g * 16 < BN && !(p.dbg & 4)) {
                     uint32_t r[16];
                     tmem_ld16(t_main + g * 16, r);
                     if (SPLIT) {
@@ -300,10 +314,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * as);   // TMEM free: the next item's MMAs may start
+            if (stats) t_drain += clock64() - t_d0;
 
             const int row = kGuardRows + st * kSuperRows + t * 128 + q * 32 + lane;
             const bool live = p.mask[row] != 0;
-            const size_t off = (size_t)row * p.out_pitch + (size_t)nt * BN;
+            // C8 layout: 16 columns = two 16-byte pieces, `chunk_stride` halves apart; lanes are consecutive rows
+            const size_t chunk_stride = (size_t)p.rows * 8;
+            const size_t off = act_index(row, nt * BN, p.rows);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 if (g * 16 < BN) {
@@ -311,9 +328,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[nt * BN + c0 + i];
+                    const size_t o0 = off + (size_t)(c0 >> 3) * chunk_stride, o1 = o0 + chunk_stride;
                     if (live && p.res_hi != nullptr) {
-                        const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + off + c0);
-                        uint4 a0 = rh[0], a1 = rh[1];
+                        const uint4 a0 = *reinterpret_cast<const uint4*>(p.res_hi + o0);
+                        const uint4 a1 = *reinterpret_cast<const uint4*>(p.res_hi + o1);
                         const __half* hh0 = reinterpret_cast<const __half*>(&a0);
                         const __half* hh1 = reinterpret_cast<const __half*>(&a1);
 #pragma unroll
@@ -322,8 +340,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             v[8 + i] += __half2float(hh1[i]);
                         }
                         if (SPLIT) {
-                            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + off + c0);
-                            uint4 b0 = rl[0], b1 = rl[1];
+                            const uint4 b0 = *reinterpret_cast<const uint4*>(p.res_lo + o0);
+                            const uint4 b1 = *reinterpret_cast<const uint4*>(p.res_lo + o1);
                             const __half* ll0 = reinterpret_cast<const __half*>(&b0);
                             const __half* ll1 = reinterpret_cast<const __half*>(&b1);
 #pragma unroll
@@ -333,20 +351,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             }
                         }
                     }
-                    __align__(16) __half oh[16];
-                    __align__(16) __half ol[16];
+                    uint32_t oh[8], ol[8];
+                    if (p.dbg & 2) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float a = live ? activate_t<ACT>(v[i]) : 0.f;   // select, not multiply: garbage rows may hold NaN
-                        split_f16(a, oh[i], ol[i]);
+                        for (int i = 0; i < 8; ++i) oh[i] = ol[i] = __float_as_uint(v[i]);
+                    } else {
+                        activate16<ACT>(v);
+                        if (!live) {   // select, not multiply: garbage rows may hold NaN
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                        }
+                        split16(v, oh, ol, SPLIT);
                     }
-                    uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off + c0);
-                    dh[0] = reinterpret_cast<const uint4*>(oh)[0];
-                    dh[1] = reinterpret_cast<const uint4*>(oh)[1];
+                    if (p.dbg & 1) {
+                        if (oh[0] == 0x12345678u) p.err[0] = 99;   // keep the math alive without storing
+                        continue;
+                    }
+                    *reinterpret_cast<uint4*>(p.out_hi + o0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                    *reinterpret_cast<uint4*>(p.out_hi + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
                     if (SPLIT) {
-                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off + c0);
-                        dl[0] = reinterpret_cast<const uint4*>(ol)[0];
-                        dl[1] = reinterpret_cast<const uint4*>(ol)[1];
+                        *reinterpret_cast<uint4*>(p.out_lo + o0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                        *reinterpret_cast<uint4*>(p.out_lo + o1) = make_uint4(ol[4], ol[5], ol[6], ol[7]);
                     }
                 }
             }
@@ -355,6 +380,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             long long* st = p.stats + (size_t)blockIdx.x * 8;
             st[4] = t_wait_full;
             st[5] = clock64() - t_begin;
+            st[7] = t_drain;
         }
     }
 

@@ -74,6 +74,23 @@ static CUtensorMap MakeMap2D(const void* base, int rows, int cols, int box_rows)
     return m;
 }
 
+// C8 activation tensor [chunks][R rows][8 ch] viewed as 4-D {8, R, 2, chunks} with an overlapping row split
+// (stride of dim 2 = 152 rows) so that ONE box {8, 152, 2, 8} covers 304 consecutive rows of 8 chunks and
+// lands in shared memory as [chunk][304 rows][16 B] (box dimensions are limited to 256).
+static CUtensorMap MakeActMap(const void* base, int R, int chunks) {
+    CUtensorMap m;
+    const int half = kSlabRows / 2;
+    cuuint64_t dims[4] = {8u, (cuuint64_t)(R - half), 2u, (cuuint64_t)chunks};
+    cuuint64_t strides[3] = {16u, (cuuint64_t)half * 16u, (cuuint64_t)R * 16u};
+    cuuint32_t box[4] = {8u, (cuuint32_t)half, 2u, 8u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = GetEncodeTiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled (activation) failed with code " + std::to_string((int)r)};
+    return m;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight blob: every device-resident parameter of one replica, packed once on the host.
 struct ConvLayout {
@@ -213,7 +230,8 @@ static std::vector<uint8_t> PackBlob(const HostNet& n, const BlobLayout& L) {
 struct ActBuf {
     __half* hi = nullptr;
     __half* lo = nullptr;
-    int pitch = 0;
+    int channels = 0;   // padded to a multiple of 64
+    int rows = 0;       // R
     CUtensorMap tm_hi, tm_lo;
 };
 
@@ -273,6 +291,8 @@ struct sb_engine {
     int rows_alloc = 0;
     int precision = SB_PRECISION_FP32_SPLIT;
     int collect_stats = 0;
+    int desc_swap = 0;
+    int conv_dbg = 0;
     int n_slots = 2;
     bool weights_ready = false;
     std::atomic<long long> launches{0};
@@ -311,16 +331,17 @@ static void FreeSlot(Slot& s) {
     s = Slot{};
 }
 
-static void AllocAct(ActBuf& a, int rows, int pitch, bool split) {
-    a.pitch = pitch;
-    const size_t bytes = (size_t)rows * pitch * sizeof(__half);
+static void AllocAct(ActBuf& a, int rows, int channels, bool split) {
+    a.channels = channels;
+    a.rows = rows;
+    const size_t bytes = (size_t)rows * channels * sizeof(__half);
     SB_CUDA(cudaMalloc(&a.hi, bytes));
     SB_CUDA(cudaMemset(a.hi, 0, bytes));
-    a.tm_hi = MakeMap2D(a.hi, rows, pitch, kSlabRows / 2);
+    a.tm_hi = MakeActMap(a.hi, rows, channels / 8);
     if (split) {
         SB_CUDA(cudaMalloc(&a.lo, bytes));
         SB_CUDA(cudaMemset(a.lo, 0, bytes));
-        a.tm_lo = MakeMap2D(a.lo, rows, pitch, kSlabRows / 2);
+        a.tm_lo = MakeActMap(a.lo, rows, channels / 8);
     } else {
         a.lo = a.hi;
         a.tm_lo = a.tm_hi;
@@ -468,7 +489,7 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
                                                           reinterpret_cast<const float*>(r.blob + c.L.bias),
                                                           res ? res->hi : nullptr, res ? res->lo : nullptr, s.mask,
                                                           c.L.cout, n_super * kSuperRows, e->geom.P, act, out.hi, out.lo,
-                                                          out.pitch);
+                                                          out.rows);
     } else {
         ConvParams p;
         p.out_hi = out.hi;
@@ -478,12 +499,15 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.bias = reinterpret_cast<const float*>(r.blob + c.L.bias);
         p.mask = s.mask;
         p.cout = c.L.cout;
-        p.out_pitch = out.pitch;
+        p.rows = out.rows;
         p.kh = c.L.kh;
         p.bn = c.L.bn;
         p.n_super = n_super;
         p.n_ntiles = c.L.ntiles;
         p.pitch = e->geom.P;
+        p.dbg = e->conv_dbg;
+        p.a_lbo = e->desc_swap ? 128 : kSlabRows * 16;
+        p.a_sbo = e->desc_swap ? kSlabRows * 16 : 128;
         p.err = s.d_err;
         p.stats = e->collect_stats ? s.d_stats : nullptr;
         const int items = n_super * c.L.ntiles;
@@ -512,7 +536,7 @@ static void LaunchHeadConv(sb_engine* e, Replica& r, Slot& s, const ActBuf& x, i
     const size_t smem = ((size_t)C * PV + PV) * sizeof(float);   // opt-in size set once in BuildReplica
     SB_DISPATCH_ACT(e->net_shape.act, ACT, (head_conv_kernel<PV, ACT><<<(n_rows + 127) / 128, 128, smem, s.stream>>>(
         x.hi, x.lo, Split(e), s.mask, reinterpret_cast<const float*>(r.blob + e->layout.head_wT),
-        reinterpret_cast<const float*>(r.blob + e->layout.head_b), C, x.pitch, n_rows, s.pv)));
+        reinterpret_cast<const float*>(r.blob + e->layout.head_b), C, x.rows, n_rows, s.pv)));
 }
 
 // Everything between "inputs are in d_in / d_meta" and "outputs are in d_out", on the slot's stream.
@@ -530,7 +554,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     {   // input planes -> canvas
         const int threads = n_rows * 8;
         unpack_planes_kernel<<<(threads + 255) / 256, 256, 0, s.stream>>>(s.d_in, (size_t)SB_PLANE_FLOATS, d_sizes, g, n,
-                                                                          n_rows, s.in.hi, s.in.lo, split, s.mask);
+                                                                          n_rows, s.in.rows, s.in.hi, s.in.lo, split, s.mask);
         SB_CUDA(cudaGetLastError());
         e->launches++;
     }
@@ -545,13 +569,13 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
             LaunchConv(e, r, s, r.conv2[b], *t, *u, nullptr, kIdentity, n, tm);
             const int n_rg = 256 / (C / 2);
             const size_t smem = ((size_t)2 * n_rg * C + 3 * C + se) * sizeof(float);
-            se_pool_fc_kernel<<<n, 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->pitch, se,
+            se_pool_fc_kernel<<<n, 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se,
                                                           F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
                                                           F(L.excite[b].b), act, s.gb);
             SB_CUDA(cudaGetLastError());
             const size_t total = (size_t)n_rows * (C / 8);
             SB_DISPATCH_ACT(act, ACT, (se_apply_kernel<ACT><<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(
-                                          u->hi, u->lo, x->hi, x->lo, split, s.mask, s.gb, g, C, u->pitch, n_rows)));
+                                          u->hi, u->lo, x->hi, x->lo, split, s.mask, s.gb, g, C, u->rows, n_rows)));
             SB_CUDA(cudaGetLastError());
             e->launches += 2;
         } else {
@@ -1022,16 +1046,16 @@ int sb_debug_read_trunk(sb_engine* e, int gpu, int slot, int sample, float* out)
         SB_CUDA(cudaSetDevice(r.device));
         SB_CUDA(cudaStreamSynchronize(s.stream));
         const Geom g = e->geom;
-        const int C = e->net_shape.channels, pitch = s.trunk->pitch, bs = s.sizes[sample];
-        std::vector<__half> hi((size_t)g.SS * pitch), lo((size_t)g.SS * pitch);
-        const size_t off = (size_t)g.row(sample, 0, 0) * pitch;
-        SB_CUDA(cudaMemcpy(hi.data(), s.trunk->hi + off, hi.size() * sizeof(__half), cudaMemcpyDeviceToHost));
-        SB_CUDA(cudaMemcpy(lo.data(), s.trunk->lo + off, lo.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+        const int C = e->net_shape.channels, R = s.trunk->rows, bs = s.sizes[sample];
+        const size_t total = (size_t)R * s.trunk->channels;
+        std::vector<__half> hi(total), lo(total);
+        SB_CUDA(cudaMemcpy(hi.data(), s.trunk->hi, total * sizeof(__half), cudaMemcpyDeviceToHost));
+        SB_CUDA(cudaMemcpy(lo.data(), s.trunk->lo, total * sizeof(__half), cudaMemcpyDeviceToHost));
         const bool split = Split(e);
         for (int c = 0; c < C; ++c)
             for (int y = 0; y < bs; ++y)
                 for (int x = 0; x < bs; ++x) {
-                    const size_t i = (size_t)(y * g.P + x) * pitch + c;
+                    const size_t i = act_index(g.row(sample, y, x), c, R);
                     out[(size_t)c * bs * bs + y * bs + x] = __half2float(hi[i]) + (split ? __half2float(lo[i]) : 0.f);
                 }
     } catch (const CudaError& ce) {
@@ -1057,6 +1081,14 @@ int sb_conv_stats(sb_engine* e, int gpu, int slot, long long* out, int capacity)
 
 int sb_set_option(sb_engine* e, const char* key, int value) {
     if (!e || !key) return SB_ERR_INVALID;
+    if (!std::strcmp(key, "desc_swap")) {
+        e->desc_swap = value ? 1 : 0;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "conv_dbg")) {
+        e->conv_dbg = value;
+        return SB_OK;
+    }
     if (!std::strcmp(key, "stats")) {
         e->collect_stats = value ? 1 : 0;
         return SB_OK;

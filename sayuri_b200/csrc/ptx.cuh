@@ -81,6 +81,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         : "memory");
 }
 
+// 4-D tiled load (used for the channel-blocked activation slabs).
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -139,6 +150,14 @@ constexpr uint64_t kUmmaDescSw128 = ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4
                                     ((uint64_t)2 << 61);
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return kUmmaDescSw128 | (uint64_t)((saddr & 0x3FFFFu) >> 4);
+}
+
+// K-major operand WITHOUT swizzle ("interleaved" core matrices, cute/atom/mma_traits_sm100.hpp: ((8,n),2):((1,SBO),LBO)
+// in 16-byte units): a core matrix is 8 rows x 16 bytes, contiguous (128 B); `sbo` bytes between row groups,
+// `lbo` bytes between the two core matrices adjacent in K.  Start addresses need only 16-byte alignment.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           ((uint64_t)1 << 46);
 }
 
 // Instruction descriptor for kind::f16, A=B=fp16, D=fp32, both K-major, dense.

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--net", default="10bx128")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--precision", type=int, default=0)
+ap.add_argument("--dbg", type=int, default=0)
 a = ap.parse_args()
 path = os.path.join(tempfile.gettempdir(), "stats_%s.bin" % a.net)
 synth.write_synth_net(path, a.net, seed=1)
@@ -21,11 +22,12 @@ x = synth.synth_positions(min(a.batch, 32), 19, seed=3).reshape(-1, engine.PLANE
 planes = [x[i % x.shape[0]] for i in range(a.batch)]
 pipe.batch_forward(0, planes, [19] * a.batch, [0] * a.batch)
 pipe.set_option("stats", 1)
+pipe.set_option("conv_dbg", a.dbg)
 pipe.batch_forward(0, planes, [19] * a.batch, [0] * a.batch)
 st = pipe.conv_stats(0, 0).astype(np.float64)
-names = ["mma_total", "wait_tmem_empty", "wait_slab", "wait_b", "epi_wait_full", "epi_total", "items", "-"]
-print("net %s batch %d precision %d: %d CTAs" % (a.net, a.batch, a.precision, st.shape[0]))
-for i, n in enumerate(names[:7]):
+names = ["mma_total", "wait_tmem_empty", "wait_slab", "wait_b", "epi_wait_full", "epi_total", "items", "epi_drain"]
+print("net %s batch %d precision %d dbg %d: %d CTAs" % (a.net, a.batch, a.precision, a.dbg, st.shape[0]))
+for i, n in enumerate(names):
     col = st[:, i]
     print("  %-16s mean %10.0f  min %10.0f  max %10.0f" % (n, col.mean(), col.min(), col.max()))
 busy = st[:, 0] - st[:, 1] - st[:, 2] - st[:, 3]
