@@ -1,0 +1,401 @@
+// conv3x3_tc2 — the CTA-pair (tcgen05 cta_group::2) form of conv3x3_tc: same math, same canvas / C8 layout, same
+// epilogue semantics, but two SMs of a TPC cooperate on one 256-row work item:
+//   * UMMA M = 256 (128 rows from each CTA), N = BN; each CTA stages only ITS HALF of every weight block
+//     ([BN/2][64], 8 KB): L2 -> SM weight traffic and the B-operand shared-memory reads per SM are halved (the
+//     single-CTA kernel was L2-bandwidth bound on weight streaming: ~25 B/clk/SM of a ~24 B/clk/SM budget);
+//   * each CTA owns ONE 128-row tile, so its 512 TMEM columns hold main + lo accumulators DOUBLE-buffered:
+//     the drain of item j overlaps the MMAs of item j+1 also on the split-precision rung, and the epilogue per
+//     item is half as long (4 warps x 128 rows), which shrinks the exposed tail;
+//   * 256 threads per CTA: every epilogue thread can hold its 128-column accumulator row without setmaxnreg.
+// Protocol (leader = cluster rank 0 issues every MMA): `full` barriers live in the leader and receive the TMA
+// transaction bytes of BOTH CTAs (the peer's loads signal the leader's barrier through its shared::cluster
+// address); `empty` / `tmem_full` barriers are local to each CTA and are signalled by multicast tcgen05.commit;
+// `tmem_empty` lives in the leader and collects the epilogue warps of both CTAs (remote mbarrier.arrive).
+// Reference lines replaced: see conv3x3_tc.cuh.
+#pragma once
+#include "common.cuh"
+#include "conv3x3_tc.cuh"
+#include "ptx.cuh"
+
+namespace sb {
+
+constexpr int kTileRows2 = 128;                              // rows per CTA per item
+constexpr int kSlabRows2 = kTileRows2 + 2 * kSlabMargin;     // 176
+
+template <bool SPLIT>
+struct Conv2Cfg {
+    static constexpr int kParts = SPLIT ? 2 : 1;
+    static constexpr int kSlabPartBytes = kSlabRows2 * 128;          // [8 chunks][176 rows][16 B]
+    static constexpr int kSlabBytes = kParts * kSlabPartBytes;
+    static constexpr int kNumSlabs = 3;
+    static constexpr int kBStageBytes = 64 * 128;                    // this CTA's half: up to 64 rows x 64 fp16
+    static constexpr int kNumBStages = 8;
+    static constexpr int kOffB = kNumSlabs * kSlabBytes;
+    static constexpr int kOffBar = kOffB + kNumBStages * kBStageBytes;
+    static constexpr int kOffBias = kOffBar + 512;
+    static constexpr int kSmemBytes = kOffBias + 256 * 4 + 1024;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kThreads = 384;
+    static_assert(kSlabPartBytes % 1024 == 0, "slab parts must keep the weight stages 1024-byte aligned");
+    static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+};
+
+// ---- cluster / cta_group::2 PTX ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address of THIS kernel's layout) inside CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion bytes are credited to a barrier given by its shared::cluster address
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+
+template <bool SPLIT, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                   const ConvParams p) {
+    using Cfg = Conv2Cfg<SPLIT>;
+    const int KH = p.kh, BN = p.bn, HB = p.bn >> 1;   // HB: weight rows staged by this CTA
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const uint32_t slab_addr = smem_base;
+    const uint32_t bst_addr = smem_base + Cfg::kOffB;
+    const uint32_t bar_addr = smem_base + Cfg::kOffBar;
+    const uint32_t a_full = bar_addr + 0, a_empty = bar_addr + 32;                // [3] each
+    const uint32_t tmem_full = bar_addr + 64, tmem_empty = bar_addr + 80;         // [2] each
+    const uint32_t b_full = bar_addr + 128, b_empty = bar_addr + 192;             // [8] each
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 256);
+    float* sbias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
+    constexpr uint32_t kNB = Cfg::kNumBStages, kNA = Cfg::kNumSlabs;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_items = p.n_super * p.n_ntiles;
+
+    for (int i = threadIdx.x; i < p.cout && i < 256; i += blockDim.x) sbias[i] = p.bias[i];
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < (int)kNA; ++i) {
+            mbar_init(a_full + 8 * i, 1);    // leader's own arrive.expect_tx (bytes of both CTAs)
+            mbar_init(a_empty + 8 * i, 1);   // one multicast commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tmem_full + 8 * i, 1);
+            mbar_init(tmem_empty + 8 * i, 16);  // 8 epilogue warps x 2 CTAs
+        }
+        for (int i = 0; i < (int)kNB; ++i) {
+            mbar_init(b_full + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, 1);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA_hi);
+        tma_prefetch_desc(&tmW_hi);
+        if (SPLIT) {
+            tma_prefetch_desc(&tmA_lo);
+            tma_prefetch_desc(&tmW_lo);
+        }
+    }
+    if (warp == 2) {
+        tmem_alloc2(smem_u32(tmem_ptr_smem), Cfg::kTmemCols);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // barriers of both CTAs are initialised before any remote arrive / TMA credit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 3) {
+        // ===================== activation-slab producer (own 128-row tile, +-24 rows) =====================
+        uint32_t it = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const int st = item / p.n_ntiles;
+            const int row_lo = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 - kSlabMargin;
+            for (int h = 0; h < KH; ++h, ++it) {
+                const uint32_t s = it % kNA, ph = (it / kNA) & 1u;
+                mbar_wait(a_empty + 8 * s, ph ^ 1u, p.err, 1);
+                if (elect_one()) {
+                    const uint32_t full0 = mapa_u32(a_full + 8 * s, 0);
+                    if (leader) mbar_arrive_expect_tx(a_full + 8 * s, 2u * Cfg::kSlabBytes);
+#pragma unroll
+                    for (int part = 0; part < Cfg::kParts; ++part) {
+                        tma2_load_3d(slab_addr + s * Cfg::kSlabBytes + part * Cfg::kSlabPartBytes, part ? &tmA_lo : &tmA_hi, 0,
+                                     row_lo, h * 8, full0);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 0) {
+        // ===================== weight-stage producer (own N-half of every block) =====================
+        uint32_t it = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const int nt = item % p.n_ntiles;
+            for (int h = 0; h < KH; ++h) {
+                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int part = 0; part < Cfg::kParts; ++part, ++it) {
+                        const uint32_t s = it % kNB, ph = (it / kNB) & 1u;
+                        mbar_wait(b_empty + 8 * s, ph ^ 1u, p.err, 2);
+                        if (elect_one()) {
+                            const uint32_t full0 = mapa_u32(b_full + 8 * s, 0);
+                            if (leader) mbar_arrive_expect_tx(b_full + 8 * s, 2u * (uint32_t)HB * 128u);
+                            tma2_load_2d(bst_addr + s * Cfg::kBStageBytes, part ? &tmW_lo : &tmW_hi, tap * (KH * 64) + h * 64,
+                                         nt * BN + (int)rank * HB, full0);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            // TMEM columns per CTA: stage as -> main at as*2*BN, lo at as*2*BN + BN (fp16 rung: main at as*BN).
+            const uint32_t idesc = umma_idesc_f16(256, BN);
+            constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
+            const bool stats = p.stats != nullptr;
+            uint32_t a_it = 0, b_it = 0, j = 0;
+            long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0, t0 = 0;
+            const long long t_begin = stats ? clock64() : 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
+                const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+                if (stats) t0 = clock64();
+                mbar_wait(tmem_empty + 8 * as, aph ^ 1u, p.err, 3);
+                if (stats) t_wait_tmem += clock64() - t0;
+                tc_fence_after();
+                const uint32_t d_main = tmem_base + (SPLIT ? as * 2 * BN : as * BN);
+                const uint32_t d_lo = d_main + BN;
+                for (int h = 0; h < KH; ++h, ++a_it) {
+                    const uint32_t s = a_it % kNA, sph = (a_it / kNA) & 1u;
+                    if (stats) t0 = clock64();
+                    mbar_wait(a_full + 8 * s, sph, p.err, 4);
+                    if (stats) t_wait_slab += clock64() - t0;
+                    tc_fence_after();
+                    const uint32_t a_hi = slab_addr + s * Cfg::kSlabBytes;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
+                        const uint32_t first = (h | tap) == 0 ? 0u : 1u;
+                        const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
+                        {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
+                            const uint32_t bs = b_it % kNB, bph = (b_it / kNB) & 1u;
+                            if (stats) t0 = clock64();
+                            mbar_wait(b_full + 8 * bs, bph, p.err, 5);
+                            if (stats) t_wait_b += clock64() - t0;
+                            tc_fence_after();
+                            const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma2_f16(d_main, ad0 + kAStep * k, bd0 + 2 * k, idesc, (k == 0) ? first : 1u);
+                                    if (SPLIT)
+                                        umma2_f16(d_lo, ad0 + (Cfg::kSlabPartBytes >> 4) + kAStep * k, bd0 + 2 * k, idesc,
+                                                  (k == 0) ? first : 1u);
+                                }
+                                umma2_commit_mc(b_empty + 8 * bs, 3);
+                            }
+                            __syncwarp();
+                            ++b_it;
+                        }
+                        if (SPLIT) {   // weights lo x activations hi -> lo accumulator
+                            const uint32_t bs = b_it % kNB, bph = (b_it / kNB) & 1u;
+                            if (stats) t0 = clock64();
+                            mbar_wait(b_full + 8 * bs, bph, p.err, 6);
+                            if (stats) t_wait_b += clock64() - t0;
+                            tc_fence_after();
+                            const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma2_f16(d_lo, ad0 + kAStep * k, bd0 + 2 * k, idesc, 1u);
+                                umma2_commit_mc(b_empty + 8 * bs, 3);
+                            }
+                            __syncwarp();
+                            ++b_it;
+                        }
+                    }
+                    if (elect_one()) umma2_commit_mc(a_empty + 8 * s, 3);
+                    __syncwarp();
+                }
+                if (elect_one()) umma2_commit_mc(tmem_full + 8 * as, 3);
+                __syncwarp();
+            }
+            if (stats && lane == 0) {
+                long long* st = p.stats + (size_t)cluster_id * 8;
+                st[0] = clock64() - t_begin;
+                st[1] = t_wait_tmem;
+                st[2] = t_wait_slab;
+                st[3] = t_wait_b;
+                st[6] = j;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 8 warps; warp%4 = TMEM lane quadrant, (warp-4)/4 = column half =====================
+        // Two warps per scheduler: each thread owns half an accumulator row (BN/2 columns, 64 registers), so
+        // the dependent ALU/MUFU chains of one warp are hidden behind the other.
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int HC = BN >> 1;                  // columns per thread (multiple of 16)
+        const int cbase = half * HC;
+        const bool stats = p.stats != nullptr;
+        uint32_t j = 0;
+        long long t_wait_full = 0, t_drain = 0;
+        const long long t_begin = stats ? clock64() : 0;
+        const uint32_t empty0 = mapa_u32(tmem_empty, 0);   // leader's tmem_empty[0]; [1] is +8
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
+            const int st = item / p.n_ntiles, nt = item % p.n_ntiles;
+            const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+            const long long t0 = stats ? clock64() : 0;
+            mbar_wait(tmem_full + 8 * as, aph, p.err, 7);
+            if (stats) t_wait_full += clock64() - t0;
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_main = lane_base + (SPLIT ? as * 2 * BN : as * BN) + cbase;
+            const uint32_t t_lo = t_main + BN;
+            float acc[64];
+            const long long t_d0 = stats ? clock64() : 0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g * 16 < HC) {
+                    uint32_t r[16];
+                    tmem_ld16(t_main + g * 16, r);
+                    if (SPLIT) {
+                        uint32_t r2[16];
+                        tmem_ld16(t_lo + g * 16, r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(empty0 + 8 * as);   // accumulator stage is free again
+            if (stats) t_drain += clock64() - t_d0;
+
+            const int row = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 + q * 32 + lane;
+            const bool live = p.mask[row] != 0;
+            const size_t chunk_stride = (size_t)p.rows * 8;
+            const size_t off = act_index(row, nt * BN + cbase, p.rows);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g * 16 < HC) {
+                    const int c0 = g * 16;
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[nt * BN + cbase + c0 + i];
+                    const size_t o0 = off + (size_t)(c0 >> 3) * chunk_stride, o1 = o0 + chunk_stride;
+                    if (live && p.res_hi != nullptr) {
+                        const uint4 a0 = *reinterpret_cast<const uint4*>(p.res_hi + o0);
+                        const uint4 a1 = *reinterpret_cast<const uint4*>(p.res_hi + o1);
+                        const __half* hh0 = reinterpret_cast<const __half*>(&a0);
+                        const __half* hh1 = reinterpret_cast<const __half*>(&a1);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            v[i] += __half2float(hh0[i]);
+                            v[8 + i] += __half2float(hh1[i]);
+                        }
+                        if (SPLIT) {
+                            const uint4 b0 = *reinterpret_cast<const uint4*>(p.res_lo + o0);
+                            const uint4 b1 = *reinterpret_cast<const uint4*>(p.res_lo + o1);
+                            const __half* ll0 = reinterpret_cast<const __half*>(&b0);
+                            const __half* ll1 = reinterpret_cast<const __half*>(&b1);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                v[i] += __half2float(ll0[i]);
+                                v[8 + i] += __half2float(ll1[i]);
+                            }
+                        }
+                    }
+                    uint32_t oh[8], ol[8];
+                    activate16<ACT>(v);
+                    if (!live) {   // select, not multiply: garbage rows may hold NaN
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                    }
+                    split16(v, oh, ol, SPLIT);
+                    *reinterpret_cast<uint4*>(p.out_hi + o0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                    *reinterpret_cast<uint4*>(p.out_hi + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+                    if (SPLIT) {
+                        *reinterpret_cast<uint4*>(p.out_lo + o0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                        *reinterpret_cast<uint4*>(p.out_lo + o1) = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+                    }
+                }
+            }
+        }
+        if (stats && leader && warp == 4 && lane == 0) {
+            long long* st = p.stats + (size_t)cluster_id * 8;
+            st[4] = t_wait_full;
+            st[5] = clock64() - t_begin;
+            st[7] = t_drain;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // nobody leaves (or frees TMEM) while the peer may still read this CTA's memory
+    if (warp == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+}
+
+}  // namespace sb

@@ -21,6 +21,7 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "conv3x3_tc.cuh"
+#include "conv3x3_tc2.cuh"
 #include "host_net.h"
 
 namespace sb {
@@ -88,6 +89,20 @@ static CUtensorMap MakeActMap(const void* base, int R, int chunks) {
                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled (activation) failed with code " + std::to_string((int)r)};
+    return m;
+}
+
+// Same tensor as a plain 3-D {8, R, chunks} view with a 176-row box: the per-CTA slab of the CTA-pair kernel.
+static CUtensorMap MakeActMap3(const void* base, int R, int chunks) {
+    CUtensorMap m;
+    cuuint64_t dims[3] = {8u, (cuuint64_t)R, (cuuint64_t)chunks};
+    cuuint64_t strides[2] = {16u, (cuuint64_t)R * 16u};
+    cuuint32_t box[3] = {8u, (cuuint32_t)kSlabRows2, 8u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = GetEncodeTiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled (activation, pair kernel) failed with code " + std::to_string((int)r)};
     return m;
 }
 
@@ -232,7 +247,8 @@ struct ActBuf {
     __half* lo = nullptr;
     int channels = 0;   // padded to a multiple of 64
     int rows = 0;       // R
-    CUtensorMap tm_hi, tm_lo;
+    CUtensorMap tm_hi, tm_lo;       // 304-row slabs (single-CTA kernel)
+    CUtensorMap tm3_hi, tm3_lo;     // 176-row slabs (CTA-pair kernel)
 };
 
 struct Slot {
@@ -262,7 +278,8 @@ struct Slot {
 
 struct DevConv {
     ConvLayout L;
-    CUtensorMap tm_hi, tm_lo;
+    CUtensorMap tm_hi, tm_lo;     // box [bn][64]
+    CUtensorMap tm2_hi, tm2_lo;   // box [bn/2][64]: one CTA's half in the CTA-pair kernel
     float* wT = nullptr;  // fp32 [9*cinp][cout], SIMT debug only
 };
 
@@ -293,6 +310,7 @@ struct sb_engine {
     int collect_stats = 0;
     int desc_swap = 0;
     int conv_dbg = 0;
+    int conv_impl = 2;   // 1 = single-CTA conv3x3_tc, 2 = CTA-pair conv3x3_tc2 (default)
     int n_slots = 2;
     bool weights_ready = false;
     std::atomic<long long> launches{0};
@@ -338,10 +356,13 @@ static void AllocAct(ActBuf& a, int rows, int channels, bool split) {
     SB_CUDA(cudaMalloc(&a.hi, bytes));
     SB_CUDA(cudaMemset(a.hi, 0, bytes));
     a.tm_hi = MakeActMap(a.hi, rows, channels / 8);
+    a.tm3_hi = MakeActMap3(a.hi, rows, channels / 8);
+    a.tm3_lo = a.tm3_hi;
     if (split) {
         SB_CUDA(cudaMalloc(&a.lo, bytes));
         SB_CUDA(cudaMemset(a.lo, 0, bytes));
         a.tm_lo = MakeActMap(a.lo, rows, channels / 8);
+        a.tm3_lo = MakeActMap3(a.lo, rows, channels / 8);
     } else {
         a.lo = a.hi;
         a.tm_lo = a.tm_hi;
@@ -392,6 +413,8 @@ static void AllocSlots(sb_engine* e, Replica& r) {
 static void MakeConvMaps(const Replica& r, DevConv& c) {
     c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, 9 * c.L.cinp, c.L.bn);
     c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, 9 * c.L.cinp, c.L.bn);
+    c.tm2_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, 9 * c.L.cinp, c.L.bn / 2);
+    c.tm2_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, 9 * c.L.cinp, c.L.bn / 2);
 }
 
 // fp32 transposed weights for the SIMT cross-check kernel, derived from the packed hi/lo matrices.
@@ -445,6 +468,8 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
             SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<32, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 32 + 32) * 4));
             SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<48, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 48 + 48) * 4));
             SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<64, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 64 + 64) * 4));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes));
             SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::kSmemBytes));
             SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::kSmemBytes)));
     }
@@ -512,7 +537,16 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.stats = e->collect_stats ? s.d_stats : nullptr;
         const int items = n_super * c.L.ntiles;
         const int grid = std::min(items, r.sm_count);
-        if (Split(e)) {
+        if (e->conv_impl == 2) {
+            const int grid2 = 2 * std::min(items, r.sm_count / 2);
+            if (Split(e)) {
+                SB_DISPATCH_ACT(act, ACT, (conv3x3_tc2_kernel<true, ACT><<<grid2, 384, Conv2Cfg<true>::kSmemBytes, s.stream>>>(
+                                              in.tm3_hi, in.tm3_lo, c.tm2_hi, c.tm2_lo, p)));
+            } else {
+                SB_DISPATCH_ACT(act, ACT, (conv3x3_tc2_kernel<false, ACT><<<grid2, 384, Conv2Cfg<false>::kSmemBytes, s.stream>>>(
+                                              in.tm3_hi, in.tm3_hi, c.tm2_hi, c.tm2_hi, p)));
+            }
+        } else if (Split(e)) {
             SB_DISPATCH_ACT(act, ACT, (conv3x3_tc_kernel<true, ACT><<<grid, 384, ConvCfg<true>::kSmemBytes, s.stream>>>(
                                           in.tm_hi, in.tm_lo, c.tm_hi, c.tm_lo, p)));
         } else {
@@ -1083,6 +1117,11 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     if (!e || !key) return SB_ERR_INVALID;
     if (!std::strcmp(key, "desc_swap")) {
         e->desc_swap = value ? 1 : 0;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "conv_impl")) {
+        if (value != 1 && value != 2) return Fail(e, SB_ERR_INVALID, "conv_impl must be 1 or 2");
+        e->conv_impl = value;
         return SB_OK;
     }
     if (!std::strcmp(key, "conv_dbg")) {

@@ -14,17 +14,20 @@ ap.add_argument("--net", default="10bx128")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--precision", type=int, default=0)
 ap.add_argument("--dbg", type=int, default=0)
+ap.add_argument("--impl", type=int, default=1)
 a = ap.parse_args()
 path = os.path.join(tempfile.gettempdir(), "stats_%s.bin" % a.net)
 synth.write_synth_net(path, a.net, seed=1)
 pipe = engine.B200ForwardPipe().initialize(path, 19, a.batch, gpus=[0], precision=a.precision)
 x = synth.synth_positions(min(a.batch, 32), 19, seed=3).reshape(-1, engine.PLANE_FLOATS)
 planes = [x[i % x.shape[0]] for i in range(a.batch)]
+pipe.set_option("conv_impl", a.impl)
 pipe.batch_forward(0, planes, [19] * a.batch, [0] * a.batch)
 pipe.set_option("stats", 1)
 pipe.set_option("conv_dbg", a.dbg)
 pipe.batch_forward(0, planes, [19] * a.batch, [0] * a.batch)
 st = pipe.conv_stats(0, 0).astype(np.float64)
+st = st[st[:, 6] > 0]
 names = ["mma_total", "wait_tmem_empty", "wait_slab", "wait_b", "epi_wait_full", "epi_total", "items", "epi_drain"]
 print("net %s batch %d precision %d dbg %d: %d CTAs" % (a.net, a.batch, a.precision, a.dbg, st.shape[0]))
 for i, n in enumerate(names):

@@ -28,7 +28,7 @@ SHAPES = {
     "20bx256": (20, 256, 32, 32, None),
     "golden": None,
 }
-MODES = {"simt": (2, 0), "split": (0, 0), "fp16": (1, 0), "split_swap": (0, 1)}
+MODES = {"simt": (2, 0), "split": (0, 0), "fp16": (1, 0), "split2": (0, 2), "fp16_2": (1, 2)}
 
 
 def run_case(shape, mode, n, seed):
@@ -47,8 +47,8 @@ def run_case(shape, mode, n, seed):
     planes = [synth.synth_positions(1, bs, seed=seed + i)[0].ravel() for i, bs in enumerate(sizes)]
     offsets = [i % 5 for i in range(n)]
     pipe = engine.B200ForwardPipe().initialize(path, 19, max(n, 4), gpus=[0], precision=prec)
-    if bo:
-        pipe.set_option("desc_swap", 1)
+    if bo == 2:
+        pipe.set_option("conv_impl", 2)
     out = pipe.batch_forward(0, planes, sizes, offsets)
     orc = Oracle(path)
     res = {"shape": shape, "mode": mode, "n": n, "trunk": 0.0, "prob": 0.0, "own": 0.0, "misc": 0.0, "scale": 0.0}
