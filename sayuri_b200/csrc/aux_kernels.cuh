@@ -64,6 +64,49 @@ __global__ void unpack_planes_kernel(const float* __restrict__ planes, size_t sa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-sample pooling over a C8 tensor: sum and max of every channel over the sample's board cells.
+// One CTA of 256 threads; warp w takes channel chunks w, w+8, ...; its lanes stride the sample's rows, so every
+// load is a coalesced run of 16-byte pieces; a fixed shuffle tree finishes the reduction (batch-invariant order).
+__device__ __forceinline__ void pool_sample_c8(const __half* __restrict__ hi, const __half* __restrict__ lo, bool split,
+                                               const uint8_t* __restrict__ mask, int row0, int SS, int C, int R,
+                                               float* s_sum, float* s_max) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int chunk = warp; chunk < (C >> 3); chunk += 8) {
+        float s[8], m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s[i] = 0.f;
+            m[i] = -5000.f;   // "crazy negative value", se_unit.cc:22
+        }
+        for (int r = lane; r < SS; r += 32) {
+            if (!mask[row0 + r]) continue;
+            float v[8];
+            const size_t off = act_index(row0 + r, chunk * 8, R);
+            load8(hi + off, lo + off, split, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s[i] += v[i];
+                m[i] = fmaxf(m[i], v[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+                m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], o));
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s_sum[chunk * 8 + i] = s[i];
+                s_max[chunk * 8 + i] = m[i];
+            }
+        }
+    }
+}
+
 // se_pool_fc: GlobalPooling<false> + squeeze FC + excite FC of SEUnit::Forward
 // (/root/reference/src/neural/blas/se_unit.cc:9-37,70-90; GPU twins cuda_kernels.cu:241-321 and the
 // cuBLAS FCs cuda_layers.cc:975-1017).  One CTA (256 threads) per sample; writes sigmoid(gamma) and
@@ -76,48 +119,19 @@ se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_
     extern __shared__ float sm[];
     const int b = blockIdx.x;
     const int bs = board_sizes[b];
-    const int halfC = C >> 1;
-    const int n_rg = 256 / halfC;                 // row groups
-    float* part_sum = sm;                          // [n_rg][C]
-    float* part_max = sm + n_rg * C;               // [n_rg][C]
-    float* pool = part_max + n_rg * C;             // [3C]
-    float* hid = pool + 3 * C;                     // [se]
+    float* s_sum = sm;              // [C]
+    float* s_max = sm + C;          // [C]
+    float* pool = s_max + C;        // [3C]
+    float* hid = pool + 3 * C;      // [se]
     const int tid = threadIdx.x;
-    const int rg = tid / halfC, c2 = tid - rg * halfC;
-    if (rg < n_rg) {
-        float s0 = 0.f, s1 = 0.f, m0 = -5000.f, m1 = -5000.f;   // "crazy negative value", se_unit.cc:22
-        const int row0 = kGuardRows + b * g.SS;
-        for (int r = rg; r < g.SS; r += n_rg) {
-            if (!mask[row0 + r]) continue;
-            const size_t off = act_index(row0 + r, 2 * c2, R);
-            float2 v = __half22float2(*reinterpret_cast<const __half2*>(u_hi + off));
-            if (split) {
-                const float2 l = __half22float2(*reinterpret_cast<const __half2*>(u_lo + off));
-                v.x += l.x;
-                v.y += l.y;
-            }
-            s0 += v.x;
-            s1 += v.y;
-            m0 = fmaxf(m0, v.x);
-            m1 = fmaxf(m1, v.y);
-        }
-        part_sum[rg * C + 2 * c2] = s0;
-        part_sum[rg * C + 2 * c2 + 1] = s1;
-        part_max[rg * C + 2 * c2] = m0;
-        part_max[rg * C + 2 * c2 + 1] = m1;
-    }
+    pool_sample_c8(u_hi, u_lo, split, mask, kGuardRows + b * g.SS, g.SS, C, R, s_sum, s_max);
     __syncthreads();
     const float b_coeff = ((float)bs - 14.0f) / 10.f;   // se_unit.h:17-20
     for (int c = tid; c < C; c += 256) {
-        float s = 0.f, m = -5000.f;
-        for (int k = 0; k < n_rg; ++k) {
-            s += part_sum[k * C + c];
-            m = fmaxf(m, part_max[k * C + c]);
-        }
-        const float mean = s / (float)(bs * bs);
+        const float mean = s_sum[c] / (float)(bs * bs);
         pool[c] = mean;
         pool[C + c] = mean * b_coeff;
-        pool[2 * C + c] = m;
+        pool[2 * C + c] = s_max[c];
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -167,56 +181,8 @@ __global__ void se_apply_kernel(__half* __restrict__ u_hi, __half* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// head_conv: the two head-entry 1x1 convolutions fused into one pass over the trunk:
-//   pv[row][0:P]   = act(Wp x + bp)   (policy, blas_forward_pipe.cc:430-442)
-//   pv[row][P:P+V] = act(Wv x + bv)   (value,  blas_forward_pipe.cc:513-522)
-// fp32 out, zero on non-board rows.  One thread per canvas row; W^T [C][PV] broadcast from shared memory.
-template <int PV, int ACT>
-__global__ void __launch_bounds__(128)
-head_conv_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, bool split,
-                 const uint8_t* __restrict__ mask, const float* __restrict__ wT, const float* __restrict__ bias,
-                 int C, int R, int n_rows, float* __restrict__ pv) {
-    extern __shared__ float sw[];   // [C][PV] + [PV]
-    for (int i = threadIdx.x; i < C * PV; i += blockDim.x) sw[i] = wT[i];
-    float* sb_ = sw + C * PV;
-    for (int i = threadIdx.x; i < PV; i += blockDim.x) sb_[i] = bias[i];
-    __syncthreads();
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    const int row = kGuardRows + r;
-    float acc[PV];
-    const bool live = mask[row] != 0;
-    if (live) {
-#pragma unroll
-        for (int j = 0; j < PV; ++j) acc[j] = sb_[j];
-        for (int c0 = 0; c0 < C; c0 += 8) {
-            float x[8];
-            const size_t off = act_index(row, c0, R);
-            load8(x_hi + off, x_lo + off, split, x);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4* w4 = reinterpret_cast<const float4*>(sw + (c0 + i) * PV);
-#pragma unroll
-                for (int j4 = 0; j4 < PV / 4; ++j4) {
-                    const float4 w = w4[j4];
-                    acc[4 * j4 + 0] += x[i] * w.x;
-                    acc[4 * j4 + 1] += x[i] * w.y;
-                    acc[4 * j4 + 2] += x[i] * w.z;
-                    acc[4 * j4 + 3] += x[i] * w.w;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < PV; ++j) acc[j] = activate_t<ACT>(acc[j]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < PV; ++j) acc[j] = 0.f;
-    }
-    float4* o = reinterpret_cast<float4*>(pv + (size_t)row * PV);
-#pragma unroll
-    for (int j4 = 0; j4 < PV / 4; ++j4) o[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
-}
-
+// (The two head-entry 1x1 convolutions, blas_forward_pipe.cc:430-442,513-522, run as ONE single-tap launch of
+// the tensor-core conv kernel with the policy and value filters concatenated: pv[row][0:P] policy, [P:P+V] value.)
 struct HeadWeights {
     const float* p_inter_w;  // [P][3P]
     const float* p_inter_b;  // [P]
@@ -234,48 +200,32 @@ struct HeadWeights {
 
 // head_pool_fc: GlobalPooling<false> of the policy planes, GlobalPooling<true> of the value planes
 // (se_unit.cc:9-68) and the four small FCs (blas_forward_pipe.cc:473-481,501-507,524-532,549-555).
-// One CTA (256 threads) per sample.  Writes pint[n][P], pass5[n][5], misc15[n][15].
+// One CTA (256 threads) per sample.  pv is the C8 tensor written by the head 1x1 conv (P policy + V value
+// channels).  Writes pint[n][P], pass5[n][5], misc15[n][15].
 __global__ void __launch_bounds__(256)
-head_pool_fc_kernel(const float* __restrict__ pv, const uint8_t* __restrict__ mask,
-                    const int* __restrict__ board_sizes, Geom g, int P, int V, HeadWeights hw, int act,
-                    float* __restrict__ pint, float* __restrict__ pass5, float* __restrict__ misc15) {
+head_pool_fc_kernel(const __half* __restrict__ pv_hi, const __half* __restrict__ pv_lo, bool split, int R,
+                    const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int P, int V,
+                    HeadWeights hw, int act, float* __restrict__ pint, float* __restrict__ pass5,
+                    float* __restrict__ misc15) {
     extern __shared__ float sm[];
     const int PV = P + V;
     const int b = blockIdx.x, bs = board_sizes[b];
-    const int n_rg = 256 / PV;
-    float* part_sum = sm;                    // [n_rg][PV]
-    float* part_max = sm + n_rg * PV;        // [n_rg][PV]
-    float* ppool = part_max + n_rg * PV;     // [3P]
+    float* s_sum = sm;                       // [PV]
+    float* s_max = sm + PV;                  // [PV]
+    float* ppool = s_max + PV;               // [3P]
     float* vpool = ppool + 3 * P;            // [3V]
     float* spint = vpool + 3 * V;            // [P]
     float* svint = spint + P;                // [3V]
     const int tid = threadIdx.x;
-    const int rg = tid / PV, c = tid - rg * PV;
-    const int row0 = kGuardRows + b * g.SS;
-    if (rg < n_rg) {
-        float s = 0.f, m = -5000.f;
-        for (int r = rg; r < g.SS; r += n_rg) {
-            if (!mask[row0 + r]) continue;
-            const float v = pv[(size_t)(row0 + r) * PV + c];
-            s += v;
-            m = fmaxf(m, v);
-        }
-        part_sum[rg * PV + c] = s;
-        part_max[rg * PV + c] = m;
-    }
+    pool_sample_c8(pv_hi, pv_lo, split, mask, kGuardRows + b * g.SS, g.SS, PV, R, s_sum, s_max);
     __syncthreads();
     const float b_diff = (float)bs - 14.0f;
     if (tid < PV) {
-        float s = 0.f, m = -5000.f;
-        for (int k = 0; k < n_rg; ++k) {
-            s += part_sum[k * PV + tid];
-            m = fmaxf(m, part_max[k * PV + tid]);
-        }
-        const float mean = s / (float)(bs * bs);
+        const float mean = s_sum[tid] / (float)(bs * bs);
         if (tid < P) {
             ppool[tid] = mean;
             ppool[P + tid] = mean * (b_diff / 10.f);
-            ppool[2 * P + tid] = m;
+            ppool[2 * P + tid] = s_max[tid];
         } else {
             const int v = tid - P;
             vpool[v] = mean;
@@ -329,23 +279,32 @@ constexpr int kOutFloats = 2 * kMaxIntersections + 8;
 // batch_forward_pipe.cc:48-67) and zero-filled up to 361, misc values are gathered to
 // {pass[offset], wdl0..2, stm(3), final_score(8), q_error(13), score_error(14)}.
 __global__ void __launch_bounds__(384)
-head_out_kernel(const float* __restrict__ pv, const int* __restrict__ board_sizes,
-                const int* __restrict__ offsets, Geom g, int P, int V, HeadWeights hw,
+head_out_kernel(const __half* __restrict__ pv_hi, const __half* __restrict__ pv_lo, bool split, int R,
+                const int* __restrict__ board_sizes, const int* __restrict__ offsets, Geom g, int P, int V, HeadWeights hw,
                 const float* __restrict__ pint, const float* __restrict__ pass5,
                 const float* __restrict__ misc15, float* __restrict__ out) {
     const int b = blockIdx.x, i = threadIdx.x;
     const int bs = board_sizes[b], off = offsets[b];
-    const int PV = P + V;
     float* o = out + (size_t)b * kOutFloats;
     if (i < kMaxIntersections) {
         float prob = 0.f, own = 0.f;
         if (i < bs * bs) {
             const int y = i / bs, x = i - y * bs;
-            const float* row = pv + (size_t)g.row(b, y, x) * PV;
+            const int row = g.row(b, y, x);
             prob = hw.prob_b[off];
-            for (int c = 0; c < P; ++c) prob += hw.prob_w[off * P + c] * (row[c] + pint[(size_t)b * P + c]);
             own = hw.own_b[0];
-            for (int c = 0; c < V; ++c) own += hw.own_w[c] * row[P + c];
+            for (int c0 = 0; c0 < P + V; c0 += 8) {     // P and V are multiples of 8: a chunk is all-policy or all-value
+                float v[8];
+                const size_t idx = act_index(row, c0, R);
+                load8(pv_hi + idx, pv_lo + idx, split, v);
+                if (c0 < P) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) prob += hw.prob_w[off * P + c0 + k] * (v[k] + pint[(size_t)b * P + c0 + k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) own += hw.own_w[c0 - P + k] * v[k];
+                }
+            }
         }
         o[i] = prob;
         o[kMaxIntersections + i] = own;
@@ -376,7 +335,7 @@ __global__ void __launch_bounds__(256)
 conv3x3_simt_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, bool split, int cinp,
                     const float* __restrict__ wT, const float* __restrict__ bias,
                     const __half* __restrict__ res_hi, const __half* __restrict__ res_lo,
-                    const uint8_t* __restrict__ mask, int cout, int n_rows, int pitch, int act,
+                    const uint8_t* __restrict__ mask, int cout, int n_rows, int pitch, int ntaps, int act,
                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int R) {
     const int co = blockIdx.y * 32 + threadIdx.x;
     const int r = blockIdx.x * 8 + threadIdx.y;
@@ -386,8 +345,8 @@ conv3x3_simt_kernel(const __half* __restrict__ in_hi, const __half* __restrict__
     float v = 0.f;
     if (mask[row]) {
         float acc = 0.f;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int src = row + (tap / 3 - 1) * pitch + (tap % 3 - 1);
+        for (int tap = 0; tap < ntaps; ++tap) {
+            const int src = ntaps == 1 ? row : row + (tap / 3 - 1) * pitch + (tap % 3 - 1);
             const float* w = wT + (size_t)tap * cinp * cout + co;
             for (int c = 0; c < cinp; ++c) {
                 const size_t ai = act_index(src, c, R);

@@ -43,6 +43,7 @@ struct ConvParams {
     int n_super;             // number of 256-row work items along M
     int n_ntiles;            // cout / bn
     int pitch;               // P = N + 1
+    int ntaps;               // 9 = 3x3 convolution, 1 = 1x1 convolution (centre tap only)
     int dbg;                 // ablation bits for profiling only: 1 skip stores, 2 skip activation+split math, 4 skip drain
     int a_lbo, a_sbo;        // A-operand descriptor strides in bytes (K-adjacent / row-group-adjacent core matrices)
     int* err;                // device int, receives a site code if a barrier wait times out
@@ -158,7 +159,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int nt = item % p.n_ntiles;
             for (int h = 0; h < KH; ++h) {
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int tap = 0; tap < p.ntaps; ++tap) {
 #pragma unroll
                     for (int part = 0; part < Cfg::kParts; ++part, ++it) {
                         const uint32_t s = it % kNB, ph = (it / kNB) & 1u;
@@ -199,8 +200,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 if (stats) t_wait_slab += clock64() - t0;
                 tc_fence_after();
                 const uint32_t a_hi = slab_addr + s * Cfg::kSlabBytes;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const int shift = p.ntaps == 1 ? 0 : (tap / 3 - 1) * p.pitch + (tap % 3 - 1);   // 1 tap = 1x1 convolution
                     const uint32_t first = (h | tap) == 0 ? 0u : 1u;
                     // A: no-swizzle core matrices, row r of chunk j at j*304*16 + r*16; a tap is a +16*shift byte offset
                     const uint64_t ad_t0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, (uint32_t)p.a_lbo, (uint32_t)p.a_sbo);

@@ -190,7 +190,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int item = cluster_id; item < n_items; item += n_clusters) {
             const int nt = item % p.n_ntiles;
             for (int h = 0; h < KH; ++h) {
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int tap = 0; tap < p.ntaps; ++tap) {
 #pragma unroll
                     for (int part = 0; part < Cfg::kParts; ++part, ++it) {
                         const uint32_t s = it % kNB, ph = (it / kNB) & 1u;
@@ -231,8 +231,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     if (stats) t_wait_slab += clock64() - t0;
                     tc_fence_after();
                     const uint32_t a_hi = slab_addr + s * Cfg::kSlabBytes;
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const int shift = p.ntaps == 1 ? 0 : (tap / 3 - 1) * p.pitch + (tap % 3 - 1);   // 1 tap = 1x1 convolution
                         const uint32_t first = (h | tap) == 0 ? 0u : 1u;
                         const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
                         {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
@@ -292,8 +292,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         // the dependent ALU/MUFU chains of one warp are hidden behind the other.
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
-        const int HC = BN >> 1;                  // columns per thread (multiple of 16)
-        const int cbase = half * HC;
+        const int c_split = ((BN >> 1) + 15) & ~15;            // column split, rounded to the 16-column ld granule
+        const int cbase = half ? c_split : 0;
+        const int HC = half ? BN - c_split : c_split;          // columns of this thread (multiple of 16, may be 0)
         const bool stats = p.stats != nullptr;
         uint32_t j = 0;
         long long t_wait_full = 0, t_drain = 0;

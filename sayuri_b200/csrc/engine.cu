@@ -109,7 +109,7 @@ static CUtensorMap MakeActMap3(const void* base, int R, int chunks) {
 // ------------------------------------------------------------------------------------------------
 // Weight blob: every device-resident parameter of one replica, packed once on the host.
 struct ConvLayout {
-    int cin = 0, cinp = 0, cout = 0, kh = 0, bn = 0, ntiles = 0;
+    int cin = 0, cinp = 0, cout = 0, kh = 0, bn = 0, ntiles = 0, taps = 9;
     size_t w_hi = 0, w_lo = 0, bias = 0;  // byte offsets into the blob
 };
 struct FcLayout {
@@ -120,7 +120,7 @@ struct BlobLayout {
     ConvLayout input;
     std::vector<ConvLayout> conv1, conv2;
     std::vector<FcLayout> squeeze, excite;  // per block (unused entries when se_size == 0)
-    size_t head_wT = 0, head_b = 0;         // [C][P+V], [P+V]
+    ConvLayout head;                        // policy + value head-entry 1x1 convs as one single-tap conv, cout = P + V
     FcLayout p_inter, pass, v_inter, misc;
     size_t prob_w = 0, prob_b = 0, own_w = 0, own_b = 0;
     size_t bytes = 0;
@@ -132,15 +132,16 @@ static size_t Take(size_t& cursor, size_t bytes) {
     return at;
 }
 
-static ConvLayout LayConv(size_t& cur, int cin, int cout) {
+static ConvLayout LayConv(size_t& cur, int cin, int cout, int taps = 9) {
     ConvLayout c;
+    c.taps = taps;
     c.cin = cin;
     c.cinp = RoundUp(cin, 64);
     c.cout = cout;
     c.kh = c.cinp / 64;
     c.bn = cout <= 128 ? cout : cout / 2;
     c.ntiles = cout / c.bn;
-    const size_t mat = (size_t)cout * 9 * c.cinp * sizeof(__half);
+    const size_t mat = (size_t)cout * taps * c.cinp * sizeof(__half);
     c.w_hi = Take(cur, mat);
     c.w_lo = Take(cur, mat);
     c.bias = Take(cur, (size_t)cout * sizeof(float));
@@ -171,8 +172,7 @@ static BlobLayout ComputeLayout(int blocks, int C, int P, int V, const std::vect
             L.excite[b] = LayFc(cur, se[b], 2 * C);
         }
     }
-    L.head_wT = Take(cur, (size_t)C * (P + V) * sizeof(float));
-    L.head_b = Take(cur, (size_t)(P + V) * sizeof(float));
+    L.head = LayConv(cur, C, P + V, 1);
     L.p_inter = LayFc(cur, 3 * P, P);
     L.pass = LayFc(cur, P, 5);
     L.v_inter = LayFc(cur, 3 * V, 3 * V);
@@ -189,12 +189,12 @@ static BlobLayout ComputeLayout(int blocks, int C, int P, int V, const std::vect
 static void PackConv(const HostConv& hc, const ConvLayout& L, uint8_t* blob) {
     __half* hi = reinterpret_cast<__half*>(blob + L.w_hi);
     __half* lo = reinterpret_cast<__half*>(blob + L.w_lo);
-    const size_t K = (size_t)9 * L.cinp;
+    const size_t K = (size_t)L.taps * L.cinp;
     for (int o = 0; o < L.cout; ++o) {
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < L.taps; ++tap) {
             for (int c = 0; c < L.cinp; ++c) {
                 float w = 0.f;
-                if (c < L.cin) w = hc.w[((size_t)o * L.cin + c) * 9 + tap];
+                if (c < L.cin) w = hc.w[((size_t)o * L.cin + c) * L.taps + tap];
                 const __half h = __float2half_rn(w);
                 const __half l = __float2half_rn(w - __half2float(h));
                 hi[(size_t)o * K + (size_t)tap * L.cinp + c] = h;
@@ -221,15 +221,18 @@ static std::vector<uint8_t> PackBlob(const HostNet& n, const BlobLayout& L) {
             PackFc(n.tower[b].excite, L.excite[b], p);
         }
     }
-    const int C = n.channels, P = n.P, V = n.V, PV = P + V;
-    float* wT = reinterpret_cast<float*>(p + L.head_wT);
-    float* hb = reinterpret_cast<float*>(p + L.head_b);
-    for (int c = 0; c < C; ++c) {
-        for (int j = 0; j < P; ++j) wT[(size_t)c * PV + j] = n.p_hd_conv.w[(size_t)j * C + c];
-        for (int j = 0; j < V; ++j) wT[(size_t)c * PV + P + j] = n.v_hd_conv.w[(size_t)j * C + c];
+    const int C = n.channels, P = n.P, V = n.V;
+    {   // policy and value head-entry filters concatenated along the output dimension
+        HostConv head;
+        head.in = C;
+        head.out = P + V;
+        head.k = 1;
+        head.w = n.p_hd_conv.w;
+        head.w.insert(head.w.end(), n.v_hd_conv.w.begin(), n.v_hd_conv.w.end());
+        head.b = n.p_hd_conv.b;
+        head.b.insert(head.b.end(), n.v_hd_conv.b.begin(), n.v_hd_conv.b.end());
+        PackConv(head, L.head, p);
     }
-    for (int j = 0; j < P; ++j) hb[j] = n.p_hd_conv.b[j];
-    for (int j = 0; j < V; ++j) hb[P + j] = n.v_hd_conv.b[j];
     PackFc(n.p_inter_fc, L.p_inter, p);
     PackFc(n.pass_fc, L.pass, p);
     PackFc(n.v_inter_fc, L.v_inter, p);
@@ -264,7 +267,7 @@ struct Slot {
     ActBuf* trunk = nullptr;   // which buffer holds the tower output after the last forward
     uint8_t* mask = nullptr;
     float* gb = nullptr;       // [max_batch][2C]
-    float* pv = nullptr;       // [rows][P+V]
+    ActBuf pv;                 // head-entry conv output: P policy + V value channels (padded to 64)
     float* pint = nullptr;
     float* pass5 = nullptr;
     float* misc15 = nullptr;
@@ -286,7 +289,7 @@ struct DevConv {
 struct Replica {
     int device = -1;
     uint8_t* blob = nullptr;
-    DevConv input;
+    DevConv input, head;
     std::vector<DevConv> conv1, conv2;
     std::vector<Slot> slots;
     void* flush_buf = nullptr;
@@ -334,13 +337,12 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.d_meta);
     cudaFree(s.d_out);
     cudaFreeHost(s.h_out);
-    for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u}) {
+    for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u, &s.pv}) {
         if (a->lo != a->hi) cudaFree(a->lo);   // single-pass fp16 mode aliases lo to hi
         cudaFree(a->hi);
     }
     cudaFree(s.mask);
     cudaFree(s.gb);
-    cudaFree(s.pv);
     cudaFree(s.pint);
     cudaFree(s.pass5);
     cudaFree(s.misc15);
@@ -371,7 +373,7 @@ static void AllocAct(ActBuf& a, int rows, int channels, bool split) {
 
 static void AllocSlots(sb_engine* e, Replica& r) {
     SB_CUDA(cudaSetDevice(r.device));
-    const int C = e->net_shape.channels, P = e->net_shape.P, V = e->net_shape.V;
+    const int C = e->net_shape.channels, P = e->net_shape.P;
     const int Cp = RoundUp(C, 64);
     const int rows = e->rows_alloc;
     const bool split = Split(e);
@@ -395,8 +397,7 @@ static void AllocSlots(sb_engine* e, Replica& r) {
         SB_CUDA(cudaMalloc(&s.mask, (size_t)rows));
         SB_CUDA(cudaMemset(s.mask, 0, (size_t)rows));
         SB_CUDA(cudaMalloc(&s.gb, (size_t)e->max_batch * 2 * C * sizeof(float)));
-        SB_CUDA(cudaMalloc(&s.pv, (size_t)rows * (P + V) * sizeof(float)));
-        SB_CUDA(cudaMemset(s.pv, 0, (size_t)rows * (P + V) * sizeof(float)));
+        AllocAct(s.pv, rows, 64, split);
         SB_CUDA(cudaMalloc(&s.pint, (size_t)e->max_batch * P * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.pass5, (size_t)e->max_batch * 5 * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.misc15, (size_t)e->max_batch * 15 * sizeof(float)));
@@ -411,15 +412,16 @@ static void AllocSlots(sb_engine* e, Replica& r) {
 }
 
 static void MakeConvMaps(const Replica& r, DevConv& c) {
-    c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, 9 * c.L.cinp, c.L.bn);
-    c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, 9 * c.L.cinp, c.L.bn);
-    c.tm2_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, 9 * c.L.cinp, c.L.bn / 2);
-    c.tm2_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, 9 * c.L.cinp, c.L.bn / 2);
+    const int K = c.L.taps * c.L.cinp;
+    c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, c.L.bn);
+    c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, c.L.bn);
+    c.tm2_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, c.L.bn / 2);
+    c.tm2_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, c.L.bn / 2);
 }
 
 // fp32 transposed weights for the SIMT cross-check kernel, derived from the packed hi/lo matrices.
 static void MakeSimtWeights(sb_engine* e, Replica& r, DevConv& c, const std::vector<uint8_t>& blob) {
-    const size_t K = (size_t)9 * c.L.cinp;
+    const size_t K = (size_t)c.L.taps * c.L.cinp;
     std::vector<float> wT(K * c.L.cout);
     const __half* hi = reinterpret_cast<const __half*>(blob.data() + c.L.w_hi);
     const __half* lo = reinterpret_cast<const __half*>(blob.data() + c.L.w_lo);
@@ -445,6 +447,8 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     const int blocks = e->net_shape.blocks;
     r.input.L = e->layout.input;
     MakeConvMaps(r, r.input);
+    r.head.L = e->layout.head;
+    MakeConvMaps(r, r.head);
     r.conv1.resize(blocks);
     r.conv2.resize(blocks);
     for (int b = 0; b < blocks; ++b) {
@@ -455,6 +459,7 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     }
     if (blob && e->precision == SB_PRECISION_SIMT_DEBUG) {
         MakeSimtWeights(e, r, r.input, *blob);
+        MakeSimtWeights(e, r, r.head, *blob);
         for (int b = 0; b < blocks; ++b) {
             MakeSimtWeights(e, r, r.conv1[b], *blob);
             MakeSimtWeights(e, r, r.conv2[b], *blob);
@@ -464,10 +469,6 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     // widths can coexist in one process
     for (int act = 0; act < 8; ++act) {
         SB_DISPATCH_ACT(act, ACT,
-            SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<16, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 16 + 16) * 4));
-            SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<32, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 32 + 32) * 4));
-            SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<48, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 48 + 48) * 4));
-            SB_CUDA(cudaFuncSetAttribute(head_conv_kernel<64, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 64 + 64) * 4));
             SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
             SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes));
             SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::kSmemBytes));
@@ -484,6 +485,7 @@ static void DestroyReplica(Replica& r) {
         c.wT = nullptr;
     };
     free_conv(r.input);
+    free_conv(r.head);
     for (auto& c : r.conv1) free_conv(c);
     for (auto& c : r.conv2) free_conv(c);
     cudaFree(r.blob);
@@ -513,8 +515,8 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         conv3x3_simt_kernel<<<grid, block, 0, s.stream>>>(in.hi, in.lo, true, c.L.cinp, c.wT,
                                                           reinterpret_cast<const float*>(r.blob + c.L.bias),
                                                           res ? res->hi : nullptr, res ? res->lo : nullptr, s.mask,
-                                                          c.L.cout, n_super * kSuperRows, e->geom.P, act, out.hi, out.lo,
-                                                          out.rows);
+                                                          c.L.cout, n_super * kSuperRows, e->geom.P, c.L.taps, act, out.hi,
+                                                          out.lo, out.rows);
     } else {
         ConvParams p;
         p.out_hi = out.hi;
@@ -530,6 +532,7 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.n_super = n_super;
         p.n_ntiles = c.L.ntiles;
         p.pitch = e->geom.P;
+        p.ntaps = c.L.taps;
         p.dbg = e->conv_dbg;
         p.a_lbo = e->desc_swap ? 128 : kSlabRows * 16;
         p.a_sbo = e->desc_swap ? kSlabRows * 16 : 128;
@@ -564,15 +567,6 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
     }
 }
 
-template <int PV>
-static void LaunchHeadConv(sb_engine* e, Replica& r, Slot& s, const ActBuf& x, int n_rows) {
-    const int C = e->net_shape.channels;
-    const size_t smem = ((size_t)C * PV + PV) * sizeof(float);   // opt-in size set once in BuildReplica
-    SB_DISPATCH_ACT(e->net_shape.act, ACT, (head_conv_kernel<PV, ACT><<<(n_rows + 127) / 128, 128, smem, s.stream>>>(
-        x.hi, x.lo, Split(e), s.mask, reinterpret_cast<const float*>(r.blob + e->layout.head_wT),
-        reinterpret_cast<const float*>(r.blob + e->layout.head_b), C, x.rows, n_rows, s.pv)));
-}
-
 // Everything between "inputs are in d_in / d_meta" and "outputs are in d_out", on the slot's stream.
 static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* tm = nullptr) {
     const HostNet& ns = e->net_shape;
@@ -601,8 +595,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         const int se = e->se_sizes[b];
         if (se > 0) {
             LaunchConv(e, r, s, r.conv2[b], *t, *u, nullptr, kIdentity, n, tm);
-            const int n_rg = 256 / (C / 2);
-            const size_t smem = ((size_t)2 * n_rg * C + 3 * C + se) * sizeof(float);
+            const size_t smem = ((size_t)5 * C + se) * sizeof(float);
             se_pool_fc_kernel<<<n, 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se,
                                                           F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
                                                           F(L.excite[b].b), act, s.gb);
@@ -618,15 +611,8 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         std::swap(x, u);
     }
     s.trunk = x;
-    // heads
-    switch (P + V) {
-        case 16: LaunchHeadConv<16>(e, r, s, *x, n_rows); break;
-        case 32: LaunchHeadConv<32>(e, r, s, *x, n_rows); break;
-        case 48: LaunchHeadConv<48>(e, r, s, *x, n_rows); break;
-        case 64: LaunchHeadConv<64>(e, r, s, *x, n_rows); break;
-        default: throw CudaError{"unsupported policy+value head width " + std::to_string(P + V) + " (16/32/48/64)"};
-    }
-    SB_CUDA(cudaGetLastError());
+    // heads: the two head-entry 1x1 convs as one single-tap tensor-core launch
+    LaunchConv(e, r, s, r.head, *x, s.pv, nullptr, act, n, nullptr);
     HeadWeights hw;
     hw.p_inter_w = F(L.p_inter.w);
     hw.p_inter_b = F(L.p_inter.b);
@@ -641,14 +627,16 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     hw.own_w = F(L.own_w);
     hw.own_b = F(L.own_b);
     {
-        const int PV = P + V, n_rg = 256 / PV;
-        const size_t smem = ((size_t)2 * n_rg * PV + 3 * P + 3 * V + P + 3 * V) * sizeof(float);
-        head_pool_fc_kernel<<<n, 256, smem, s.stream>>>(s.pv, s.mask, d_sizes, g, P, V, hw, act, s.pint, s.pass5, s.misc15);
+        const int PV = P + V;
+        const size_t smem = ((size_t)2 * PV + 3 * P + 3 * V + P + 3 * V) * sizeof(float);
+        head_pool_fc_kernel<<<n, 256, smem, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, s.mask, d_sizes, g, P, V, hw, act,
+                                                        s.pint, s.pass5, s.misc15);
         SB_CUDA(cudaGetLastError());
-        head_out_kernel<<<n, 384, 0, s.stream>>>(s.pv, d_sizes, d_offsets, g, P, V, hw, s.pint, s.pass5, s.misc15, s.d_out);
+        head_out_kernel<<<n, 384, 0, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, d_sizes, d_offsets, g, P, V, hw, s.pint,
+                                                 s.pass5, s.misc15, s.d_out);
         SB_CUDA(cudaGetLastError());
     }
-    e->launches += 3;
+    e->launches += 2;
 }
 
 static void CheckSlotError(Slot& s, cudaError_t err, const char* what) {
@@ -722,8 +710,8 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
     }
     {
         const int PV = e->net_shape.P + e->net_shape.V;
-        if (PV != 16 && PV != 32 && PV != 48 && PV != 64)
-            return Fail(nullptr, SB_ERR_INVALID, "policy+value head channels must sum to 16, 32, 48 or 64");
+        if ((PV != 16 && PV != 32 && PV != 48 && PV != 64) || e->net_shape.P % 8 || e->net_shape.V % 8)
+            return Fail(nullptr, SB_ERR_INVALID, "policy and value head channels must be multiples of 8 summing to 16, 32, 48 or 64");
         if (e->net_shape.channels % 8) return Fail(nullptr, SB_ERR_INVALID, "channels must be a multiple of 8");
     }
     e->layout = ComputeLayout(e->net_shape.blocks, e->net_shape.channels, e->net_shape.P, e->net_shape.V, e->se_sizes);
