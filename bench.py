@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -230,9 +230,14 @@ def run_ours(args, rank, local_rank, world):
     conv_flops = conv3x3_flops_per_eval(blocks, C) * B
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
     peak = peaks["tflops_sustained"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")   # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.precision, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "kernel": "conv3x3_tc_kernel<%s>" % ("true" if precision == engine.PRECISION_FP32_SPLIT else "false"),
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "kernel": "conv3x3_tc2_kernel<%s, mish> (tcgen05 cta_group::2)" % ("split" if precision == engine.PRECISION_FP32_SPLIT else "fp16"),
                 "launches_per_step": conv_n, "kernel_ms_per_step": conv_ms,
                 "kernel_share_of_step": conv_ms / float(ms.mean()) if len(ms) else None,
                 "algorithmic_flops_per_launch_avg": conv_flops / max(conv_n, 1),
