@@ -59,53 +59,68 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  The sampler is
+    started before the warm-up (nvidia-smi needs ~100 ms to print its first line) and every line is stamped with the
+    host time it arrived; only samples that fall inside a marked timed window are reported (if a window was too short
+    to catch one, the samples taken under load around it are used and the line says so)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []      # (host time, text)
+        self.windows = []    # (t0, t1)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 3.0:   # first line = the sampler is live
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        rows = []
+        for t, line in self.lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                rows.append((t, float(f[0]), float(f[1]), float(f[2]), [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if any(t0 <= r[0] <= t1 + 0.02 for t0, t1 in self.windows)]
+        how = "samples inside the timed regions"
+        if not inside and rows:
+            pmax = max(r[3] for r in rows)
+            inside = [r for r in rows if r[3] >= 0.6 * pmax]
+            how = "timed regions shorter than the sampling period: samples under load (>= 60 % of peak power) around them"
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+                "sm_max_mhz": max(r[2] for r in rows) if rows else None, "reasons": reasons, "samples": len(inside),
+                "power_w_max": max(r[3] for r in inside) if inside else None, "how": how}
 
 
 def weights_file(net, seed=20260417):
@@ -212,14 +227,15 @@ def run_ours(args, rank, local_rank, world):
         raise RuntimeError("non-finite outputs")
 
     # ---- (1) device-timed, inputs resident: warm-up W, then exactly K steps -------------------------
-    pipe.time_forward(0, 0, args.warmup, flush_l2=True)
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    pipe.time_forward(0, 0, args.warmup, flush_l2=True)
+    barrier()
     launches0 = pipe.launch_count()
+    tw0 = time.perf_counter()
     ms, _, _ = pipe.time_forward(0, 0, args.steps, flush_l2=True)
+    sampler.window(tw0, time.perf_counter())
     launches = pipe.launch_count() - launches0
-    clocks = sampler.stop()
     barrier()
     t_dev = reduce_max(float(ms.sum()) / 1e3)
     value = world * B * args.steps / t_dev
@@ -260,12 +276,32 @@ def run_ours(args, rank, local_rank, world):
     t0 = time.perf_counter()
     e2e_loop(args.steps)
     t_e2e = time.perf_counter() - t0
+    sampler.window(t0, t0 + t_e2e)
     barrier()
     t_e2e = reduce_max(t_e2e)
     e2e = {"value": world * B * args.steps / t_e2e, "unit": UNIT,
            "h2d_bytes_per_step": B * engine.PLANE_FLOATS * 4 + 2 * B * 4,
            "d2h_bytes_per_step": B * (2 * 361 + 8) * 4,
            "timing": "host perf_counter around K pipelined sb_submit/sb_wait steps (2 slots), device idle on both sides"}
+
+    # ---- (3) the single-position call of the plugin interface (NetworkForwardPipe::Forward -> sb_eval): T native
+    #      host threads, fp32 planes in pageable memory, packing + H2D + forward + D2H + wake-up inside the region ----
+    e2e_eval = None
+    if args.eval_threads > 0:
+        try:
+            pipe.batcher_config(B, 200)
+            n_thr = args.eval_threads
+            tw0 = time.perf_counter()
+            ev = pipe.eval_throughput(pos, 19, n_thr, args.eval_seconds)
+            sampler.window(tw0 + 0.2, time.perf_counter())
+            st = pipe.batcher_stats()
+            e2e_eval = {"value": world * ev, "unit": UNIT, "host_threads": n_thr, "seconds": args.eval_seconds,
+                        "mean_batch": st["positions"] / max(st["batches"], 1),
+                        "h2d_bytes_per_eval": 2252, "d2h_bytes_per_eval": (2 * 361 + 8) * 4,
+                        "call": "sb_eval (blocking, one position per call; the engine's batcher forms the batches)"}
+        except RuntimeError as ex:
+            e2e_eval = {"value": None, "error": str(ex)}
+    clocks = sampler.stop()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -275,7 +311,7 @@ def run_ours(args, rank, local_rank, world):
                        "net": args.net, "board": 19, "batch_per_gpu": B, "precision": args.precision,
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "parallelism": "replica per GPU, weights NCCL-broadcast from rank 0"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "e2e_eval": e2e_eval, "gpu_launches": int(launches), "roofline": roofline,
             "algorithmic_gflop_per_eval": algorithmic_flops_per_eval(blocks, C, P, V, n_se) / 1e9}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's Eigen forward on host cores -----
@@ -324,6 +360,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-threads", type=int, default=512, help="host threads of the sb_eval leg (0 = skip)")
+    ap.add_argument("--eval-seconds", type=float, default=2.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -89,6 +89,20 @@ typedef struct sb_output {
     int fp16;                                  /* 1 if SB_PRECISION_FP16 was used                        */
 } sb_output;
 
+/* Compact, EXACT encoding of one InputData (src/neural/network_basic.h:23-34) for the host->device hop.  The
+ * encoder (src/neural/encoder.cc:80-100,296-319) emits 37 planes of {0,1} and 6 board-constant planes, i.e. every
+ * plane takes at most one non-zero value: plane c == scale[c] * bit-mask c.  2.2 KB instead of 62 KB per position. */
+#define SB_PACKED_WORDS 12                     /* ceil(361 / 32) bit words per plane                       */
+#define SB_PACKED_RAW 1                        /* flags: planes were not two-valued, raw fp32 planes follow */
+typedef struct sb_packed_position {
+    uint32_t bits[SB_INPUT_CHANNELS][SB_PACKED_WORDS]; /* bit i of plane c <=> planes[c][i] != 0, native n*n order */
+    float scale[SB_INPUT_CHANNELS];                    /* the non-zero value of plane c (0 if the plane is empty)  */
+    int32_t board_size;
+    int32_t offset;                                    /* PolicyBufferOffset                                       */
+    int32_t flags;
+    int32_t reserved;
+} sb_packed_position;                                  /* 2252 bytes */
+
 typedef struct sb_engine sb_engine;
 
 /* ---- lifetime: CudaForwardPipe::Initialize/Construct/Release/Destroy, ------------------------------
@@ -140,6 +154,34 @@ int sb_forward_batch(sb_engine* e, int gpu, int n, const float* const* planes, c
 int sb_submit(sb_engine* e, int gpu, int slot, int n, const float* planes, long long plane_stride,
               const int* board_sizes, const int* policy_offsets);
 int sb_wait(sb_engine* e, int gpu, int slot, sb_output* out);
+
+/* ---- the batcher: NetworkForwardPipe::Forward for one position from ANY number of threads -----------------
+ *      replaces BatchForwardPipe::SendQueryAndWait + Worker/GatherBatches (src/neural/batch_forward_pipe.cc:7-193)
+ *      and the per-call host copies of NNGraph::BatchForward (cuda_forward_pipe.cc:694-701).  The calling thread
+ *      packs its position straight into a pinned batch record (sb_pack_position), one worker thread per
+ *      (GPU, stream) closes a batch when it is full or `wait_us` after its first position arrived (and no earlier
+ *      than a stream is free: batches grow while the GPU is busy), runs it and wakes the callers.             */
+
+/* Exact packing of one position; returns 1 and fills *out, or returns 0 (out->flags = SB_PACKED_RAW) when some
+ * plane holds two different non-zero values or a NaN.  Pure host function, thread-safe. */
+int sb_pack_position(const float* planes, int board_size, int offset, sb_packed_position* out);
+int sb_unpack_position(const sb_packed_position* rec, float* planes);   /* inverse, for tests */
+
+/* Blocking, thread-safe evaluation of ONE position (planes: 43 * bs * bs floats at the native board size).
+ * The first call starts the worker threads (2 per GPU, each with its own device slot and stream). */
+int sb_eval(sb_engine* e, const float* planes, int board_size, int policy_offset, sb_output* out);
+
+/* BatchForwardPipe::SetForwardingSize (batch_size <= max_batch; <= 0 keeps) and the --gpu-waittime analogue in
+ * microseconds (< 0 keeps; default 200). */
+int sb_batcher_config(sb_engine* e, int batch_size, int wait_us);
+/* out[0..5] = batches run, positions evaluated, batches closed full, batches closed by the timer,
+ * positions that could not be packed (raw fp32 fallback), worker threads. */
+int sb_batcher_stats(sb_engine* e, long long* out6);
+
+/* Measurement helper (bench.py e2e leg, tools/): `threads` native host threads call sb_eval in a loop for
+ * `seconds` over n_pos positions (planes: n_pos records SB_PLANE_FLOATS apart, native packing, pageable memory).
+ * Returns evaluations per second (wall clock), or a negative sb_status. */
+double sb_eval_throughput(sb_engine* e, const float* planes, int n_pos, int board_size, int threads, double seconds);
 
 /* Pinned host memory (the reference's host_input_planes_ / host_output_* buffers, cuda_forward_pipe.cc:560-577). */
 void* sb_host_alloc(size_t bytes);

@@ -3,6 +3,7 @@
 // vectorised (16 B) row accesses; per-sample reductions run in a fixed order (batch-invariant results).
 #pragma once
 #include "common.cuh"
+#include "../../include/sayuri_b200.h"
 
 namespace sb {
 
@@ -63,41 +64,97 @@ __global__ void unpack_planes_kernel(const float* __restrict__ planes, size_t sa
     if (cg == 0) mask[kGuardRows + r] = live ? 1 : 0;
 }
 
+// unpack_packed: the same canvas construction from COMPACT records (sb_packed_position, include/sayuri_b200.h):
+// plane c of sample b is scale[c] * bit-mask, so the host->device hop carries 2.2 KB per position instead of 62 KB.
+// Samples flagged SB_PACKED_RAW read their fp32 planes from `raw` (same layout as unpack_planes) instead.
+// Also scatters board sizes / policy offsets of the records into the d_meta arrays the later kernels read.
+__global__ void unpack_packed_kernel(const sb_packed_position* __restrict__ rec, const float* __restrict__ raw,
+                                     size_t sample_stride, Geom g, int n, int n_rows, int R, int max_batch,
+                                     __half* __restrict__ hi, __half* __restrict__ lo, bool split,
+                                     uint8_t* __restrict__ mask, int* __restrict__ meta) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) {
+        meta[idx] = rec[idx].board_size;
+        meta[max_batch + idx] = rec[idx].offset;
+    }
+    const int cg = idx / n_rows, r = idx - cg * n_rows;   // rows fastest: coalesced 16-byte pieces
+    if (cg >= 8) return;
+    const int b = r / g.SS, rem = r - b * g.SS;
+    const int y = rem / g.P, x = rem - y * g.P;
+    int bs = 0;
+    if (b < n) bs = rec[b].board_size;
+    const bool live = (b < n) && (y < bs) && (x < bs);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (live) {
+        const sb_packed_position& p = rec[b];
+        const int cell = y * bs + x;
+        if (p.flags & SB_PACKED_RAW) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = cg * 8 + i;
+                if (c < kInputChannels) v[i] = raw[(size_t)b * sample_stride + (size_t)c * bs * bs + cell];
+            }
+        } else {
+            const int word = cell >> 5, bit = cell & 31;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = cg * 8 + i;
+                if (c < kInputChannels && ((p.bits[c][word] >> bit) & 1u)) v[i] = p.scale[c];
+            }
+        }
+    }
+    const size_t off = act_index(kGuardRows + r, cg * 8, R);
+    store8(hi + off, lo + off, split, v);
+    if (cg == 0) mask[kGuardRows + r] = live ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Per-sample pooling over a C8 tensor: sum and max of every channel over the sample's board cells.
-// One CTA of 256 threads; warp w takes channel chunks w, w+8, ...; its lanes stride the sample's rows, so every
-// load is a coalesced run of 16-byte pieces; a fixed shuffle tree finishes the reduction (batch-invariant order).
+// One CTA of 256 threads.  L = 256 / chunks (rounded down to a power of two, <= 32) adjacent lanes share one
+// 8-channel chunk and stride the sample's rows, so a warp reads L consecutive 16-byte pieces of 32/L chunks per
+// step; the row loop is branch-free (select on the mask byte) and unrolled so that several independent 16-byte
+// loads are in flight per thread; a fixed shuffle tree over the L lanes finishes the reduction (the order never
+// depends on the batch: batch-invariant results).
 __device__ __forceinline__ void pool_sample_c8(const __half* __restrict__ hi, const __half* __restrict__ lo, bool split,
                                                const uint8_t* __restrict__ mask, int row0, int SS, int C, int R,
                                                float* s_sum, float* s_max) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int chunk = warp; chunk < (C >> 3); chunk += 8) {
+    const int chunks = C >> 3;
+    int L = 32;
+    while (L > 1 && L * chunks > 256) L >>= 1;
+    const int sub = threadIdx.x & (L - 1);
+    const int per_pass = 256 / L;
+    for (int chunk = threadIdx.x / L; chunk < ((chunks + per_pass - 1) / per_pass) * per_pass; chunk += per_pass) {
+        const bool on = chunk < chunks;      // idle lanes still join the shuffles of their warp
         float s[8], m[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             s[i] = 0.f;
             m[i] = -5000.f;   // "crazy negative value", se_unit.cc:22
         }
-        for (int r = lane; r < SS; r += 32) {
-            if (!mask[row0 + r]) continue;
-            float v[8];
-            const size_t off = act_index(row0 + r, chunk * 8, R);
-            load8(hi + off, lo + off, split, v);
+        if (on) {
+#pragma unroll 4
+            for (int r = sub; r < SS; r += L) {
+                const bool live = mask[row0 + r] != 0;
+                float v[8];
+                const size_t off = act_index(row0 + r, chunk * 8, R);
+                load8(hi + off, lo + off, split, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                s[i] += v[i];
-                m[i] = fmaxf(m[i], v[i]);
+                for (int i = 0; i < 8; ++i) {
+                    s[i] += live ? v[i] : 0.f;
+                    m[i] = live ? fmaxf(m[i], v[i]) : m[i];
+                }
             }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = L >> 1; o > 0; o >>= 1) {
                 s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
                 m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], o));
             }
         }
-        if (lane == 0) {
+        if (on && sub == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 s_sum[chunk * 8 + i] = s[i];
@@ -142,9 +199,22 @@ se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_
         if (lane == 0) hid[o] = activate(acc + b1[o], act);
     }
     __syncthreads();
+    const bool vec4 = (se & 3) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0;
     for (int o = tid; o < 2 * C; o += 256) {     // excite: se -> 2C, identity
         float acc = 0.f;
-        for (int i = 0; i < se; ++i) acc += w2[(size_t)o * se + i] * hid[i];
+        if (vec4) {   // one 16-byte load per 4 weights, all independent (same summation order as the scalar loop)
+            const float4* wr = reinterpret_cast<const float4*>(w2 + (size_t)o * se);
+#pragma unroll 4
+            for (int i = 0; i < (se >> 2); ++i) {
+                const float4 w = wr[i];
+                acc += w.x * hid[4 * i];
+                acc += w.y * hid[4 * i + 1];
+                acc += w.z * hid[4 * i + 2];
+                acc += w.w * hid[4 * i + 3];
+            }
+        } else {
+            for (int i = 0; i < se; ++i) acc += w2[(size_t)o * se + i] * hid[i];
+        }
         acc += b2[o];
         if (o < C) acc = 1.0f / (1.0f + expf(-acc));   // gamma = sigmoid, se_unit.cc:103
         gb[(size_t)b * 2 * C + o] = acc;

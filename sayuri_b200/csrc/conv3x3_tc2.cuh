@@ -19,6 +19,12 @@
 
 namespace sb {
 
+#ifndef SB_TC2_NA
+#define SB_TC2_NA 3      // activation-slab buffers
+#endif
+#ifndef SB_TC2_NB
+#define SB_TC2_NB 8      // weight-stage ring depth (<= 16)
+#endif
 constexpr int kTileRows2 = 128;                              // rows per CTA per item
 constexpr int kSlabRows2 = kTileRows2 + 2 * kSlabMargin;     // 176
 
@@ -27,15 +33,16 @@ struct Conv2Cfg {
     static constexpr int kParts = SPLIT ? 2 : 1;
     static constexpr int kSlabPartBytes = kSlabRows2 * 128;          // [8 chunks][176 rows][16 B]
     static constexpr int kSlabBytes = kParts * kSlabPartBytes;
-    static constexpr int kNumSlabs = 3;
+    static constexpr int kNumSlabs = SB_TC2_NA;
     static constexpr int kBStageBytes = 64 * 128;                    // this CTA's half: up to 64 rows x 64 fp16
-    static constexpr int kNumBStages = 8;
+    static constexpr int kNumBStages = SB_TC2_NB;
     static constexpr int kOffB = kNumSlabs * kSlabBytes;
     static constexpr int kOffBar = kOffB + kNumBStages * kBStageBytes;
     static constexpr int kOffBias = kOffBar + 512;
     static constexpr int kSmemBytes = kOffBias + 256 * 4 + 1024;
     static constexpr int kTmemCols = 512;
     static constexpr int kThreads = 384;
+    static_assert(kNumBStages <= 16 && kNumSlabs <= 4, "barrier block layout");
     static_assert(kSlabPartBytes % 1024 == 0, "slab parts must keep the weight stages 1024-byte aligned");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
@@ -102,13 +109,36 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
                  : "memory");
 }
 
+// Work units.  An item is (256-row super tile st, N tile nt) at N = BN.  To cut the wave-quantisation loss of a
+// persistent grid (401 items over 74 CTA pairs = 5.42 -> 6 waves at batch 256), the host may turn the items of
+// the last, partial wave into TWO half units each (N = BN/2, same rows): units [0, n_full) are whole items, units
+// n_full + 2k, n_full + 2k + 1 are the N-halves of item n_full + k, so that the last wave costs half a wave.
+struct ConvUnit {
+    int st, n0, bn;
+};
+__device__ __forceinline__ ConvUnit conv_unit(int u, const ConvParams& p) {
+    ConvUnit w;
+    if (u < p.n_full) {
+        w.st = u / p.n_ntiles;
+        w.bn = p.bn;
+        w.n0 = (u % p.n_ntiles) * p.bn;
+    } else {
+        const int v = u - p.n_full, item = p.n_full + (v >> 1);
+        w.st = item / p.n_ntiles;
+        w.bn = p.bn >> 1;
+        w.n0 = (item % p.n_ntiles) * p.bn + (v & 1) * w.bn;
+    }
+    return w;
+}
+
 template <bool SPLIT, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                   const __grid_constant__ CUtensorMap tmWq_hi, const __grid_constant__ CUtensorMap tmWq_lo,
                    const ConvParams p) {
     using Cfg = Conv2Cfg<SPLIT>;
-    const int KH = p.kh, BN = p.bn, HB = p.bn >> 1;   // HB: weight rows staged by this CTA
+    const int KH = p.kh, BN = p.bn;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -118,8 +148,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t bar_addr = smem_base + Cfg::kOffBar;
     const uint32_t a_full = bar_addr + 0, a_empty = bar_addr + 32;                // [3] each
     const uint32_t tmem_full = bar_addr + 64, tmem_empty = bar_addr + 80;         // [2] each
-    const uint32_t b_full = bar_addr + 128, b_empty = bar_addr + 192;             // [8] each
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 256);
+    const uint32_t b_full = bar_addr + 128, b_empty = bar_addr + 256;             // [<= 16] each
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 384);
     float* sbias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
     constexpr uint32_t kNB = Cfg::kNumBStages, kNA = Cfg::kNumSlabs;
 
@@ -128,7 +158,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int n_items = p.n_super * p.n_ntiles;
+    const int n_items = p.n_units;   // whole items + half units of the tail wave (conv_unit)
 
     for (int i = threadIdx.x; i < p.cout && i < 256; i += blockDim.x) sbias[i] = p.bias[i];
 
@@ -152,6 +182,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             tma_prefetch_desc(&tmA_lo);
             tma_prefetch_desc(&tmW_lo);
         }
+        if (p.n_units > p.n_full) {
+            tma_prefetch_desc(&tmWq_hi);
+            if (SPLIT) tma_prefetch_desc(&tmWq_lo);
+        }
     }
     if (warp == 2) {
         tmem_alloc2(smem_u32(tmem_ptr_smem), Cfg::kTmemCols);
@@ -167,10 +201,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         // ===================== activation-slab producer (own 128-row tile, +-24 rows) =====================
         uint32_t it = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
-            const int st = item / p.n_ntiles;
+            const int st = conv_unit(item, p).st;
             const int row_lo = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 - kSlabMargin;
             for (int h = 0; h < KH; ++h, ++it) {
                 const uint32_t s = it % kNA, ph = (it / kNA) & 1u;
+                if ((p.dbg & 64) && it >= kNA) continue;   // ablation: no slab traffic after the first fills
                 mbar_wait(a_empty + 8 * s, ph ^ 1u, p.err, 1);
                 if (elect_one()) {
                     const uint32_t full0 = mapa_u32(a_full + 8 * s, 0);
@@ -187,8 +222,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     } else if (warp == 0) {
         // ===================== weight-stage producer (own N-half of every block) =====================
         uint32_t it = 0;
-        for (int item = cluster_id; item < n_items; item += n_clusters) {
-            const int nt = item % p.n_ntiles;
+        for (int item = cluster_id; item < n_items && !(p.dbg & 16); item += n_clusters) {
+            const ConvUnit w = conv_unit(item, p);
+            const int HB = w.bn >> 1;                      // weight rows staged by this CTA
+            const bool whole = w.bn == BN;
             for (int h = 0; h < KH; ++h) {
                 for (int tap = 0; tap < p.ntaps; ++tap) {
 #pragma unroll
@@ -198,8 +235,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         if (elect_one()) {
                             const uint32_t full0 = mapa_u32(b_full + 8 * s, 0);
                             if (leader) mbar_arrive_expect_tx(b_full + 8 * s, 2u * (uint32_t)HB * 128u);
-                            tma2_load_2d(bst_addr + s * Cfg::kBStageBytes, part ? &tmW_lo : &tmW_hi, tap * (KH * 64) + h * 64,
-                                         nt * BN + (int)rank * HB, full0);
+                            tma2_load_2d(bst_addr + s * Cfg::kBStageBytes,
+                                         whole ? (part ? &tmW_lo : &tmW_hi) : (part ? &tmWq_lo : &tmWq_hi),
+                                         tap * (KH * 64) + h * 64, w.n0 + (int)rank * HB, full0);
                         }
                         __syncwarp();
                     }
@@ -210,7 +248,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         if (leader) {
             // ===================== MMA issuer (leader CTA only) =====================
             // TMEM columns per CTA: stage as -> main at as*2*BN, lo at as*2*BN + BN (fp16 rung: main at as*BN).
-            const uint32_t idesc = umma_idesc_f16(256, BN);
+            const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);
             constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
             const bool stats = p.stats != nullptr;
             uint32_t a_it = 0, b_it = 0, j = 0;
@@ -218,6 +256,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const long long t_begin = stats ? clock64() : 0;
             for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
                 const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+                const uint32_t idesc = item < p.n_full ? idesc_whole : idesc_half;
                 if (stats) t0 = clock64();
                 mbar_wait(tmem_empty + 8 * as, aph ^ 1u, p.err, 3);
                 if (stats) t_wait_tmem += clock64() - t0;
@@ -227,18 +266,18 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 for (int h = 0; h < KH; ++h, ++a_it) {
                     const uint32_t s = a_it % kNA, sph = (a_it / kNA) & 1u;
                     if (stats) t0 = clock64();
-                    mbar_wait(a_full + 8 * s, sph, p.err, 4);
+                    if (!((p.dbg & 64) && a_it >= kNA)) mbar_wait(a_full + 8 * s, sph, p.err, 4);
                     if (stats) t_wait_slab += clock64() - t0;
                     tc_fence_after();
                     const uint32_t a_hi = slab_addr + s * Cfg::kSlabBytes;
                     for (int tap = 0; tap < p.ntaps; ++tap) {
-                        const int shift = p.ntaps == 1 ? 0 : (tap / 3 - 1) * p.pitch + (tap % 3 - 1);   // 1 tap = 1x1 convolution
+                        const int shift = (p.ntaps == 1 || (p.dbg & 8)) ? 0 : (tap / 3 - 1) * p.pitch + (tap % 3 - 1);   // 1 tap = 1x1 convolution
                         const uint32_t first = (h | tap) == 0 ? 0u : 1u;
                         const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
                         {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
                             const uint32_t bs = b_it % kNB, bph = (b_it / kNB) & 1u;
                             if (stats) t0 = clock64();
-                            mbar_wait(b_full + 8 * bs, bph, p.err, 5);
+                            if (!(p.dbg & 16)) mbar_wait(b_full + 8 * bs, bph, p.err, 5);
                             if (stats) t_wait_b += clock64() - t0;
                             tc_fence_after();
                             const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
@@ -258,7 +297,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         if (SPLIT) {   // weights lo x activations hi -> lo accumulator
                             const uint32_t bs = b_it % kNB, bph = (b_it / kNB) & 1u;
                             if (stats) t0 = clock64();
-                            mbar_wait(b_full + 8 * bs, bph, p.err, 6);
+                            if (!(p.dbg & 16)) mbar_wait(b_full + 8 * bs, bph, p.err, 6);
                             if (stats) t_wait_b += clock64() - t0;
                             tc_fence_after();
                             const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
@@ -292,16 +331,17 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         // the dependent ALU/MUFU chains of one warp are hidden behind the other.
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
-        const int c_split = ((BN >> 1) + 15) & ~15;            // column split, rounded to the 16-column ld granule
-        const int cbase = half ? c_split : 0;
-        const int HC = half ? BN - c_split : c_split;          // columns of this thread (multiple of 16, may be 0)
         const bool stats = p.stats != nullptr;
         uint32_t j = 0;
         long long t_wait_full = 0, t_drain = 0;
         const long long t_begin = stats ? clock64() : 0;
         const uint32_t empty0 = mapa_u32(tmem_empty, 0);   // leader's tmem_empty[0]; [1] is +8
         for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
-            const int st = item / p.n_ntiles, nt = item % p.n_ntiles;
+            const ConvUnit w = conv_unit(item, p);
+            const int st = w.st;
+            const int c_split = ((w.bn >> 1) + 15) & ~15;          // column split, rounded to the 16-column ld granule
+            const int cbase = half ? c_split : 0;
+            const int HC = half ? w.bn - c_split : c_split;        // columns of this thread (multiple of 16, may be 0)
             const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
             const long long t0 = stats ? clock64() : 0;
             mbar_wait(tmem_full + 8 * as, aph, p.err, 7);
@@ -338,16 +378,16 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const int row = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 + q * 32 + lane;
             const bool live = p.mask[row] != 0;
             const size_t chunk_stride = (size_t)p.rows * 8;
-            const size_t off = act_index(row, nt * BN + cbase, p.rows);
+            const size_t off = act_index(row, w.n0 + cbase, p.rows);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 if (g * 16 < HC) {
                     const int c0 = g * 16;
                     float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[nt * BN + cbase + c0 + i];
+                    for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[w.n0 + cbase + c0 + i];
                     const size_t o0 = off + (size_t)(c0 >> 3) * chunk_stride, o1 = o0 + chunk_stride;
-                    if (live && p.res_hi != nullptr) {
+                    if (live && p.res_hi != nullptr && !(p.dbg & 1)) {
                         const uint4 a0 = *reinterpret_cast<const uint4*>(p.res_hi + o0);
                         const uint4 a1 = *reinterpret_cast<const uint4*>(p.res_hi + o1);
                         const __half* hh0 = reinterpret_cast<const __half*>(&a0);
@@ -370,12 +410,13 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         }
                     }
                     uint32_t oh[8], ol[8];
-                    activate16<ACT>(v);
+                    if (!(p.dbg & 2)) activate16<ACT>(v);
                     if (!live) {   // select, not multiply: garbage rows may hold NaN
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = 0.f;
                     }
                     split16(v, oh, ol, SPLIT);
+                    if ((p.dbg & 1) && oh[0] != 0x12345678u) continue;
                     *reinterpret_cast<uint4*>(p.out_hi + o0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
                     *reinterpret_cast<uint4*>(p.out_hi + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
                     if (SPLIT) {

@@ -8,13 +8,22 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <climits>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sayuri_b200.h"
@@ -261,6 +270,9 @@ struct Slot {
     float* d_in = nullptr;
     int* h_meta = nullptr;     // pinned [2][max_batch]: board sizes, policy offsets
     int* d_meta = nullptr;
+    sb_packed_position* h_packed = nullptr;   // pinned [max_batch]: compact records (host_pack.cc)
+    sb_packed_position* d_packed = nullptr;
+    bool packed = false;       // the batch in flight came as compact records (unpack_packed_kernel)
     float* d_out = nullptr;    // [max_batch][kOutFloats]
     float* h_out = nullptr;    // pinned
     ActBuf in, x, t, u;
@@ -283,6 +295,7 @@ struct DevConv {
     ConvLayout L;
     CUtensorMap tm_hi, tm_lo;     // box [bn][64]
     CUtensorMap tm2_hi, tm2_lo;   // box [bn/2][64]: one CTA's half in the CTA-pair kernel
+    CUtensorMap tm2q_hi, tm2q_lo; // box [bn/4][64]: one CTA's half of a half unit (tail wave, conv_unit)
     float* wT = nullptr;  // fp32 [9*cinp][cout], SIMT debug only
 };
 
@@ -292,9 +305,45 @@ struct Replica {
     DevConv input, head;
     std::vector<DevConv> conv1, conv2;
     std::vector<Slot> slots;
+    std::vector<Slot> bslots;     // the batcher's own slots (sb_eval), allocated when its workers start
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     int sm_count = 0;
+};
+
+
+// ---- batcher (sb_eval): host-side data structures ------------------------------------------------------------
+// A ring of host batches in pinned memory.  Calling threads claim an index in the FILLING batch under the
+// batcher mutex, pack their position into it outside the lock and sleep on the batch's futex word; worker threads
+// (one per (GPU, batcher slot)) close a batch when it is full or its timer expired, run it and wake the sleepers.
+struct HostBatch {
+    sb_packed_position* rec = nullptr;   // pinned [max_batch]
+    float* raw = nullptr;                // pinned [max_batch][SB_PLANE_FLOATS], allocated on first unpackable position
+    float* out = nullptr;                // pinned [max_batch][kOutFloats]
+    int count = 0;                       // claimed entries (under Batcher::m)
+    std::atomic<int> ready{0};           // entries whose record is complete
+    std::atomic<int> readers{0};         // callers that still have to copy their result out
+    std::atomic<uint32_t> done_seq{0};   // futex word: bumped when the results (or the error) are published
+    std::atomic<int> any_raw{0};
+    int rc = 0;
+    std::string err;
+    std::chrono::steady_clock::time_point first;
+};
+
+struct Batcher {
+    std::mutex m;
+    std::condition_variable cv_work;     // workers: a batch was closed / the first position of a batch arrived
+    std::condition_variable cv_space;    // callers: a batch became free
+    std::vector<std::unique_ptr<HostBatch>> ring;
+    std::vector<int> free_list;
+    std::deque<int> closed;
+    int fill = -1;
+    int batch_size = 0;
+    int wait_us = 200;                   // configured ceiling (reference default gpu_waittime = 2 ms, config.cc:59)
+    int cur_wait_us = 200;               // adaptive: 0 after a futile timer close, restored while idle (batch_forward_pipe.cc:120-147)
+    bool quit = false;
+    std::vector<std::thread> workers;
+    std::atomic<long long> n_batches{0}, n_positions{0}, n_full{0}, n_timer{0}, n_raw{0};
 };
 
 }  // namespace sb
@@ -311,9 +360,20 @@ struct sb_engine {
     int rows_alloc = 0;
     int precision = SB_PRECISION_FP32_SPLIT;
     int collect_stats = 0;
+    int stats_launch = -1;   // conv launch index within a forward whose counters are kept (-1: every launch, last wins)
+    int conv_counter = 0;
     int desc_swap = 0;
     int conv_dbg = 0;
     int conv_impl = 2;   // 1 = single-CTA conv3x3_tc, 2 = CTA-pair conv3x3_tc2 (default)
+    int tail_split = 1;  // split the items of a partial last wave into N-halves (conv3x3_tc2)
+    int pack_inputs = 1; // pageable inputs travel as compact exact records (host_pack.cc); 0 = always fp32 staging
+    int pack_threads = 4;
+    int batcher_batch = 0;      // 0 = max_batch
+    int batcher_wait_us = 200;
+    std::unique_ptr<sb::Batcher> batcher;   // sb_eval
+    std::mutex batcher_start_mutex;
+    std::atomic<bool> batcher_on{false};
+    std::mutex error_mutex;
     int n_slots = 2;
     bool weights_ready = false;
     std::atomic<long long> launches{0};
@@ -335,6 +395,8 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.d_in);
     cudaFreeHost(s.h_meta);
     cudaFree(s.d_meta);
+    cudaFreeHost(s.h_packed);
+    cudaFree(s.d_packed);
     cudaFree(s.d_out);
     cudaFreeHost(s.h_out);
     for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u, &s.pv}) {
@@ -371,14 +433,14 @@ static void AllocAct(ActBuf& a, int rows, int channels, bool split) {
     }
 }
 
-static void AllocSlots(sb_engine* e, Replica& r) {
+static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int count) {
     SB_CUDA(cudaSetDevice(r.device));
     const int C = e->net_shape.channels, P = e->net_shape.P;
     const int Cp = RoundUp(C, 64);
     const int rows = e->rows_alloc;
     const bool split = Split(e);
-    r.slots.resize(e->n_slots);
-    for (Slot& s : r.slots) {
+    slots.resize(count);
+    for (Slot& s : slots) {
         SB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         SB_CUDA(cudaEventCreate(&s.ev_a));
         SB_CUDA(cudaEventCreate(&s.ev_b));
@@ -387,6 +449,8 @@ static void AllocSlots(sb_engine* e, Replica& r) {
         SB_CUDA(cudaMalloc(&s.d_in, in_bytes));
         SB_CUDA(cudaHostAlloc(&s.h_meta, (size_t)2 * e->max_batch * sizeof(int), cudaHostAllocDefault));
         SB_CUDA(cudaMalloc(&s.d_meta, (size_t)2 * e->max_batch * sizeof(int)));
+        SB_CUDA(cudaHostAlloc(&s.h_packed, (size_t)e->max_batch * sizeof(sb_packed_position), cudaHostAllocDefault));
+        SB_CUDA(cudaMalloc(&s.d_packed, (size_t)e->max_batch * sizeof(sb_packed_position)));
         const size_t out_bytes = (size_t)e->max_batch * kOutFloats * sizeof(float);
         SB_CUDA(cudaMalloc(&s.d_out, out_bytes));
         SB_CUDA(cudaHostAlloc(&s.h_out, out_bytes, cudaHostAllocDefault));
@@ -411,12 +475,17 @@ static void AllocSlots(sb_engine* e, Replica& r) {
     }
 }
 
+static void AllocSlots(sb_engine* e, Replica& r) { AllocSlotVec(e, r, r.slots, e->n_slots); }
+
 static void MakeConvMaps(const Replica& r, DevConv& c) {
     const int K = c.L.taps * c.L.cinp;
     c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, c.L.bn);
     c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, c.L.bn);
     c.tm2_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, c.L.bn / 2);
     c.tm2_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, c.L.bn / 2);
+    const int q = c.L.bn % 32 == 0 ? c.L.bn / 4 : c.L.bn / 2;   // half units need N/2 to be a multiple of 16
+    c.tm2q_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, q);
+    c.tm2q_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, q);
 }
 
 // fp32 transposed weights for the SIMT cross-check kernel, derived from the packed hi/lo matrices.
@@ -480,6 +549,8 @@ static void DestroyReplica(Replica& r) {
     if (r.device >= 0) cudaSetDevice(r.device);
     for (Slot& s : r.slots) FreeSlot(s);
     r.slots.clear();
+    for (Slot& s : r.bslots) FreeSlot(s);
+    r.bslots.clear();
     auto free_conv = [](DevConv& c) {
         cudaFree(c.wT);
         c.wT = nullptr;
@@ -531,23 +602,34 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.bn = c.L.bn;
         p.n_super = n_super;
         p.n_ntiles = c.L.ntiles;
+        p.n_full = n_super * c.L.ntiles;
+        p.n_units = p.n_full;
         p.pitch = e->geom.P;
         p.ntaps = c.L.taps;
         p.dbg = e->conv_dbg;
         p.a_lbo = e->desc_swap ? 128 : kSlabRows * 16;
         p.a_sbo = e->desc_swap ? kSlabRows * 16 : 128;
         p.err = s.d_err;
-        p.stats = e->collect_stats ? s.d_stats : nullptr;
+        p.stats = (e->collect_stats && (e->stats_launch < 0 || e->stats_launch == e->conv_counter)) ? s.d_stats : nullptr;
+        e->conv_counter++;
         const int items = n_super * c.L.ntiles;
         const int grid = std::min(items, r.sm_count);
         if (e->conv_impl == 2) {
-            const int grid2 = 2 * std::min(items, r.sm_count / 2);
+            // persistent CTA pairs; the items of a partial last wave are split into N-halves when that makes the
+            // wave half as long (conv_unit in conv3x3_tc2.cuh)
+            const int pairs = std::min(items, r.sm_count / 2);
+            const int grid2 = 2 * pairs;
+            const int rem = items % pairs;
+            int n_tail = 0;
+            if (e->tail_split && items > pairs && rem > 0 && 2 * rem <= pairs && c.L.bn % 32 == 0) n_tail = rem;
+            p.n_full = items - n_tail;
+            p.n_units = items + n_tail;
             if (Split(e)) {
                 SB_DISPATCH_ACT(act, ACT, (conv3x3_tc2_kernel<true, ACT><<<grid2, 384, Conv2Cfg<true>::kSmemBytes, s.stream>>>(
-                                              in.tm3_hi, in.tm3_lo, c.tm2_hi, c.tm2_lo, p)));
+                                              in.tm3_hi, in.tm3_lo, c.tm2_hi, c.tm2_lo, c.tm2q_hi, c.tm2q_lo, p)));
             } else {
                 SB_DISPATCH_ACT(act, ACT, (conv3x3_tc2_kernel<false, ACT><<<grid2, 384, Conv2Cfg<false>::kSmemBytes, s.stream>>>(
-                                              in.tm3_hi, in.tm3_hi, c.tm2_hi, c.tm2_hi, p)));
+                                              in.tm3_hi, in.tm3_hi, c.tm2_hi, c.tm2_hi, c.tm2q_hi, c.tm2q_hi, p)));
             }
         } else if (Split(e)) {
             SB_DISPATCH_ACT(act, ACT, (conv3x3_tc_kernel<true, ACT><<<grid, 384, ConvCfg<true>::kSmemBytes, s.stream>>>(
@@ -579,10 +661,17 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     const BlobLayout& L = e->layout;
     auto F = [&](size_t off) { return reinterpret_cast<const float*>(r.blob + off); };
 
+    e->conv_counter = 0;
     {   // input planes -> canvas
         const int threads = n_rows * 8;
-        unpack_planes_kernel<<<(threads + 255) / 256, 256, 0, s.stream>>>(s.d_in, (size_t)SB_PLANE_FLOATS, d_sizes, g, n,
-                                                                          n_rows, s.in.rows, s.in.hi, s.in.lo, split, s.mask);
+        if (s.packed) {
+            unpack_packed_kernel<<<(threads + 255) / 256, 256, 0, s.stream>>>(s.d_packed, s.d_in, (size_t)SB_PLANE_FLOATS, g, n,
+                                                                              n_rows, s.in.rows, e->max_batch, s.in.hi, s.in.lo,
+                                                                              split, s.mask, s.d_meta);
+        } else {
+            unpack_planes_kernel<<<(threads + 255) / 256, 256, 0, s.stream>>>(s.d_in, (size_t)SB_PLANE_FLOATS, d_sizes, g, n,
+                                                                              n_rows, s.in.rows, s.in.hi, s.in.lo, split, s.mask);
+        }
         SB_CUDA(cudaGetLastError());
         e->launches++;
     }
@@ -764,10 +853,42 @@ static int SubmitImpl(sb_engine* e, int gpu, int slot, int n, const float* plane
             if (cudaPointerGetAttributes(&attr, planes) == cudaSuccess && attr.type == cudaMemoryTypeHost) direct = true;
             cudaGetLastError();
         }
+        s.packed = false;
         if (direct) {
             const size_t width = (size_t)std::min<long long>(stride, SB_PLANE_FLOATS) * sizeof(float);
             SB_CUDA(cudaMemcpy2DAsync(s.d_in, (size_t)SB_PLANE_FLOATS * sizeof(float), planes, (size_t)stride * sizeof(float),
                                       width, n, cudaMemcpyHostToDevice, s.stream));
+        } else if (e->pack_inputs) {
+            // pageable caller memory: pack every position exactly into a 2.2 KB record in pinned memory (host_pack.cc)
+            // instead of staging 62 KB of fp32; a position that is not two-valued per plane travels raw.
+            auto pack_range = [&](int lo, int hi) {
+                for (int i = lo; i < hi; ++i) {
+                    const float* src = plane_ptrs ? plane_ptrs[i] : planes + (size_t)i * stride;
+                    if (!sb_pack_position(src, sizes[i], offsets[i], &s.h_packed[i])) {
+                        s.h_packed[i].board_size = sizes[i];
+                        s.h_packed[i].offset = offsets[i];
+                        s.h_packed[i].flags = SB_PACKED_RAW;
+                        std::memcpy(s.h_in + (size_t)i * SB_PLANE_FLOATS, src,
+                                    (size_t)SB_INPUT_CHANNELS * sizes[i] * sizes[i] * sizeof(float));
+                    }
+                }
+            };
+            const int n_thr = n >= 64 ? std::min(e->pack_threads, n / 32) : 1;
+            if (n_thr > 1) {
+                std::vector<std::thread> pool;
+                for (int t = 1; t < n_thr; ++t) pool.emplace_back(pack_range, (int)((long long)n * t / n_thr), (int)((long long)n * (t + 1) / n_thr));
+                pack_range(0, n / n_thr);
+                for (auto& th : pool) th.join();
+            } else {
+                pack_range(0, n);
+            }
+            SB_CUDA(cudaMemcpyAsync(s.d_packed, s.h_packed, (size_t)n * sizeof(sb_packed_position), cudaMemcpyHostToDevice, s.stream));
+            for (int i = 0; i < n; ++i) {
+                if (s.h_packed[i].flags & SB_PACKED_RAW)
+                    SB_CUDA(cudaMemcpyAsync(s.d_in + (size_t)i * SB_PLANE_FLOATS, s.h_in + (size_t)i * SB_PLANE_FLOATS,
+                                            (size_t)SB_INPUT_CHANNELS * sizes[i] * sizes[i] * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+            }
+            s.packed = true;
         } else {
             for (int i = 0; i < n; ++i) {
                 const float* src = plane_ptrs ? plane_ptrs[i] : planes + (size_t)i * stride;
@@ -822,6 +943,246 @@ static int WaitImpl(sb_engine* e, int gpu, int slot, sb_output* out) {
     return SB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batcher (sb_eval).  Replaces BatchForwardPipe::SendQueryAndWait / Worker / GatherBatches
+// (/root/reference/src/neural/batch_forward_pipe.cc:7-193).
+static void FutexWait(std::atomic<uint32_t>* a, uint32_t expected) {
+    syscall(SYS_futex, reinterpret_cast<uint32_t*>(a), FUTEX_WAIT_PRIVATE, expected, nullptr, nullptr, 0);
+}
+static void FutexWakeAll(std::atomic<uint32_t>* a) {
+    syscall(SYS_futex, reinterpret_cast<uint32_t*>(a), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
+}
+
+constexpr int kBatcherSlots = 2;   // worker threads (= device slots = streams) per GPU
+
+// caller holds B.m: the FILLING batch stops accepting positions; the next free batch (if any) takes over
+static int CloseFill(Batcher& B) {
+    const int idx = B.fill;
+    HostBatch& hb = *B.ring[idx];
+    hb.readers.store(hb.count, std::memory_order_relaxed);
+    if (B.free_list.empty()) {
+        B.fill = -1;
+    } else {
+        B.fill = B.free_list.back();
+        B.free_list.pop_back();
+    }
+    return idx;
+}
+
+static void RunHostBatch(sb_engine* e, Replica& r, Slot& s, HostBatch& hb) {
+    const int n = hb.count;
+    try {
+        cudaGetLastError();
+        SB_CUDA(cudaMemcpyAsync(s.d_packed, hb.rec, (size_t)n * sizeof(sb_packed_position), cudaMemcpyHostToDevice, s.stream));
+        if (hb.any_raw.load(std::memory_order_relaxed)) {
+            for (int i = 0; i < n; ++i) {
+                if (hb.rec[i].flags & SB_PACKED_RAW) {
+                    const int bs = hb.rec[i].board_size;
+                    SB_CUDA(cudaMemcpyAsync(s.d_in + (size_t)i * SB_PLANE_FLOATS, hb.raw + (size_t)i * SB_PLANE_FLOATS,
+                                            (size_t)SB_INPUT_CHANNELS * bs * bs * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+                }
+            }
+        }
+        for (int i = 0; i < n; ++i) {
+            s.sizes[i] = hb.rec[i].board_size;
+            s.offsets[i] = hb.rec[i].offset;
+        }
+        s.n = n;
+        s.packed = true;
+        EnqueueForward(e, r, s, n);
+        SB_CUDA(cudaMemcpyAsync(hb.out, s.d_out, (size_t)n * kOutFloats * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        CheckSlotError(s, cudaStreamSynchronize(s.stream), "batched forward");
+        hb.rc = SB_OK;
+    } catch (const CudaError& ce) {
+        hb.rc = SB_ERR_CUDA;
+        hb.err = ce.msg;
+    }
+}
+
+static void BatchWorker(sb_engine* e, int gpu, int k) {
+    Batcher& B = *e->batcher;
+    Replica& r = e->replicas[gpu];
+    Slot& s = r.bslots[k];
+    cudaSetDevice(r.device);
+    for (;;) {
+        int idx = -1;
+        {
+            std::unique_lock<std::mutex> lk(B.m);
+            for (;;) {
+                if (B.quit) return;
+                if (!B.closed.empty()) {
+                    idx = B.closed.front();
+                    B.closed.pop_front();
+                    break;
+                }
+                if (B.fill >= 0 && B.ring[B.fill]->count > 0) {
+                    HostBatch& hb = *B.ring[B.fill];
+                    const auto deadline = hb.first + std::chrono::microseconds(B.cur_wait_us);
+                    if (std::chrono::steady_clock::now() >= deadline) {
+                        // closed by the timer: if nothing joined while we waited the traffic is low or the front-end is
+                        // CPU-bound, so stop waiting (batch_forward_pipe.cc:139-143)
+                        if (hb.count <= 1 && B.cur_wait_us > 0) B.cur_wait_us = 0;
+                        idx = CloseFill(B);
+                        B.n_timer++;
+                        break;
+                    }
+                    B.cv_work.wait_until(lk, deadline);
+                } else {
+                    // idle: restore the configured wait step by step (batch_forward_pipe.cc:132-138)
+                    B.cur_wait_us = std::min(B.wait_us, B.cur_wait_us + std::max(1, B.wait_us / 8));
+                    B.cv_work.wait(lk);
+                }
+            }
+        }
+        HostBatch& hb = *B.ring[idx];
+        while (hb.ready.load(std::memory_order_acquire) < hb.count) std::this_thread::yield();   // packers still writing
+        RunHostBatch(e, r, s, hb);
+        B.n_batches++;
+        B.n_positions += hb.count;
+        hb.done_seq.fetch_add(1, std::memory_order_release);
+        FutexWakeAll(&hb.done_seq);
+    }
+}
+
+static void StopBatcher(sb_engine* e) {
+    std::lock_guard<std::mutex> g(e->batcher_start_mutex);
+    if (!e->batcher) return;
+    Batcher& B = *e->batcher;
+    {
+        std::lock_guard<std::mutex> lk(B.m);
+        B.quit = true;
+    }
+    B.cv_work.notify_all();
+    B.cv_space.notify_all();
+    for (auto& t : B.workers) t.join();
+    for (auto& hb : B.ring) {
+        cudaFreeHost(hb->rec);
+        cudaFreeHost(hb->raw);
+        cudaFreeHost(hb->out);
+    }
+    for (Replica& r : e->replicas) {
+        if (r.device >= 0) cudaSetDevice(r.device);
+        for (Slot& s : r.bslots) FreeSlot(s);
+        r.bslots.clear();
+    }
+    e->batcher_on.store(false, std::memory_order_release);
+    e->batcher.reset();
+}
+
+// Starts the worker threads on first use.  Throws CudaError.
+static void StartBatcher(sb_engine* e) {
+    std::lock_guard<std::mutex> g(e->batcher_start_mutex);
+    if (e->batcher) return;
+    std::unique_ptr<Batcher> B(new Batcher);
+    B->batch_size = e->batcher_batch > 0 ? std::min(e->batcher_batch, e->max_batch) : e->max_batch;
+    B->wait_us = B->cur_wait_us = e->batcher_wait_us;
+    const int n_workers = (int)e->replicas.size() * kBatcherSlots;
+    const int n_ring = n_workers + 2;
+    for (int i = 0; i < n_ring; ++i) {
+        std::unique_ptr<HostBatch> hb(new HostBatch);
+        SB_CUDA(cudaHostAlloc(&hb->rec, (size_t)e->max_batch * sizeof(sb_packed_position), cudaHostAllocPortable));
+        SB_CUDA(cudaHostAlloc(&hb->out, (size_t)e->max_batch * kOutFloats * sizeof(float), cudaHostAllocPortable));
+        B->ring.push_back(std::move(hb));
+        if (i > 0) B->free_list.push_back(i);
+    }
+    B->fill = 0;
+    for (Replica& r : e->replicas) AllocSlotVec(e, r, r.bslots, kBatcherSlots);
+    e->batcher = std::move(B);
+    for (int g2 = 0; g2 < (int)e->replicas.size(); ++g2)
+        for (int k = 0; k < kBatcherSlots; ++k) e->batcher->workers.emplace_back(BatchWorker, e, g2, k);
+    e->batcher_on.store(true, std::memory_order_release);
+}
+
+static int EvalImpl(sb_engine* e, const float* planes, int board_size, int offset, sb_output* out) {
+    if (!e || !planes || !out) return SB_ERR_INVALID;
+    if (board_size < 2 || board_size > e->geom.N) return Fail(e, SB_ERR_INVALID, "board size of a sample exceeds the NN canvas");
+    if (offset < 0 || offset > 4) return Fail(e, SB_ERR_INVALID, "policy offset must be in [0, 4]");
+    if (!e->weights_ready) return Fail(e, SB_ERR_STATE, "weights have not been loaded");
+    if (!e->batcher_on.load(std::memory_order_acquire)) {
+        try {
+            StartBatcher(e);
+        } catch (const CudaError& ce) {
+            return Fail(e, SB_ERR_CUDA, ce.msg);
+        }
+    }
+    Batcher& B = *e->batcher;
+    HostBatch* hb = nullptr;
+    int idx = -1, i = -1;
+    uint32_t seq0 = 0;
+    {
+        std::unique_lock<std::mutex> lk(B.m);
+        while (B.fill < 0 && !B.quit) B.cv_space.wait(lk);
+        if (B.quit) return Fail(e, SB_ERR_STATE, "the batcher is shutting down");
+        idx = B.fill;
+        hb = B.ring[idx].get();
+        i = hb->count++;
+        seq0 = hb->done_seq.load(std::memory_order_relaxed);
+        if (i == 0) hb->first = std::chrono::steady_clock::now();
+        if (hb->count >= B.batch_size) {
+            B.closed.push_back(CloseFill(B));
+            B.n_full++;
+            B.cv_work.notify_one();
+        } else if (i == 0) {
+            B.cv_work.notify_one();   // somebody has to watch this batch's timer
+        }
+    }
+    // pack outside the lock, straight into the pinned batch record
+    if (!sb_pack_position(planes, board_size, offset, &hb->rec[i])) {
+        hb->rec[i].board_size = board_size;
+        hb->rec[i].offset = offset;
+        hb->rec[i].flags = SB_PACKED_RAW;
+        if (!hb->raw) {
+            std::lock_guard<std::mutex> lk(B.m);
+            if (!hb->raw && cudaHostAlloc(&hb->raw, (size_t)e->max_batch * SB_PLANE_FLOATS * sizeof(float), cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                hb->raw = nullptr;
+            }
+        }
+        if (hb->raw) {
+            std::memcpy(hb->raw + (size_t)i * SB_PLANE_FLOATS, planes, (size_t)SB_INPUT_CHANNELS * board_size * board_size * sizeof(float));
+            hb->any_raw.store(1, std::memory_order_relaxed);
+        }
+        B.n_raw++;
+    }
+    hb->ready.fetch_add(1, std::memory_order_release);
+    while (hb->done_seq.load(std::memory_order_acquire) == seq0) FutexWait(&hb->done_seq, seq0);
+    const int rc = hb->rc;
+    if (rc == SB_OK) {
+        const float* src = hb->out + (size_t)i * kOutFloats;
+        std::memcpy(out->probabilities, src, sizeof(float) * SB_MAX_INTERSECTIONS);
+        std::memcpy(out->ownership, src + SB_MAX_INTERSECTIONS, sizeof(float) * SB_MAX_INTERSECTIONS);
+        const float* m = src + 2 * SB_MAX_INTERSECTIONS;
+        out->pass_probability = m[0];
+        out->wdl[0] = m[1];
+        out->wdl[1] = m[2];
+        out->wdl[2] = m[3];
+        out->stm_winrate = m[4];
+        out->final_score = m[5];
+        out->q_error = m[6];
+        out->score_error = m[7];
+        out->board_size = board_size;
+        out->offset = offset;
+        out->fp16 = e->precision == SB_PRECISION_FP16 ? 1 : 0;
+    } else {
+        std::lock_guard<std::mutex> lk(e->error_mutex);
+        e->last_error = hb->err;
+    }
+    if (hb->readers.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        // last reader recycles the batch
+        hb->count = 0;
+        hb->ready.store(0, std::memory_order_relaxed);
+        hb->any_raw.store(0, std::memory_order_relaxed);
+        std::lock_guard<std::mutex> lk(B.m);
+        if (B.fill < 0) {
+            B.fill = idx;
+            B.cv_space.notify_all();
+        } else {
+            B.free_list.push_back(idx);
+        }
+    }
+    return rc;
+}
+
 }  // namespace sb
 
 // =================================================================================================
@@ -862,6 +1223,7 @@ int sb_reconfigure(sb_engine* e, int board_size, int max_batch) {
     for (Replica& r : e->replicas)
         for (Slot& s : r.slots)
             if (s.busy) return Fail(e, SB_ERR_STATE, "cannot reconfigure while a batch is in flight");
+    StopBatcher(e);   // restarted by the next sb_eval with the new geometry (no Forward may be in flight, as in the reference)
     try {
         Configure(e, board, std::max(batch, board == e->geom.N ? e->max_batch : batch));
     } catch (const CudaError& ce) {
@@ -871,6 +1233,7 @@ int sb_reconfigure(sb_engine* e, int board_size, int max_batch) {
 }
 
 static int ReloadImpl(sb_engine* e, HostNet& net) {
+    StopBatcher(e);
     if (net.blocks != e->net_shape.blocks || net.channels != e->net_shape.channels || net.P != e->net_shape.P ||
         net.V != e->net_shape.V || net.se_sizes() != e->se_sizes)
         return Fail(e, SB_ERR_INVALID, "reload requires the same architecture; destroy and create for a new one");
@@ -908,6 +1271,7 @@ int sb_reload_weights_from_file(sb_engine* e, const char* weights_path) {
 
 void sb_destroy(sb_engine* e) {
     if (!e) return;
+    StopBatcher(e);
     for (Replica& r : e->replicas) {
         if (r.device >= 0) {
             cudaSetDevice(r.device);
@@ -955,6 +1319,76 @@ int sb_submit(sb_engine* e, int gpu, int slot, int n, const float* planes, long 
 }
 
 int sb_wait(sb_engine* e, int gpu, int slot, sb_output* out) { return WaitImpl(e, gpu, slot, out); }
+
+int sb_eval(sb_engine* e, const float* planes, int board_size, int policy_offset, sb_output* out) {
+    return EvalImpl(e, planes, board_size, policy_offset, out);
+}
+
+int sb_batcher_config(sb_engine* e, int batch_size, int wait_us) {
+    if (!e) return SB_ERR_INVALID;
+    if (batch_size > e->max_batch) return Fail(e, SB_ERR_INVALID, "batch size exceeds max_batch");
+    if (batch_size > 0) e->batcher_batch = batch_size;
+    if (wait_us >= 0) e->batcher_wait_us = wait_us;
+    std::lock_guard<std::mutex> g(e->batcher_start_mutex);
+    if (e->batcher) {
+        std::lock_guard<std::mutex> lk(e->batcher->m);
+        if (batch_size > 0) e->batcher->batch_size = batch_size;
+        if (wait_us >= 0) e->batcher->wait_us = e->batcher->cur_wait_us = wait_us;
+        // a FILLING batch that is already over the new size is closed by the next arrival or its timer
+    }
+    return SB_OK;
+}
+
+int sb_batcher_stats(sb_engine* e, long long* out6) {
+    if (!e || !out6) return SB_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->batcher_start_mutex);
+    for (int i = 0; i < 6; ++i) out6[i] = 0;
+    if (e->batcher) {
+        Batcher& B = *e->batcher;
+        out6[0] = B.n_batches;
+        out6[1] = B.n_positions;
+        out6[2] = B.n_full;
+        out6[3] = B.n_timer;
+        out6[4] = B.n_raw;
+        out6[5] = (long long)B.workers.size();
+    }
+    return SB_OK;
+}
+
+double sb_eval_throughput(sb_engine* e, const float* planes, int n_pos, int board_size, int threads, double seconds) {
+    if (!e || !planes || n_pos < 1 || threads < 1 || seconds <= 0) return (double)SB_ERR_INVALID;
+    sb_output warm;
+    int rc = EvalImpl(e, planes, board_size, 0, &warm);   // starts the workers, surfaces configuration errors
+    if (rc) return (double)rc;
+    std::atomic<long long> total{0};
+    std::atomic<int> failed{0};
+    std::atomic<bool> stop{false};
+    const size_t rec = (size_t)SB_PLANE_FLOATS;
+    std::vector<std::thread> pool;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t]() {
+            std::unique_ptr<sb_output> o(new sb_output);
+            long long n = 0;
+            int i = t % n_pos;
+            while (!stop.load(std::memory_order_relaxed)) {
+                if (EvalImpl(e, planes + (size_t)i * rec, board_size, i % 5, o.get())) {
+                    failed.store(1);
+                    break;
+                }
+                i = (i + 1) % n_pos;
+                ++n;
+            }
+            total += n;
+        });
+    }
+    std::this_thread::sleep_for(std::chrono::duration<double>(seconds));
+    stop.store(true);
+    for (auto& th : pool) th.join();
+    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (failed.load()) return (double)SB_ERR_CUDA;
+    return (double)total.load() / el;
+}
 
 void* sb_host_alloc(size_t bytes) {
     void* p = nullptr;
@@ -1114,6 +1548,22 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     }
     if (!std::strcmp(key, "conv_dbg")) {
         e->conv_dbg = value;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "pack_inputs")) {
+        e->pack_inputs = value ? 1 : 0;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "pack_threads")) {
+        e->pack_threads = std::max(1, value);
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "tail_split")) {
+        e->tail_split = value ? 1 : 0;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "stats_launch")) {
+        e->stats_launch = value;
         return SB_OK;
     }
     if (!std::strcmp(key, "stats")) {

@@ -8,6 +8,7 @@
 #include "neural/cuda/cuda_forward_pipe.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -50,12 +51,43 @@ void CudaForwardPipe::Initialize(std::shared_ptr<DNNWeights> weights) {
     auto option = ForwardPipeOption::Get()
                       .SetBoardSize(GetOption<int>("defualt_boardsize"))
                       .SetBatchSize(GetOption<int>("batch_size"));
+    // SAYURI_B200_REF_BATCHER=1 keeps the reference's own queue + one worker per GPU (SendQueryAndWait / Worker,
+    // batch_forward_pipe.cc:7-193) in front of sb_forward_batch, for A/B runs; the default is the engine's batcher.
+    const char* env = std::getenv("SAYURI_B200_REF_BATCHER");
+    ref_batcher_ = env && env[0] == '1';
     Construct(option, weights);
-    BatchForwardPipe::AssignWorkers(num_gpus_);
+    // With our batcher no reference worker threads exist; AssignWorkers(0) only creates the (empty) thread group
+    // that QuitWorkers joins at shutdown.
+    BatchForwardPipe::AssignWorkers(ref_batcher_ ? num_gpus_ : 0);
 }
 
 OutputResult CudaForwardPipe::Forward(const InputData& input) {
-    return BatchForwardPipe::SendQueryAndWait(input);
+    if (ref_batcher_) {
+        return BatchForwardPipe::SendQueryAndWait(input);
+    }
+    // NetworkForwardPipe::Forward from any number of search threads (network.cc:179): the calling thread packs its
+    // planes (InputData::planes is packed at the native board size, encoder.cc:31-50) straight into a pinned batch
+    // record and blocks until its batch has run.
+    sb_output o;
+    const int offset = input.offset == PolicyBufferOffset::kDefault ? 0 : static_cast<int>(input.offset);
+    Check(sb_eval(engine_, input.planes.data(), input.board_size, offset, &o), engine_);
+    OutputResult r;
+    const int ns = input.board_size * input.board_size;
+    std::memcpy(r.probabilities.data(), o.probabilities, sizeof(float) * ns);
+    std::memcpy(r.ownership.data(), o.ownership, sizeof(float) * ns);
+    r.pass_probability = o.pass_probability;
+    r.wdl[0] = o.wdl[0];
+    r.wdl[1] = o.wdl[1];
+    r.wdl[2] = o.wdl[2];
+    r.stm_winrate = o.stm_winrate;
+    r.final_score = o.final_score;
+    r.q_error = o.q_error;
+    r.score_error = o.score_error;
+    r.offset = input.offset;
+    r.board_size = input.board_size;
+    r.komi = input.komi;
+    r.fp16 = o.fp16 != 0;
+    return r;
 }
 
 bool CudaForwardPipe::Valid() const {
@@ -83,6 +115,7 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
     }
     BatchForwardPipe::SetForwardingSize(batch_size);
     if (engine_ && !weights && board_size_ == board_size && batch_size <= max_batch_per_nn_) {
+        ConfigureBatcher(batch_size);
         return;   // current engine already supports this configuration
     }
     if (engine_ && !weights) {
@@ -91,6 +124,7 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
         board_size_ = board_size;
         max_batch_per_nn_ = std::max(batch_size, max_batch_per_nn_);
         BatchForwardPipe::SetBoardSize(board_size);
+        ConfigureBatcher(batch_size);
         return;
     }
     Release();
@@ -153,11 +187,18 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
         throw std::runtime_error(std::string("sayuri_b200: ") + sb_last_error(nullptr));
     }
     num_gpus_ = sb_num_gpus(engine_);
+    ConfigureBatcher(max_batch_per_nn_);
     if (dump_gpu_info_) {
         LOGGING << Format("sayuri_b200: %d GPU replica(s), NN board %d, max batch %d, precision %s\n", num_gpus_,
                           board_size_, max_batch_per_nn_, precision == SB_PRECISION_FP16 ? "fp16" : "fp32-split");
     }
     dump_gpu_info_ = false;
+}
+
+void CudaForwardPipe::ConfigureBatcher(int batch_size) {
+    // SetForwardingSize + --gpu-waittime (ms, default 2: config.cc:59).  Our timer runs from the arrival of a batch's
+    // first position and a batch never waits for a busy GPU, so a tenth of the reference's wait is used.
+    if (engine_) Check(sb_batcher_config(engine_, batch_size, GetOption<int>("gpu_waittime") * 100), engine_);
 }
 
 void CudaForwardPipe::Release() {

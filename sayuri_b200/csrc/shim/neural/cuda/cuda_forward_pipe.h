@@ -36,7 +36,10 @@ public:
     virtual ~CudaForwardPipe();
 
 private:
+    void ConfigureBatcher(int batch_size);
+
     sb_engine* engine_{nullptr};
+    bool ref_batcher_{false};
     bool dump_gpu_info_{true};
     int max_batch_per_nn_{0};
     int board_size_{0};

@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsayuri_b200.so")
+# SAYURI_B200_LIB selects an alternative build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("SAYURI_B200_LIB") or os.path.join(HERE, "libsayuri_b200.so")
 
 MAX_INTERSECTIONS = 361
 INPUT_CHANNELS = 43
@@ -52,6 +53,17 @@ class SbOutput(ctypes.Structure):
                 ("fp16", ctypes.c_int)]
 
 
+PACKED_WORDS = 12
+PACKED_RAW = 1
+
+
+class SbPackedPosition(ctypes.Structure):
+    """sb_packed_position: exact 2.2 KB encoding of one InputData (include/sayuri_b200.h)."""
+    _fields_ = [("bits", (ctypes.c_uint32 * PACKED_WORDS) * INPUT_CHANNELS), ("scale", ctypes.c_float * INPUT_CHANNELS),
+                ("board_size", ctypes.c_int32), ("offset", ctypes.c_int32), ("flags", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
 OUTPUT_DTYPE = np.dtype([("probabilities", np.float32, MAX_INTERSECTIONS), ("ownership", np.float32, MAX_INTERSECTIONS),
                          ("pass_probability", np.float32), ("wdl", np.float32, 3), ("stm_winrate", np.float32),
                          ("final_score", np.float32), ("q_error", np.float32), ("score_error", np.float32),
@@ -65,6 +77,7 @@ ABI_SYMBOLS = [
     "sb_forward_batch", "sb_submit", "sb_wait", "sb_host_alloc", "sb_host_free", "sb_weights_blob",
     "sb_weights_export", "sb_weights_import",
     "sb_weights_checksum", "sb_time_forward", "sb_launch_count", "sb_debug_read_trunk", "sb_conv_stats", "sb_set_option",
+    "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
 ]
 
 _lib = None
@@ -111,8 +124,34 @@ def load_library():
     lib.sb_debug_read_trunk.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F]
     lib.sb_conv_stats.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     lib.sb_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    lib.sb_pack_position.argtypes = [_F, ctypes.c_int, ctypes.c_int, ctypes.POINTER(SbPackedPosition)]
+    lib.sb_unpack_position.argtypes = [ctypes.POINTER(SbPackedPosition), _F]
+    lib.sb_eval.argtypes = [vp, _F, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.sb_batcher_config.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.sb_batcher_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
+    lib.sb_eval_throughput.argtypes = [vp, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+    lib.sb_eval_throughput.restype = ctypes.c_double
     _lib = lib
     return lib
+
+
+def pack_position(planes, board_size, offset=0):
+    """sb_pack_position: (record, ok).  ok == False means the planes are not two-valued per plane (raw fallback)."""
+    a = np.ascontiguousarray(planes, dtype=np.float32).ravel()
+    if a.size < INPUT_CHANNELS * board_size * board_size:
+        raise ValueError("planes array smaller than 43*bs*bs")
+    rec = SbPackedPosition()
+    ok = load_library().sb_pack_position(a.ctypes.data_as(_F), board_size, offset, ctypes.byref(rec))
+    return rec, bool(ok)
+
+
+def unpack_position(rec):
+    """sb_unpack_position: fp32 planes [43, bs*bs] of a packed record (host inverse, for tests)."""
+    n = rec.board_size * rec.board_size
+    out = np.zeros(INPUT_CHANNELS * n, dtype=np.float32)
+    if not load_library().sb_unpack_position(ctypes.byref(rec), out.ctypes.data_as(_F)):
+        raise ValueError("record is flagged raw")
+    return out.reshape(INPUT_CHANNELS, n)
 
 
 class PinnedArray:
@@ -239,9 +278,58 @@ class B200ForwardPipe:
         self._check(self._lib.sb_forward_batch(self._h, gpu, n, ptrs, sizes, offs, out.ctypes.data))
         return out
 
+    def time_batch_forward_host(self, gpu, planes_list, board_sizes, offsets, seconds):
+        """Wall-clock throughput of the blocking sb_forward_batch call with pageable host buffers (argument
+        marshalling hoisted out of the loop).  Returns (evals/s, ms per call)."""
+        import time
+        n = len(planes_list)
+        keep = [np.ascontiguousarray(p, dtype=np.float32).ravel() for p in planes_list]
+        ptrs = (_F * n)(*[a.ctypes.data_as(_F) for a in keep])
+        sizes = (ctypes.c_int * n)(*[int(b) for b in board_sizes])
+        offs = (ctypes.c_int * n)(*[int(o) for o in offsets])
+        out = np.zeros(n, dtype=OUTPUT_DTYPE)
+        iters = 0
+        t0 = time.perf_counter()
+        while True:
+            self._check(self._lib.sb_forward_batch(self._h, gpu, n, ptrs, sizes, offs, out.ctypes.data))
+            iters += 1
+            el = time.perf_counter() - t0
+            if el >= seconds:
+                break
+        return iters * n / el, 1e3 * el / iters
+
     def forward(self, planes, board_size, offset=0, gpu=0):
         """NetworkForwardPipe::Forward for one InputData."""
         return self.batch_forward(gpu, [planes], [board_size], [offset])[0]
+
+    # ---- the batcher: NetworkForwardPipe::Forward from any number of threads (sb_eval) ----------------
+    def eval(self, planes, board_size, offset=0):
+        """Blocking, thread-safe single-position evaluation through the engine's own batcher (ctypes releases the
+        GIL during the call, so Python threads batch together like the front-end's search threads)."""
+        a = np.ascontiguousarray(planes, dtype=np.float32).ravel()
+        if a.size < INPUT_CHANNELS * board_size * board_size:
+            raise ValueError("planes array smaller than 43*bs*bs")
+        out = np.zeros(1, dtype=OUTPUT_DTYPE)
+        self._check(self._lib.sb_eval(self._h, a.ctypes.data_as(_F), board_size, offset, out.ctypes.data))
+        return out[0]
+
+    def batcher_config(self, batch_size=0, wait_us=-1):
+        self._check(self._lib.sb_batcher_config(self._h, batch_size, wait_us))
+
+    def batcher_stats(self):
+        buf = (ctypes.c_longlong * 6)()
+        self._check(self._lib.sb_batcher_stats(self._h, buf))
+        return dict(zip(("batches", "positions", "full", "timer", "raw", "workers"), [int(v) for v in buf]))
+
+    def eval_throughput(self, positions, board_size, threads, seconds):
+        """positions: [n_pos, 43*361] float32 (records SB_PLANE_FLOATS apart).  Native host threads, wall clock."""
+        a = np.ascontiguousarray(positions, dtype=np.float32)
+        if a.ndim != 2 or a.shape[1] != PLANE_FLOATS:
+            raise ValueError("positions must be [n_pos, 43*361]")
+        v = self._lib.sb_eval_throughput(self._h, a.ctypes.data_as(_F), a.shape[0], board_size, threads, seconds)
+        if v < 0:
+            self._check(int(v))
+        return float(v)
 
     def submit(self, gpu, slot, planes, board_sizes, offsets, plane_stride=PLANE_FLOATS):
         """planes: contiguous float32 array (ideally a PinnedArray.array) of n records plane_stride apart."""

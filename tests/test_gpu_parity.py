@@ -283,3 +283,103 @@ def test_full_size_config2_properties(eng, oracle_lib):
         assert np.isfinite(out["probabilities"]).all()
     finally:
         pipe.destroy()
+
+
+FIELDS = ("probabilities", "ownership", "pass_probability", "wdl", "stm_winrate", "final_score", "q_error", "score_error")
+
+
+def test_packed_records_equal_fp32_staging_bit_exact_and_raw_fallback(golden_pipe, oracle_lib, golden_weights_bin):
+    """The compact host->device records (sb_pack_position) are an EXACT encoding: outputs are bit-identical to the
+    fp32 staging path; a position with a many-valued plane travels raw inside the same batch and still matches the
+    oracle."""
+    from sayuri_b200 import synth
+    sizes = [19, 9, 13, 19, 13]
+    planes = [synth.synth_positions(1, bs, seed=900 + i)[0].ravel().copy() for i, bs in enumerate(sizes)]
+    offs = [0, 1, 2, 3, 4]
+    golden_pipe.set_option("pack_inputs", 0)
+    plain = golden_pipe.batch_forward(0, planes, sizes, offs)
+    golden_pipe.set_option("pack_inputs", 1)
+    packed = golden_pipe.batch_forward(0, planes, sizes, offs)
+    for f in FIELDS:
+        assert np.array_equal(plain[f], packed[f]), f
+    # make sample 3 unpackable: a plane with several different non-zero values
+    rng = np.random.default_rng(5)
+    planes[3].reshape(43, -1)[7] = rng.uniform(-1, 1, 361).astype(np.float32)
+    from sayuri_b200 import engine
+    assert not engine.pack_position(planes[3], 19)[1]
+    mixed = golden_pipe.batch_forward(0, planes, sizes, offs)
+    golden_pipe.set_option("pack_inputs", 0)
+    mixed_plain = golden_pipe.batch_forward(0, planes, sizes, offs)
+    golden_pipe.set_option("pack_inputs", 1)
+    for f in FIELDS:
+        assert np.array_equal(mixed[f], mixed_plain[f]), f
+    for i in (0, 1, 2, 4):
+        assert np.array_equal(mixed[i]["probabilities"], packed[i]["probabilities"])
+    orc = oracle_lib.Oracle(golden_weights_bin)
+    _check(mixed[3], orc.forward(planes[3], 19, 3), 19)
+
+
+def test_batcher_eval_from_many_threads_is_bit_identical_to_batch_forward(eng, golden_weights_bin):
+    """sb_eval (NetworkForwardPipe::Forward from many threads, the engine's own batcher) returns, for every position,
+    exactly what sb_forward_batch returns for it: batch composition is decided by thread timing and must not
+    matter.  Also covers a raw-fallback position and mixed board sizes."""
+    import threading
+    from sayuri_b200 import synth
+    sizes = [(19, 13, 9)[i % 3] for i in range(48)]
+    planes = [synth.synth_positions(1, bs, seed=1200 + i)[0].ravel().copy() for i, bs in enumerate(sizes)]
+    planes[5].reshape(43, -1)[11, :20] = np.linspace(0.1, 0.9, 20, dtype=np.float32)   # unpackable
+    offs = [i % 5 for i in range(48)]
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 16, gpus=[0])
+    try:
+        ref = np.concatenate([pipe.batch_forward(0, planes[i:i + 16], sizes[i:i + 16], offs[i:i + 16]) for i in (0, 16, 32)])
+        pipe.batcher_config(batch_size=8, wait_us=2000)
+        got = [None] * 48
+
+        def worker(t):
+            for i in range(t, 48, 12):
+                got[i] = pipe.eval(planes[i], sizes[i], offs[i])
+
+        for rounds in range(2):
+            ts = [threading.Thread(target=worker, args=(t,)) for t in range(12)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            for i in range(48):
+                for f in FIELDS:
+                    assert np.array_equal(got[i][f], ref[i][f]), (rounds, i, f)
+                assert got[i]["board_size"] == sizes[i] and got[i]["offset"] == offs[i]
+        st = pipe.batcher_stats()
+        assert st["positions"] == 96 and st["raw"] == 2 and st["workers"] == 2 and st["batches"] >= 12
+        with pytest.raises(RuntimeError, match="exceeds the NN canvas"):
+            pipe.eval(planes[0], 21, 0)
+        # single caller: closed by the timer, still exact
+        one = pipe.eval(planes[0], sizes[0], offs[0])
+        assert np.array_equal(one["probabilities"], ref[0]["probabilities"])
+        # reconfigure stops the workers; the next eval restarts them on the new geometry
+        pipe.construct(batch_size=32)
+        again = pipe.eval(planes[1], sizes[1], offs[1])
+        assert np.array_equal(again["ownership"], ref[1]["ownership"])
+    finally:
+        pipe.destroy()
+
+
+def test_tail_wave_split_is_bit_exact(eng):
+    """conv3x3_tc2 splits the work items of a partial last wave into N-halves (conv_unit): same MMAs per output
+    element in the same order, so the results are bit-identical with the split on and off.  Batch 100 of a 128-wide
+    net gives 157 items over 74 CTA pairs: 2 full waves + 9 items, which do get split."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_4bx128.bin")
+    synth.write_synth_net(path, (4, 128, 16, 16), seed=77)
+    n = 100
+    x = synth.synth_positions(n, 19, seed=31).reshape(n, -1)
+    for prec in (eng.PRECISION_FP32_SPLIT, eng.PRECISION_FP16):
+        pipe = eng.B200ForwardPipe().initialize(path, 19, n, gpus=[0], precision=prec)
+        try:
+            pipe.set_option("tail_split", 1)
+            a = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
+            pipe.set_option("tail_split", 0)
+            b = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
+            for f in FIELDS:
+                assert np.array_equal(a[f], b[f]), (prec, f)
+            assert np.isfinite(a["probabilities"]).all()
+        finally:
+            pipe.destroy()

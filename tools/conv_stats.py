@@ -14,7 +14,9 @@ ap.add_argument("--net", default="10bx128")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--precision", type=int, default=0)
 ap.add_argument("--dbg", type=int, default=0)
-ap.add_argument("--impl", type=int, default=1)
+ap.add_argument("--impl", type=int, default=2)
+ap.add_argument("--tail-split", type=int, default=1)
+ap.add_argument("--launch", type=int, default=2, help="conv launch index within the forward (2 = second tower conv)")
 a = ap.parse_args()
 path = os.path.join(tempfile.gettempdir(), "stats_%s.bin" % a.net)
 synth.write_synth_net(path, a.net, seed=1)
@@ -22,14 +24,18 @@ pipe = engine.B200ForwardPipe().initialize(path, 19, a.batch, gpus=[0], precisio
 x = synth.synth_positions(min(a.batch, 32), 19, seed=3).reshape(-1, engine.PLANE_FLOATS)
 planes = [x[i % x.shape[0]] for i in range(a.batch)]
 pipe.set_option("conv_impl", a.impl)
+pipe.set_option("tail_split", a.tail_split)
 pipe.batch_forward(0, planes, [19] * a.batch, [0] * a.batch)
 pipe.set_option("stats", 1)
+pipe.set_option("stats_launch", a.launch)
 pipe.set_option("conv_dbg", a.dbg)
 pipe.batch_forward(0, planes, [19] * a.batch, [0] * a.batch)
 st = pipe.conv_stats(0, 0).astype(np.float64)
 st = st[st[:, 6] > 0]
 names = ["mma_total", "wait_tmem_empty", "wait_slab", "wait_b", "epi_wait_full", "epi_total", "items", "epi_drain"]
-print("net %s batch %d precision %d dbg %d: %d CTAs" % (a.net, a.batch, a.precision, a.dbg, st.shape[0]))
+ms, conv_ms, conv_n = pipe.time_forward(0, 0, 10, flush_l2=True, profile_conv=True)
+print("net %s batch %d precision %d dbg %d tail_split %d launch %d: %d clusters; forward %.3f ms, convs %.3f ms over %d launches" % (
+    a.net, a.batch, a.precision, a.dbg, a.tail_split, a.launch, st.shape[0], float(np.median(ms)), conv_ms, conv_n))
 for i, n in enumerate(names):
     col = st[:, i]
     print("  %-16s mean %10.0f  min %10.0f  max %10.0f" % (n, col.mean(), col.min(), col.max()))
