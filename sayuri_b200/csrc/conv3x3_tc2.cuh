@@ -28,6 +28,13 @@ namespace sb {
 constexpr int kTileRows2 = 128;                              // rows per CTA per item
 constexpr int kSlabRows2 = kTileRows2 + 2 * kSlabMargin;     // 176
 
+// Programmatic dependent launch: consecutive convolutions of a forward are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of layer L+1 become resident as soon as the CTAs of
+// layer L leave their SM, run their prologue (barrier init, TMEM alloc, bias, first WEIGHT stages: constants) and
+// block in griddepcontrol.wait only before touching activations written (or still read) by layer L.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <bool SPLIT>
 struct Conv2Cfg {
     static constexpr int kParts = SPLIT ? 2 : 1;
@@ -196,9 +203,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     cluster_sync_all();     // barriers of both CTAs are initialised before any remote arrive / TMA credit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x == 0) pdl_launch_dependents();   // the next layer may start its prologue whenever SMs free up
 
     if (warp == 3) {
         // ===================== activation-slab producer (own 128-row tile, +-24 rows) =====================
+        pdl_wait();   // the slabs are the previous layer's output
         uint32_t it = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
             const int st = conv_unit(item, p).st;
@@ -336,6 +345,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         long long t_wait_full = 0, t_drain = 0;
         const long long t_begin = stats ? clock64() : 0;
         const uint32_t empty0 = mapa_u32(tmem_empty, 0);   // leader's tmem_empty[0]; [1] is +8
+        pdl_wait();   // residual reads, and our stores may overwrite a buffer the previous layer still reads
         for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
             const ConvUnit w = conv_unit(item, p);
             const int st = w.st;

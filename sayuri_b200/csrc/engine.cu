@@ -266,6 +266,7 @@ struct ActBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_done = nullptr;   // forward of this slot has finished computing (before its D2H)
     float* h_in = nullptr;     // pinned [max_batch][SB_PLANE_FLOATS]
     float* d_in = nullptr;
     int* h_meta = nullptr;     // pinned [2][max_batch]: board sizes, policy offsets
@@ -294,8 +295,10 @@ struct Slot {
 struct DevConv {
     ConvLayout L;
     CUtensorMap tm_hi, tm_lo;     // box [bn][64]
-    CUtensorMap tm2_hi, tm2_lo;   // box [bn/2][64]: one CTA's half in the CTA-pair kernel
-    CUtensorMap tm2q_hi, tm2q_lo; // box [bn/4][64]: one CTA's half of a half unit (tail wave, conv_unit)
+    // CTA-pair kernel: box [(bn >> level) / 2][64] = one CTA's half of an N tile of width bn >> level.  Level 0 is the
+    // throughput shape; levels 1-2 spread small batches over more CTA pairs and serve the tail-wave half units.
+    CUtensorMap tm2_hi[4], tm2_lo[4];
+    int levels = 1;               // usable N widths: bn >> 0 .. bn >> (levels - 1), each a multiple of 16
     float* wT = nullptr;  // fp32 [9*cinp][cout], SIMT debug only
 };
 
@@ -306,6 +309,11 @@ struct Replica {
     std::vector<DevConv> conv1, conv2;
     std::vector<Slot> slots;
     std::vector<Slot> bslots;     // the batcher's own slots (sb_eval), allocated when its workers start
+    // Forwards of different slots are chained on the device: H2D / D2H copies of one slot overlap the other slot's
+    // kernels, but two forwards never interleave (each conv launch fills the GPU anyway, and two interleaved batches
+    // evict each other's activations from L2).
+    std::unique_ptr<std::mutex> chain_mutex{new std::mutex};
+    cudaEvent_t chain_tail = nullptr;   // ev_done of the forward enqueued last on this replica
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     int sm_count = 0;
@@ -365,6 +373,9 @@ struct sb_engine {
     int desc_swap = 0;
     int conv_dbg = 0;
     int conv_impl = 2;   // 1 = single-CTA conv3x3_tc, 2 = CTA-pair conv3x3_tc2 (default)
+    int chain_forwards = 1;      // forwards of different slots of a replica run back to back, never interleaved
+    int small_batch_split = 1;   // narrower N tiles when a batch does not fill one wave of CTA pairs
+    int use_pdl = 1;     // programmatic dependent launch between consecutive conv3x3_tc2 launches
     int tail_split = 1;  // split the items of a partial last wave into N-halves (conv3x3_tc2)
     int pack_inputs = 1; // pageable inputs travel as compact exact records (host_pack.cc); 0 = always fp32 staging
     int pack_threads = 4;
@@ -391,6 +402,7 @@ static void FreeSlot(Slot& s) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.ev_a) cudaEventDestroy(s.ev_a);
     if (s.ev_b) cudaEventDestroy(s.ev_b);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
     cudaFreeHost(s.h_in);
     cudaFree(s.d_in);
     cudaFreeHost(s.h_meta);
@@ -444,6 +456,7 @@ static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int
         SB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         SB_CUDA(cudaEventCreate(&s.ev_a));
         SB_CUDA(cudaEventCreate(&s.ev_b));
+        SB_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
         const size_t in_bytes = (size_t)e->max_batch * SB_PLANE_FLOATS * sizeof(float);
         SB_CUDA(cudaHostAlloc(&s.h_in, in_bytes, cudaHostAllocDefault));
         SB_CUDA(cudaMalloc(&s.d_in, in_bytes));
@@ -481,11 +494,18 @@ static void MakeConvMaps(const Replica& r, DevConv& c) {
     const int K = c.L.taps * c.L.cinp;
     c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, c.L.bn);
     c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, c.L.bn);
-    c.tm2_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, c.L.bn / 2);
-    c.tm2_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, c.L.bn / 2);
-    const int q = c.L.bn % 32 == 0 ? c.L.bn / 4 : c.L.bn / 2;   // half units need N/2 to be a multiple of 16
-    c.tm2q_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, q);
-    c.tm2q_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, q);
+    c.levels = 0;
+    for (int lv = 0; lv < 4; ++lv) {
+        const int bn = c.L.bn >> lv;
+        if (bn < 16 || bn % 16 || (bn << lv) != c.L.bn) break;    // UMMA N (M = 256) must be a multiple of 16
+        c.tm2_hi[lv] = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, bn / 2);
+        c.tm2_lo[lv] = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, bn / 2);
+        c.levels = lv + 1;
+    }
+    for (int lv = c.levels; lv < 4; ++lv) {
+        c.tm2_hi[lv] = c.tm2_hi[c.levels - 1];
+        c.tm2_lo[lv] = c.tm2_lo[c.levels - 1];
+    }
 }
 
 // fp32 transposed weights for the SIMT cross-check kernel, derived from the packed hi/lo matrices.
@@ -615,21 +635,47 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         const int items = n_super * c.L.ntiles;
         const int grid = std::min(items, r.sm_count);
         if (e->conv_impl == 2) {
+            // Small batches: narrow the N tile (bn >> level) while all items still fit in one wave, so that a handful of
+            // positions is spread over up to 4x more CTA pairs (latency of the single-position / GTP case).
+            int level = 0;
+            const int max_pairs = r.sm_count / 2;
+            while (e->small_batch_split && level + 1 < c.levels && level < 2 &&
+                   n_super * (c.L.cout / (c.L.bn >> (level + 1))) <= max_pairs)
+                ++level;
+            p.bn = c.L.bn >> level;
+            p.n_ntiles = c.L.cout / p.bn;
+            const int items2 = n_super * p.n_ntiles;
             // persistent CTA pairs; the items of a partial last wave are split into N-halves when that makes the
             // wave half as long (conv_unit in conv3x3_tc2.cuh)
-            const int pairs = std::min(items, r.sm_count / 2);
+            const int pairs = std::min(items2, max_pairs);
             const int grid2 = 2 * pairs;
-            const int rem = items % pairs;
+            const int rem = items2 % pairs;
             int n_tail = 0;
-            if (e->tail_split && items > pairs && rem > 0 && 2 * rem <= pairs && c.L.bn % 32 == 0) n_tail = rem;
-            p.n_full = items - n_tail;
-            p.n_units = items + n_tail;
+            if (e->tail_split && items2 > pairs && rem > 0 && 2 * rem <= pairs && level + 1 < c.levels) n_tail = rem;
+            p.n_full = items2 - n_tail;
+            p.n_units = items2 + n_tail;
+            const CUtensorMap& w_hi = c.tm2_hi[level];
+            const CUtensorMap& w_lo = c.tm2_lo[level];
+            const CUtensorMap& wq_hi = c.tm2_hi[level + 1];
+            const CUtensorMap& wq_lo = c.tm2_lo[level + 1];
+            // launched with the programmatic-stream-serialization attribute: see pdl_wait() in conv3x3_tc2.cuh
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid2);
+            cfg.blockDim = dim3(384);
+            cfg.stream = s.stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
             if (Split(e)) {
-                SB_DISPATCH_ACT(act, ACT, (conv3x3_tc2_kernel<true, ACT><<<grid2, 384, Conv2Cfg<true>::kSmemBytes, s.stream>>>(
-                                              in.tm3_hi, in.tm3_lo, c.tm2_hi, c.tm2_lo, c.tm2q_hi, c.tm2q_lo, p)));
+                cfg.dynamicSmemBytes = Conv2Cfg<true>::kSmemBytes;
+                SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, ACT>, in.tm3_hi, in.tm3_lo, w_hi,
+                                                                      w_lo, wq_hi, wq_lo, p)));
             } else {
-                SB_DISPATCH_ACT(act, ACT, (conv3x3_tc2_kernel<false, ACT><<<grid2, 384, Conv2Cfg<false>::kSmemBytes, s.stream>>>(
-                                              in.tm3_hi, in.tm3_hi, c.tm2_hi, c.tm2_hi, c.tm2q_hi, c.tm2q_hi, p)));
+                cfg.dynamicSmemBytes = Conv2Cfg<false>::kSmemBytes;
+                SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT>, in.tm3_hi, in.tm3_hi, w_hi,
+                                                                      w_hi, wq_hi, wq_hi, p)));
             }
         } else if (Split(e)) {
             SB_DISPATCH_ACT(act, ACT, (conv3x3_tc_kernel<true, ACT><<<grid, 384, ConvCfg<true>::kSmemBytes, s.stream>>>(
@@ -728,6 +774,19 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     e->launches += 2;
 }
 
+// Enqueue one forward on the slot's stream, ordered after the forward enqueued last on the same replica.
+static void EnqueueChainedForward(sb_engine* e, Replica& r, Slot& s, int n) {
+    if (!e->chain_forwards) {
+        EnqueueForward(e, r, s, n);
+        return;
+    }
+    std::lock_guard<std::mutex> lk(*r.chain_mutex);
+    if (r.chain_tail && r.chain_tail != s.ev_done) SB_CUDA(cudaStreamWaitEvent(s.stream, r.chain_tail, 0));
+    EnqueueForward(e, r, s, n);
+    SB_CUDA(cudaEventRecord(s.ev_done, s.stream));
+    r.chain_tail = s.ev_done;
+}
+
 static void CheckSlotError(Slot& s, cudaError_t err, const char* what) {
     if (err == cudaSuccess) return;
     std::string msg = std::string("CUDA Error: ") + cudaGetErrorString(err) + " in " + what;
@@ -743,6 +802,7 @@ static void Configure(sb_engine* e, int board, int max_batch) {
         SB_CUDA(cudaSetDevice(r.device));
         for (Slot& s : r.slots) FreeSlot(s);
         r.slots.clear();
+        r.chain_tail = nullptr;
         AllocSlots(e, r);
     }
 }
@@ -897,7 +957,7 @@ static int SubmitImpl(sb_engine* e, int gpu, int slot, int n, const float* plane
             SB_CUDA(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)n * SB_PLANE_FLOATS * sizeof(float), cudaMemcpyHostToDevice, s.stream));
         }
         s.n = n;
-        EnqueueForward(e, r, s, n);
+        EnqueueChainedForward(e, r, s, n);
         SB_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * kOutFloats * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         s.busy = true;
     } catch (const CudaError& ce) {
@@ -989,7 +1049,7 @@ static void RunHostBatch(sb_engine* e, Replica& r, Slot& s, HostBatch& hb) {
         }
         s.n = n;
         s.packed = true;
-        EnqueueForward(e, r, s, n);
+        EnqueueChainedForward(e, r, s, n);
         SB_CUDA(cudaMemcpyAsync(hb.out, s.d_out, (size_t)n * kOutFloats * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         CheckSlotError(s, cudaStreamSynchronize(s.stream), "batched forward");
         hb.rc = SB_OK;
@@ -1064,6 +1124,7 @@ static void StopBatcher(sb_engine* e) {
         if (r.device >= 0) cudaSetDevice(r.device);
         for (Slot& s : r.bslots) FreeSlot(s);
         r.bslots.clear();
+        r.chain_tail = nullptr;
     }
     e->batcher_on.store(false, std::memory_order_release);
     e->batcher.reset();
@@ -1556,6 +1617,18 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     }
     if (!std::strcmp(key, "pack_threads")) {
         e->pack_threads = std::max(1, value);
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "chain_forwards")) {
+        e->chain_forwards = value ? 1 : 0;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "small_batch_split")) {
+        e->small_batch_split = value ? 1 : 0;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "pdl")) {
+        e->use_pdl = value ? 1 : 0;
         return SB_OK;
     }
     if (!std::strcmp(key, "tail_split")) {

@@ -350,7 +350,7 @@ def test_batcher_eval_from_many_threads_is_bit_identical_to_batch_forward(eng, g
         st = pipe.batcher_stats()
         assert st["positions"] == 96 and st["raw"] == 2 and st["workers"] == 2 and st["batches"] >= 12
         with pytest.raises(RuntimeError, match="exceeds the NN canvas"):
-            pipe.eval(planes[0], 21, 0)
+            pipe.eval(np.zeros(43 * 21 * 21, dtype=np.float32), 21, 0)
         # single caller: closed by the timer, still exact
         one = pipe.eval(planes[0], sizes[0], offs[0])
         assert np.array_equal(one["probabilities"], ref[0]["probabilities"])
