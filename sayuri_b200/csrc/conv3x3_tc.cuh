@@ -42,6 +42,7 @@ struct ConvParams {
     int bn;                  // UMMA N = output channels per work item (multiple of 16, <= 128)
     int n_super;             // number of 256-row work items along M
     int n_ntiles;            // cout / bn
+    int resident;            // conv3x3_tc2, fp16 rung: this CTA's weights fit the stage ring and are loaded once per launch
     int n_full, n_units;     // conv3x3_tc2 only: whole items, and whole items + half units of the tail wave
     int pitch;               // P = N + 1
     int ntaps;               // 9 = 3x3 convolution, 1 = 1x1 convolution (centre tap only)

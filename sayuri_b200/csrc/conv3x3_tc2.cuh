@@ -42,14 +42,17 @@ struct Conv2Cfg {
     static constexpr int kSlabBytes = kParts * kSlabPartBytes;
     static constexpr int kNumSlabs = SB_TC2_NA;
     static constexpr int kBStageBytes = 64 * 128;                    // this CTA's half: up to 64 rows x 64 fp16
-    static constexpr int kNumBStages = SB_TC2_NB;
+    // fp16 rung: 18 stages x 8 KB hold ALL of this CTA's weights of a C <= 128 layer (9 taps x 2 k-halves): they are
+    // then loaded once per launch and stay resident (ConvParams::resident), instead of being re-streamed for every
+    // work item (147 KB per item per CTA, the L2 -> SM bound of this rung).  The split rung has no room for that.
+    static constexpr int kNumBStages = SPLIT ? SB_TC2_NB : 18;
     static constexpr int kOffB = kNumSlabs * kSlabBytes;
     static constexpr int kOffBar = kOffB + kNumBStages * kBStageBytes;
     static constexpr int kOffBias = kOffBar + 512;
     static constexpr int kSmemBytes = kOffBias + 256 * 4 + 1024;
     static constexpr int kTmemCols = 512;
     static constexpr int kThreads = 384;
-    static_assert(kNumBStages <= 16 && kNumSlabs <= 4, "barrier block layout");
+    static_assert(kNumBStages <= 18 && kNumSlabs <= 4, "barrier block layout");
     static_assert(kSlabPartBytes % 1024 == 0, "slab parts must keep the weight stages 1024-byte aligned");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
@@ -155,10 +158,13 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t bar_addr = smem_base + Cfg::kOffBar;
     const uint32_t a_full = bar_addr + 0, a_empty = bar_addr + 32;                // [3] each
     const uint32_t tmem_full = bar_addr + 64, tmem_empty = bar_addr + 80;         // [2] each
-    const uint32_t b_full = bar_addr + 128, b_empty = bar_addr + 256;             // [<= 16] each
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 384);
+    const uint32_t b_full = bar_addr + 128, b_empty = bar_addr + 288;             // [<= 18] each
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 448);
     float* sbias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
-    constexpr uint32_t kNB = Cfg::kNumBStages, kNA = Cfg::kNumSlabs;
+    constexpr uint32_t kNA = Cfg::kNumSlabs;
+    // resident weights: the ring is exactly one item's worth of stages, filled once, never recycled
+    const bool resident = p.resident != 0;
+    const uint32_t kNB = resident ? (uint32_t)(p.kh * p.ntaps * Cfg::kParts) : (uint32_t)Cfg::kNumBStages;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -178,7 +184,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             mbar_init(tmem_full + 8 * i, 1);
             mbar_init(tmem_empty + 8 * i, 16);  // 8 epilogue warps x 2 CTAs
         }
-        for (int i = 0; i < (int)kNB; ++i) {
+        for (int i = 0; i < Cfg::kNumBStages; ++i) {
             mbar_init(b_full + 8 * i, 1);
             mbar_init(b_empty + 8 * i, 1);
         }
@@ -232,6 +238,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         // ===================== weight-stage producer (own N-half of every block) =====================
         uint32_t it = 0;
         for (int item = cluster_id; item < n_items && !(p.dbg & 16); item += n_clusters) {
+            if (resident && item != cluster_id) break;     // everything is already in shared memory
             const ConvUnit w = conv_unit(item, p);
             const int HB = w.bn >> 1;                      // weight rows staged by this CTA
             const bool whole = w.bn == BN;
@@ -284,7 +291,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         const uint32_t first = (h | tap) == 0 ? 0u : 1u;
                         const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
                         {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
-                            const uint32_t bs = b_it % kNB, bph = (b_it / kNB) & 1u;
+                            const uint32_t bs = b_it % kNB, bph = resident ? 0u : (b_it / kNB) & 1u;
                             if (stats) t0 = clock64();
                             if (!(p.dbg & 16)) mbar_wait(b_full + 8 * bs, bph, p.err, 5);
                             if (stats) t_wait_b += clock64() - t0;
@@ -304,7 +311,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             ++b_it;
                         }
                         if (SPLIT) {   // weights lo x activations hi -> lo accumulator
-                            const uint32_t bs = b_it % kNB, bph = (b_it / kNB) & 1u;
+                            const uint32_t bs = b_it % kNB, bph = resident ? 0u : (b_it / kNB) & 1u;
                             if (stats) t0 = clock64();
                             if (!(p.dbg & 16)) mbar_wait(b_full + 8 * bs, bph, p.err, 6);
                             if (stats) t_wait_b += clock64() - t0;
@@ -353,6 +360,27 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const int cbase = half ? c_split : 0;
             const int HC = half ? w.bn - c_split : c_split;        // columns of this thread (multiple of 16, may be 0)
             const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+
+            // Everything the epilogue needs from global memory is requested BEFORE waiting for the accumulators: the
+            // mask byte and the residual pieces of the first 16-column group; the pieces of group g+1 are requested
+            // while group g is being computed (a load issued at its point of use stalled ~1 us four times per item).
+            const int row = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 + q * 32 + lane;
+            const bool live = p.mask[row] != 0;
+            const bool has_res = live && p.res_hi != nullptr && !(p.dbg & 1);
+            const size_t chunk_stride = (size_t)p.rows * 8;
+            const size_t off = act_index(row, w.n0 + cbase, p.rows);
+            uint4 rh[2][2], rl[2][2];
+            rh[0][0] = rh[0][1] = rh[1][0] = rh[1][1] = make_uint4(0u, 0u, 0u, 0u);
+            rl[0][0] = rl[0][1] = rl[1][0] = rl[1][1] = make_uint4(0u, 0u, 0u, 0u);
+            if (has_res && HC > 0) {
+                rh[0][0] = *reinterpret_cast<const uint4*>(p.res_hi + off);
+                rh[0][1] = *reinterpret_cast<const uint4*>(p.res_hi + off + chunk_stride);
+                if (SPLIT) {
+                    rl[0][0] = *reinterpret_cast<const uint4*>(p.res_lo + off);
+                    rl[0][1] = *reinterpret_cast<const uint4*>(p.res_lo + off + chunk_stride);
+                }
+            }
+
             const long long t0 = stats ? clock64() : 0;
             mbar_wait(tmem_full + 8 * as, aph, p.err, 7);
             if (stats) t_wait_full += clock64() - t0;
@@ -385,33 +413,34 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (lane == 0) mbar_arrive_cluster(empty0 + 8 * as);   // accumulator stage is free again
             if (stats) t_drain += clock64() - t_d0;
 
-            const int row = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 + q * 32 + lane;
-            const bool live = p.mask[row] != 0;
-            const size_t chunk_stride = (size_t)p.rows * 8;
-            const size_t off = act_index(row, w.n0 + cbase, p.rows);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 if (g * 16 < HC) {
                     const int c0 = g * 16;
+                    const size_t o0 = off + (size_t)(c0 >> 3) * chunk_stride, o1 = o0 + chunk_stride;
+                    if (has_res && (g + 1) * 16 < HC) {   // next group's residual pieces
+                        const size_t n0 = o0 + 2 * chunk_stride, n1 = n0 + chunk_stride;
+                        rh[(g + 1) & 1][0] = *reinterpret_cast<const uint4*>(p.res_hi + n0);
+                        rh[(g + 1) & 1][1] = *reinterpret_cast<const uint4*>(p.res_hi + n1);
+                        if (SPLIT) {
+                            rl[(g + 1) & 1][0] = *reinterpret_cast<const uint4*>(p.res_lo + n0);
+                            rl[(g + 1) & 1][1] = *reinterpret_cast<const uint4*>(p.res_lo + n1);
+                        }
+                    }
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[w.n0 + cbase + c0 + i];
-                    const size_t o0 = off + (size_t)(c0 >> 3) * chunk_stride, o1 = o0 + chunk_stride;
-                    if (live && p.res_hi != nullptr && !(p.dbg & 1)) {
-                        const uint4 a0 = *reinterpret_cast<const uint4*>(p.res_hi + o0);
-                        const uint4 a1 = *reinterpret_cast<const uint4*>(p.res_hi + o1);
-                        const __half* hh0 = reinterpret_cast<const __half*>(&a0);
-                        const __half* hh1 = reinterpret_cast<const __half*>(&a1);
+                    if (has_res) {
+                        const __half* hh0 = reinterpret_cast<const __half*>(&rh[g & 1][0]);
+                        const __half* hh1 = reinterpret_cast<const __half*>(&rh[g & 1][1]);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             v[i] += __half2float(hh0[i]);
                             v[8 + i] += __half2float(hh1[i]);
                         }
                         if (SPLIT) {
-                            const uint4 b0 = *reinterpret_cast<const uint4*>(p.res_lo + o0);
-                            const uint4 b1 = *reinterpret_cast<const uint4*>(p.res_lo + o1);
-                            const __half* ll0 = reinterpret_cast<const __half*>(&b0);
-                            const __half* ll1 = reinterpret_cast<const __half*>(&b1);
+                            const __half* ll0 = reinterpret_cast<const __half*>(&rl[g & 1][0]);
+                            const __half* ll1 = reinterpret_cast<const __half*>(&rl[g & 1][1]);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 v[i] += __half2float(ll0[i]);

@@ -373,6 +373,7 @@ struct sb_engine {
     int desc_swap = 0;
     int conv_dbg = 0;
     int conv_impl = 2;   // 1 = single-CTA conv3x3_tc, 2 = CTA-pair conv3x3_tc2 (default)
+    int resident_weights = 1;    // fp16 rung: keep a C <= 128 layer's weights in shared memory for the whole launch
     int chain_forwards = 1;      // forwards of different slots of a replica run back to back, never interleaved
     int small_batch_split = 1;   // narrower N tiles when a batch does not fill one wave of CTA pairs
     int use_pdl = 1;     // programmatic dependent launch between consecutive conv3x3_tc2 launches
@@ -624,6 +625,7 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.n_ntiles = c.L.ntiles;
         p.n_full = n_super * c.L.ntiles;
         p.n_units = p.n_full;
+        p.resident = 0;
         p.pitch = e->geom.P;
         p.ntaps = c.L.taps;
         p.dbg = e->conv_dbg;
@@ -645,13 +647,16 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
             p.bn = c.L.bn >> level;
             p.n_ntiles = c.L.cout / p.bn;
             const int items2 = n_super * p.n_ntiles;
+            // fp16 rung, one N tile, <= 18 weight stages per item: weights stay resident in shared memory
+            p.resident = (e->resident_weights && !Split(e) && p.n_ntiles == 1 && c.L.kh * c.L.taps <= Conv2Cfg<false>::kNumBStages &&
+                          items2 > max_pairs) ? 1 : 0;
             // persistent CTA pairs; the items of a partial last wave are split into N-halves when that makes the
             // wave half as long (conv_unit in conv3x3_tc2.cuh)
             const int pairs = std::min(items2, max_pairs);
             const int grid2 = 2 * pairs;
             const int rem = items2 % pairs;
             int n_tail = 0;
-            if (e->tail_split && items2 > pairs && rem > 0 && 2 * rem <= pairs && level + 1 < c.levels) n_tail = rem;
+            if (e->tail_split && !p.resident && items2 > pairs && rem > 0 && 2 * rem <= pairs && level + 1 < c.levels) n_tail = rem;
             p.n_full = items2 - n_tail;
             p.n_units = items2 + n_tail;
             const CUtensorMap& w_hi = c.tm2_hi[level];
@@ -1617,6 +1622,10 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     }
     if (!std::strcmp(key, "pack_threads")) {
         e->pack_threads = std::max(1, value);
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "resident_weights")) {
+        e->resident_weights = value ? 1 : 0;
         return SB_OK;
     }
     if (!std::strcmp(key, "chain_forwards")) {

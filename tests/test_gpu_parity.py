@@ -383,3 +383,26 @@ def test_tail_wave_split_is_bit_exact(eng):
             assert np.isfinite(a["probabilities"]).all()
         finally:
             pipe.destroy()
+
+
+def test_scheduling_knobs_do_not_change_a_single_bit(eng):
+    """Resident weights (fp16 rung), programmatic dependent launch, the small-batch N-tile split and chained forwards
+    only change WHEN and WHERE the same MMAs run: outputs are bit-identical with every knob on and off."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_4bx128.bin")
+    synth.write_synth_net(path, (4, 128, 16, 16), seed=77)
+    for prec in (eng.PRECISION_FP32_SPLIT, eng.PRECISION_FP16):
+        for n in (3, 160):
+            x = synth.synth_positions(n, 19, seed=32).reshape(n, -1)
+            pipe = eng.B200ForwardPipe().initialize(path, 19, n, gpus=[0], precision=prec)
+            try:
+                base = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
+                assert np.isfinite(base["probabilities"]).all()
+                for knob in ("resident_weights", "pdl", "small_batch_split", "chain_forwards"):
+                    pipe.set_option(knob, 0)
+                    other = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
+                    pipe.set_option(knob, 1)
+                    for f in FIELDS:
+                        assert np.array_equal(base[f], other[f]), (prec, n, knob, f)
+            finally:
+                pipe.destroy()
