@@ -111,84 +111,119 @@ __global__ void unpack_packed_kernel(const sb_packed_position* __restrict__ rec,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-sample pooling over a C8 tensor: sum and max of every channel over the sample's board cells.
-// One CTA of 256 threads.  L = 256 / chunks (rounded down to a power of two, <= 32) adjacent lanes share one
-// 8-channel chunk and stride the sample's rows, so a warp reads L consecutive 16-byte pieces of 32/L chunks per
-// step; the row loop is branch-free (select on the mask byte) and unrolled so that several independent 16-byte
-// loads are in flight per thread; a fixed shuffle tree over the L lanes finishes the reduction (the order never
-// depends on the batch: batch-invariant results).
-__device__ __forceinline__ void pool_sample_c8(const __half* __restrict__ hi, const __half* __restrict__ lo, bool split,
-                                               const uint8_t* __restrict__ mask, int row0, int SS, int C, int R,
-                                               float* s_sum, float* s_max) {
-    const int chunks = C >> 3;
-    int L = 32;
-    while (L > 1 && L * chunks > 256) L >>= 1;
-    const int sub = threadIdx.x & (L - 1);
-    const int per_pass = 256 / L;
-    for (int chunk = threadIdx.x / L; chunk < ((chunks + per_pass - 1) / per_pass) * per_pass; chunk += per_pass) {
-        const bool on = chunk < chunks;      // idle lanes still join the shuffles of their warp
-        float s[8], m[8];
+// Pooling of a SLICE of the channels of one sample by one CTA (256 threads = 8 warps), for the multi-CTA-per-sample
+// kernels below.  The CTA owns chunks [chunk0, chunk0 + ncl) (ncl <= 8); warp w takes chunk chunk0 + w % ncl and row
+// part w / ncl of 8 / ncl equal row ranges; lanes stride the rows with every load of the thread in flight at once; a
+// fixed shuffle tree and a fixed-order sum over the row parts finish the reduction.  Which CTA pools which channel
+// and in which order depends only on (C, board geometry): results are batch-invariant.
+// Writes s_sum / s_max [ncl * 8] (shared).  Needs s_part [2][8 warps][8] floats of scratch.
+__device__ __forceinline__ void pool_slice_c8(const __half* __restrict__ hi, const __half* __restrict__ lo, bool split,
+                                              const uint8_t* __restrict__ mask, int row0, int SS, int R, int chunk0, int ncl,
+                                              float* s_part, float* s_sum, float* s_max) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int parts = 8 / ncl;
+    const int cl = warp % ncl, part = warp / ncl;
+    float s[8], m[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            s[i] = 0.f;
-            m[i] = -5000.f;   // "crazy negative value", se_unit.cc:22
-        }
-        if (on) {
+    for (int i = 0; i < 8; ++i) {
+        s[i] = 0.f;
+        m[i] = -5000.f;   // "crazy negative value", se_unit.cc:22
+    }
+    if (part < parts) {
+        const int per = (SS + parts - 1) / parts;
+        const int r_end = min(SS, (part + 1) * per);
 #pragma unroll 4
-            for (int r = sub; r < SS; r += L) {
-                const bool live = mask[row0 + r] != 0;
-                float v[8];
-                const size_t off = act_index(row0 + r, chunk * 8, R);
-                load8(hi + off, lo + off, split, v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    s[i] += live ? v[i] : 0.f;
-                    m[i] = live ? fmaxf(m[i], v[i]) : m[i];
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            for (int o = L >> 1; o > 0; o >>= 1) {
-                s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-                m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], o));
-            }
-        }
-        if (on && sub == 0) {
+        for (int r = part * per + lane; r < r_end; r += 32) {
+            const bool live = mask[row0 + r] != 0;
+            float v[8];
+            const size_t off = act_index(row0 + r, (chunk0 + cl) * 8, R);
+            load8(hi + off, lo + off, split, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                s_sum[chunk * 8 + i] = s[i];
-                s_max[chunk * 8 + i] = m[i];
+                s[i] += live ? v[i] : 0.f;
+                m[i] = live ? fmaxf(m[i], v[i]) : m[i];
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+            m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], o));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s_part[warp * 8 + i] = s[i];
+            s_part[64 + warp * 8 + i] = m[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ncl * 8) {
+        const int c = threadIdx.x >> 3, i = threadIdx.x & 7;
+        float ss = 0.f, mm = -5000.f;
+        for (int pt = 0; pt < parts; ++pt) {      // fixed order over the row parts
+            ss += s_part[(pt * ncl + c) * 8 + i];
+            mm = fmaxf(mm, s_part[64 + (pt * ncl + c) * 8 + i]);
+        }
+        s_sum[threadIdx.x] = ss;
+        s_max[threadIdx.x] = mm;
+    }
+    __syncthreads();
+}
+
+// The last CTA of a sample to publish its slice runs the sample's fully-connected tail (threadfence + counter).
+__device__ __forceinline__ bool last_cta_of_sample(int* counter, int n_ctas, int* s_flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(counter, 1);
+        *s_flag = (prev == n_ctas - 1) ? 1 : 0;
+        if (prev == n_ctas - 1) *counter = 0;      // ready for the next launch
+    }
+    __syncthreads();
+    const bool last = *s_flag != 0;
+    if (last) __threadfence();
+    return last;
 }
 
 // se_pool_fc: GlobalPooling<false> + squeeze FC + excite FC of SEUnit::Forward
 // (/root/reference/src/neural/blas/se_unit.cc:9-37,70-90; GPU twins cuda_kernels.cu:241-321 and the
-// cuBLAS FCs cuda_layers.cc:975-1017).  One CTA (256 threads) per sample; writes sigmoid(gamma) and
-// beta, [n][2C].  Mean divides by the sample's own n^2, (n-14)/10 uses the sample's own n.
+// cuBLAS FCs cuda_layers.cc:975-1017).  grid (C/32, n): every CTA pools 32 channels of one sample into
+// pooled[n][2C] (sums, maxima); the sample's last CTA then runs the two FCs and writes sigmoid(gamma) and
+// beta, gb[n][2C].  Mean divides by the sample's own n^2, (n-14)/10 uses the sample's own n.
 __global__ void __launch_bounds__(256)
 se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_lo, bool split,
                   const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int C, int R,
                   int se, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                  const float* __restrict__ b2, int act, float* __restrict__ gb) {
+                  const float* __restrict__ b2, int act, float* pooled, int* counters, float* __restrict__ gb) {
     extern __shared__ float sm[];
-    const int b = blockIdx.x;
-    const int bs = board_sizes[b];
-    float* s_sum = sm;              // [C]
-    float* s_max = sm + C;          // [C]
-    float* pool = s_max + C;        // [3C]
-    float* hid = pool + 3 * C;      // [se]
+    __shared__ float s_part[128];
+    __shared__ float s_sum[64], s_max[64];
+    __shared__ int s_flag;
+    const int b = blockIdx.y;
+    const int chunk0 = blockIdx.x * 4;
+    const int ncl = min(4, (C >> 3) - chunk0);
+    pool_slice_c8(u_hi, u_lo, split, mask, kGuardRows + b * g.SS, g.SS, R, chunk0, ncl, s_part, s_sum, s_max);
     const int tid = threadIdx.x;
-    pool_sample_c8(u_hi, u_lo, split, mask, kGuardRows + b * g.SS, g.SS, C, R, s_sum, s_max);
-    __syncthreads();
+    if (tid < ncl * 8) {
+        pooled[(size_t)b * 2 * C + chunk0 * 8 + tid] = s_sum[tid];
+        pooled[(size_t)b * 2 * C + C + chunk0 * 8 + tid] = s_max[tid];
+    }
+    if (!last_cta_of_sample(counters + b, gridDim.x, &s_flag)) return;
+
+    const int bs = board_sizes[b];
+    float* pool = sm;               // [3C]
+    float* hid = pool + 3 * C;      // [se]
     const float b_coeff = ((float)bs - 14.0f) / 10.f;   // se_unit.h:17-20
+    const volatile float* pv = pooled + (size_t)b * 2 * C;   // written by other CTAs: bypass L1
     for (int c = tid; c < C; c += 256) {
-        const float mean = s_sum[c] / (float)(bs * bs);
+        const float mean = pv[c] / (float)(bs * bs);
         pool[c] = mean;
         pool[C + c] = mean * b_coeff;
-        pool[2 * C + c] = s_max[c];
+        pool[2 * C + c] = pv[C + c];
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -270,32 +305,41 @@ struct HeadWeights {
 
 // head_pool_fc: GlobalPooling<false> of the policy planes, GlobalPooling<true> of the value planes
 // (se_unit.cc:9-68) and the four small FCs (blas_forward_pipe.cc:473-481,501-507,524-532,549-555).
-// One CTA (256 threads) per sample.  pv is the C8 tensor written by the head 1x1 conv (P policy + V value
-// channels).  Writes pint[n][P], pass5[n][5], misc15[n][15].
+// grid (ceil((P+V)/32), n): every CTA pools up to 32 channels of the head-entry conv output pv (C8: P policy + V value
+// channels) of one sample; the sample's last CTA runs the FCs.  Writes pint[n][P], pass5[n][5], misc15[n][15].
 __global__ void __launch_bounds__(256)
 head_pool_fc_kernel(const __half* __restrict__ pv_hi, const __half* __restrict__ pv_lo, bool split, int R,
                     const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int P, int V,
-                    HeadWeights hw, int act, float* __restrict__ pint, float* __restrict__ pass5,
-                    float* __restrict__ misc15) {
+                    HeadWeights hw, int act, float* pooled, int* counters, float* __restrict__ pint,
+                    float* __restrict__ pass5, float* __restrict__ misc15) {
     extern __shared__ float sm[];
+    __shared__ float s_part[128];
+    __shared__ float s_sum[64], s_max[64];
+    __shared__ int s_flag;
     const int PV = P + V;
-    const int b = blockIdx.x, bs = board_sizes[b];
-    float* s_sum = sm;                       // [PV]
-    float* s_max = sm + PV;                  // [PV]
-    float* ppool = s_max + PV;               // [3P]
+    const int b = blockIdx.y, bs = board_sizes[b];
+    const int chunk0 = blockIdx.x * 4;
+    const int ncl = min(4, (PV >> 3) - chunk0);
+    pool_slice_c8(pv_hi, pv_lo, split, mask, kGuardRows + b * g.SS, g.SS, R, chunk0, ncl, s_part, s_sum, s_max);
+    const int tid = threadIdx.x;
+    if (tid < ncl * 8) {
+        pooled[(size_t)b * 2 * PV + chunk0 * 8 + tid] = s_sum[tid];
+        pooled[(size_t)b * 2 * PV + PV + chunk0 * 8 + tid] = s_max[tid];
+    }
+    if (!last_cta_of_sample(counters + b, gridDim.x, &s_flag)) return;
+
+    float* ppool = sm;                       // [3P]
     float* vpool = ppool + 3 * P;            // [3V]
     float* spint = vpool + 3 * V;            // [P]
     float* svint = spint + P;                // [3V]
-    const int tid = threadIdx.x;
-    pool_sample_c8(pv_hi, pv_lo, split, mask, kGuardRows + b * g.SS, g.SS, PV, R, s_sum, s_max);
-    __syncthreads();
+    const volatile float* pl = pooled + (size_t)b * 2 * PV;   // written by other CTAs: bypass L1
     const float b_diff = (float)bs - 14.0f;
     if (tid < PV) {
-        const float mean = s_sum[tid] / (float)(bs * bs);
+        const float mean = pl[tid] / (float)(bs * bs);
         if (tid < P) {
             ppool[tid] = mean;
             ppool[P + tid] = mean * (b_diff / 10.f);
-            ppool[2 * P + tid] = s_max[tid];
+            ppool[2 * P + tid] = pl[PV + tid];
         } else {
             const int v = tid - P;
             vpool[v] = mean;

@@ -73,7 +73,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // Default (.release.cta) semantics, as CUTLASS' ClusterBarrier::arrive(cta_id): the explicit .release.cluster form
+    // compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. every epilogue warp waited once per work item for ALL its outstanding
+    // global loads / stores (8.7 % of the kernel's stall samples, profiles/r01s2_ncu_source_*.txt).  The only data
+    // the MMA issuer must see ordered before this arrive are our tcgen05.ld reads of the accumulator, which
+    // tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion bytes are credited to a barrier given by its shared::cluster address
 __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster) {
@@ -236,7 +241,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         }
     } else if (warp == 0) {
         // ===================== weight-stage producer (own N-half of every block) =====================
-        uint32_t it = 0;
+        uint32_t s = 0, ph = 0;   // ring position and phase, advanced incrementally (kNB is a run-time value)
         for (int item = cluster_id; item < n_items && !(p.dbg & 16); item += n_clusters) {
             if (resident && item != cluster_id) break;     // everything is already in shared memory
             const ConvUnit w = conv_unit(item, p);
@@ -245,8 +250,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             for (int h = 0; h < KH; ++h) {
                 for (int tap = 0; tap < p.ntaps; ++tap) {
 #pragma unroll
-                    for (int part = 0; part < Cfg::kParts; ++part, ++it) {
-                        const uint32_t s = it % kNB, ph = (it / kNB) & 1u;
+                    for (int part = 0; part < Cfg::kParts; ++part) {
                         mbar_wait(b_empty + 8 * s, ph ^ 1u, p.err, 2);
                         if (elect_one()) {
                             const uint32_t full0 = mapa_u32(b_full + 8 * s, 0);
@@ -256,6 +260,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                          tap * (KH * 64) + h * 64, w.n0 + (int)rank * HB, full0);
                         }
                         __syncwarp();
+                        if (++s == kNB) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
             }
@@ -267,7 +275,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);
             constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
             const bool stats = p.stats != nullptr;
-            uint32_t a_it = 0, b_it = 0, j = 0;
+            uint32_t a_it = 0, j = 0;
+            uint32_t bs = 0, bph = 0;   // weight ring position and phase (incremental: kNB is a run-time value)
             long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0, t0 = 0;
             const long long t_begin = stats ? clock64() : 0;
             for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
@@ -291,9 +300,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         const uint32_t first = (h | tap) == 0 ? 0u : 1u;
                         const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
                         {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
-                            const uint32_t bs = b_it % kNB, bph = resident ? 0u : (b_it / kNB) & 1u;
                             if (stats) t0 = clock64();
-                            if (!(p.dbg & 16)) mbar_wait(b_full + 8 * bs, bph, p.err, 5);
+                            if (!(p.dbg & 16) && !(resident && j > 0)) mbar_wait(b_full + 8 * bs, bph, p.err, 5);
                             if (stats) t_wait_b += clock64() - t0;
                             tc_fence_after();
                             const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
@@ -305,25 +313,30 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                         umma2_f16(d_lo, ad0 + (Cfg::kSlabPartBytes >> 4) + kAStep * k, bd0 + 2 * k, idesc,
                                                   (k == 0) ? first : 1u);
                                 }
-                                umma2_commit_mc(b_empty + 8 * bs, 3);
+                                if (!resident) umma2_commit_mc(b_empty + 8 * bs, 3);   // resident stages are never recycled
                             }
                             __syncwarp();
-                            ++b_it;
+                            if (++bs == kNB) {
+                                bs = 0;
+                                if (!resident) bph ^= 1u;
+                            }
                         }
                         if (SPLIT) {   // weights lo x activations hi -> lo accumulator
-                            const uint32_t bs = b_it % kNB, bph = resident ? 0u : (b_it / kNB) & 1u;
                             if (stats) t0 = clock64();
-                            if (!(p.dbg & 16)) mbar_wait(b_full + 8 * bs, bph, p.err, 6);
+                            if (!(p.dbg & 16) && !(resident && j > 0)) mbar_wait(b_full + 8 * bs, bph, p.err, 6);
                             if (stats) t_wait_b += clock64() - t0;
                             tc_fence_after();
                             const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) umma2_f16(d_lo, ad0 + kAStep * k, bd0 + 2 * k, idesc, 1u);
-                                umma2_commit_mc(b_empty + 8 * bs, 3);
+                                if (!resident) umma2_commit_mc(b_empty + 8 * bs, 3);   // resident stages are never recycled
                             }
                             __syncwarp();
-                            ++b_it;
+                            if (++bs == kNB) {
+                                bs = 0;
+                                if (!resident) bph ^= 1u;
+                            }
                         }
                     }
                     if (elect_one()) umma2_commit_mc(a_empty + 8 * s, 3);

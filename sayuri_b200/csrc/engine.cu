@@ -280,6 +280,8 @@ struct Slot {
     ActBuf* trunk = nullptr;   // which buffer holds the tower output after the last forward
     uint8_t* mask = nullptr;
     float* gb = nullptr;       // [max_batch][2C]
+    float* pooled = nullptr;   // [max_batch][2 * max(C, 64)]: per-channel sums and maxima between the pooling CTAs and the FC tail
+    int* counters = nullptr;   // [max_batch]: pooling CTAs of a sample that have published (self-resetting)
     ActBuf pv;                 // head-entry conv output: P policy + V value channels (padded to 64)
     float* pint = nullptr;
     float* pass5 = nullptr;
@@ -418,6 +420,8 @@ static void FreeSlot(Slot& s) {
     }
     cudaFree(s.mask);
     cudaFree(s.gb);
+    cudaFree(s.pooled);
+    cudaFree(s.counters);
     cudaFree(s.pint);
     cudaFree(s.pass5);
     cudaFree(s.misc15);
@@ -475,6 +479,9 @@ static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int
         SB_CUDA(cudaMalloc(&s.mask, (size_t)rows));
         SB_CUDA(cudaMemset(s.mask, 0, (size_t)rows));
         SB_CUDA(cudaMalloc(&s.gb, (size_t)e->max_batch * 2 * C * sizeof(float)));
+        SB_CUDA(cudaMalloc(&s.pooled, (size_t)e->max_batch * 2 * std::max(C, 64) * sizeof(float)));
+        SB_CUDA(cudaMalloc(&s.counters, (size_t)e->max_batch * sizeof(int)));
+        SB_CUDA(cudaMemset(s.counters, 0, (size_t)e->max_batch * sizeof(int)));
         AllocAct(s.pv, rows, 64, split);
         SB_CUDA(cudaMalloc(&s.pint, (size_t)e->max_batch * P * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.pass5, (size_t)e->max_batch * 5 * sizeof(float)));
@@ -735,10 +742,10 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         const int se = e->se_sizes[b];
         if (se > 0) {
             LaunchConv(e, r, s, r.conv2[b], *t, *u, nullptr, kIdentity, n, tm);
-            const size_t smem = ((size_t)5 * C + se) * sizeof(float);
-            se_pool_fc_kernel<<<n, 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se,
-                                                          F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
-                                                          F(L.excite[b].b), act, s.gb);
+            const size_t smem = ((size_t)3 * C + se) * sizeof(float);
+            se_pool_fc_kernel<<<dim3((C + 31) / 32, n), 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se,
+                                                                                F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
+                                                                                F(L.excite[b].b), act, s.pooled, s.counters, s.gb);
             SB_CUDA(cudaGetLastError());
             const size_t total = (size_t)n_rows * (C / 8);
             SB_DISPATCH_ACT(act, ACT, (se_apply_kernel<ACT><<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(
@@ -768,9 +775,9 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     hw.own_b = F(L.own_b);
     {
         const int PV = P + V;
-        const size_t smem = ((size_t)2 * PV + 3 * P + 3 * V + P + 3 * V) * sizeof(float);
-        head_pool_fc_kernel<<<n, 256, smem, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, s.mask, d_sizes, g, P, V, hw, act,
-                                                        s.pint, s.pass5, s.misc15);
+        const size_t smem = ((size_t)3 * P + 3 * V + P + 3 * V) * sizeof(float);
+        head_pool_fc_kernel<<<dim3((PV + 31) / 32, n), 256, smem, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, s.mask, d_sizes, g, P, V,
+                                                                              hw, act, s.pooled, s.counters, s.pint, s.pass5, s.misc15);
         SB_CUDA(cudaGetLastError());
         head_out_kernel<<<n, 384, 0, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, d_sizes, d_offsets, g, P, V, hw, s.pint,
                                                  s.pass5, s.misc15, s.d_out);
