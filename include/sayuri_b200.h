@@ -43,6 +43,14 @@ typedef enum sb_precision {
                                     of the tensor-core kernel, test use only                               */
 } sb_precision;
 
+/* Tower block families (BlockBasic::Type, src/neural/description.h:88-132).  The Mixer block (depthwise conv + FFN)
+ * and the RepLK policy head are not implemented and are rejected at load. */
+typedef enum sb_block_type {
+    SB_BLOCK_RESIDUAL = 0,           /* conv3x3, conv3x3 (+skip)                    blas_forward_pipe.cc:46-88    */
+    SB_BLOCK_BOTTLENECK = 1,         /* 1x1 down, 2 x conv3x3, 1x1 up (+skip)       blas_forward_pipe.cc:90-162   */
+    SB_BLOCK_NESTED_BOTTLENECK = 2   /* 1x1 down, 2 inner residual blocks, 1x1 up   blas_forward_pipe.cc:164-263  */
+} sb_block_type;
+
 /* Network description == the scalar fields of DNNWeights (src/neural/description.h:164-215). */
 typedef struct sb_net_desc {
     int version;            /* 3..5 (43-plane encoder, 5 policy planes, 15 misc outputs)           */
@@ -52,7 +60,9 @@ typedef struct sb_net_desc {
     int policy_channels;    /* policy_head_channels                                                */
     int value_channels;     /* value_head_channels                                                 */
     int activation;         /* same ints as enum Activation, src/neural/activation.h:8-17          */
-    const int* se_sizes;    /* [blocks]: 0 = plain ResidualBlock, >0 = squeeze width of ...-SE     */
+    const int* se_sizes;    /* [blocks]: 0 = no SE unit, >0 = squeeze width of ...-SE               */
+    const int* block_types; /* [blocks] sb_block_type, or NULL = all SB_BLOCK_RESIDUAL             */
+    const int* inner_channels; /* [blocks] bottleneck_channels of (Nested)Bottleneck blocks, or NULL */
 } sb_net_desc;
 
 /* One tensor, fp32, caller-owned for the duration of the call only. */
@@ -64,7 +74,8 @@ typedef struct sb_tensor {
 /*
  * Weights in the loader's tensor order (src/neural/loader.cc:658-747) AFTER ProcessWeights
  * (loader.cc:775-831): batch-norm already folded, so every layer contributes exactly two tensors
- * {weights, biases}: input conv; per block conv1, conv2 [, squeeze FC, excite FC]; policy head conv,
+ * {weights, biases}: input conv; per block conv1, conv2 (Bottleneck: pre_btl_conv, conv1, conv2, post_btl_conv;
+ * NestedBottleneck: pre_btl_conv, conv1..conv4, post_btl_conv) [, squeeze FC, excite FC]; policy head conv,
  * policy intermediate FC, prob conv, pass FC; value head conv, value intermediate FC, ownership conv,
  * misc FC.  Conv weights are UNTRANSFORMED OIHW (ConvLayer::GetWeights, never GetTransformF);
  * FC weights [out][in].
@@ -136,6 +147,7 @@ int sb_num_slots(const sb_engine* e);          /* pipeline depth per GPU (indepe
 int sb_max_batch(const sb_engine* e);
 int sb_board_size(const sb_engine* e);
 int sb_get_net_desc(const sb_engine* e, sb_net_desc* desc, int* se_sizes, int se_capacity);
+int sb_get_block_desc(const sb_engine* e, int* block_types, int* inner_channels, int capacity);
 
 /* ---- the hot path: CudaForwardPipe::BatchForward -> NNGraph::BatchForward, --------------------------
  *      src/neural/cuda/cuda_forward_pipe.cc:32-34,684-1018 (+ FillOutputs :1020-1090);

@@ -39,8 +39,12 @@ typedef struct {
     float* b;
 } fc_t;
 
+/* description.h:88-132 (BlockBasic): the Mixer block (depthwise conv + FFN) is outside the oracle's scope */
+enum { BLK_RESIDUAL = 0, BLK_BOTTLENECK = 1, BLK_NESTED = 2 };
+
 typedef struct {
-    conv_t conv1, conv2;
+    int type, inner; /* inner = bottleneck_channels (0 for a plain residual block) */
+    conv_t conv1, conv2, conv3, conv4, pre, post;
     int apply_se, se_size;
     fc_t squeeze, excite;
 } block_t;
@@ -286,13 +290,32 @@ oracle_net* oracle_load(const char* path, char* err, int errlen) {
             char* dash = strchr(stack[b], '-');
             int se = 0;
             if (dash) { if (strcmp(dash + 1, "SE")) { snprintf(err, errlen, "block component %s outside the oracle's scope", dash + 1); goto fail; } *dash = 0; se = 1; }
-            if (strcmp(stack[b], "ResidualBlock")) { snprintf(err, errlen, "block type %s is outside the oracle's scope (plain ResidualBlock[-SE] only)", stack[b]); goto fail; }
-            /* loader.cc:385-415: conv1,bn1,conv2,bn2 [, squeeze fc, excite fc] */
-            if (rd_conv_bn(&r, &shapes[off], &blk->conv1, v1, err, errlen)) goto fail;
-            off += 2;
-            if (rd_conv_bn(&r, &shapes[off], &blk->conv2, v1, err, errlen)) goto fail;
-            off += 2;
-            if (blk->conv1.k != 3 || blk->conv2.k != 3 || blk->conv1.in != channels || blk->conv1.out != channels || blk->conv2.in != channels || blk->conv2.out != channels) { snprintf(err, errlen, "the Nth residual block is wrong"); goto fail; }
+            if (!strcmp(stack[b], "ResidualBlock")) {
+                /* loader.cc:385-415: conv1,bn1,conv2,bn2 [, squeeze fc, excite fc] */
+                blk->type = BLK_RESIDUAL;
+                if (rd_conv_bn(&r, &shapes[off], &blk->conv1, v1, err, errlen)) goto fail;
+                off += 2;
+                if (rd_conv_bn(&r, &shapes[off], &blk->conv2, v1, err, errlen)) goto fail;
+                off += 2;
+                if (blk->conv1.k != 3 || blk->conv2.k != 3 || blk->conv1.in != channels || blk->conv1.out != channels || blk->conv2.in != channels || blk->conv2.out != channels) { snprintf(err, errlen, "the Nth residual block is wrong"); goto fail; }
+            } else if (!strcmp(stack[b], "BottleneckBlock") || !strcmp(stack[b], "NestedBottleneckBlock")) {
+                /* loader.cc:416-465 (pre 1x1, conv1, conv2, post 1x1) and :466-555 (pre, conv1..conv4, post) */
+                const int nested = stack[b][0] == 'N';
+                blk->type = nested ? BLK_NESTED : BLK_BOTTLENECK;
+                conv_t* seq[6];
+                int ns = 0;
+                seq[ns++] = &blk->pre; seq[ns++] = &blk->conv1; seq[ns++] = &blk->conv2;
+                if (nested) { seq[ns++] = &blk->conv3; seq[ns++] = &blk->conv4; }
+                seq[ns++] = &blk->post;
+                for (int q = 0; q < ns; ++q) {
+                    if (rd_conv_bn(&r, &shapes[off], seq[q], v1, err, errlen)) goto fail;
+                    off += 2;
+                }
+                blk->inner = blk->pre.out;
+                if (blk->pre.k != 1 || blk->post.k != 1 || blk->pre.in != channels || blk->post.out != channels || blk->post.in != blk->inner) { snprintf(err, errlen, "the outer channels of bottleneck block is wrong"); goto fail; }
+                for (int q = 1; q < ns - 1; ++q)
+                    if (seq[q]->k != 3 || seq[q]->in != blk->inner || seq[q]->out != blk->inner) { snprintf(err, errlen, "the inner channels of bottleneck block is wrong"); goto fail; }
+            } else { snprintf(err, errlen, "block type %s is outside the oracle's scope (ResidualBlock, BottleneckBlock, NestedBottleneckBlock [-SE])", stack[b]); goto fail; }
             if (se) {
                 if (rd_fc(&r, &shapes[off], &blk->squeeze, err, errlen)) goto fail;
                 off += 1;
@@ -337,7 +360,8 @@ void oracle_free(oracle_net* n) {
     free_conv(&n->input_conv);
     if (n->tower) {
         for (int b = 0; b < n->blocks; ++b) {
-            free_conv(&n->tower[b].conv1); free_conv(&n->tower[b].conv2);
+            free_conv(&n->tower[b].conv1); free_conv(&n->tower[b].conv2); free_conv(&n->tower[b].conv3);
+            free_conv(&n->tower[b].conv4); free_conv(&n->tower[b].pre); free_conv(&n->tower[b].post);
             free_fc(&n->tower[b].squeeze); free_fc(&n->tower[b].excite);
         }
         free(n->tower);
@@ -358,7 +382,7 @@ int oracle_info(const oracle_net* n, int* out8) {
 }
 
 /* Folded tensors in loader order (for comparing the product's own loader with this one, bit-exact).
- * idx enumerates: input_conv, [conv1, conv2, (squeeze, excite)] per block, p_hd, p_inter, prob, pass,
+ * idx enumerates: input_conv, [(pre,) conv1, conv2, (conv3, conv4,) (post,) (squeeze, excite)] per block, p_hd, p_inter, prob, pass,
  * v_hd, v_inter, own, misc; which = 0 weights, 1 biases.  Returns element count, or -1 past the end. */
 int oracle_get_tensor(const oracle_net* n, int idx, int which, const float** out) {
     int i = 0;
@@ -366,8 +390,11 @@ int oracle_get_tensor(const oracle_net* n, int idx, int which, const float** out
 #define EMIT_FC(f) do { if (i++ == idx) { *out = which ? (f).b : (f).w; return which ? (f).out : (f).out * (f).in; } } while (0)
     EMIT_CONV(n->input_conv);
     for (int b = 0; b < n->blocks; ++b) {
+        if (n->tower[b].type != BLK_RESIDUAL) EMIT_CONV(n->tower[b].pre);
         EMIT_CONV(n->tower[b].conv1);
         EMIT_CONV(n->tower[b].conv2);
+        if (n->tower[b].type == BLK_NESTED) { EMIT_CONV(n->tower[b].conv3); EMIT_CONV(n->tower[b].conv4); }
+        if (n->tower[b].type != BLK_RESIDUAL) EMIT_CONV(n->tower[b].post);
         if (n->tower[b].apply_se) { EMIT_FC(n->tower[b].squeeze); EMIT_FC(n->tower[b].excite); }
     }
     EMIT_CONV(n->p_hd_conv); EMIT_FC(n->p_inter_fc); EMIT_CONV(n->prob_conv); EMIT_FC(n->pass_fc);
@@ -520,17 +547,46 @@ int oracle_forward_trace(const oracle_net* n, const float* planes, int bs, int o
     /* input layers :373-383 */
     conv_forward(&n->input_conv, bs, planes, x);
     add_spatial_biases(bs, C, x, n->input_conv.b, NULL, act);
-    /* tower :386-424, ResidualBlockForward :46-88 */
+    /* tower :386-424 */
     for (int b = 0; b < n->blocks; ++b) {
         const block_t* blk = &n->tower[b];
-        conv_forward(&blk->conv1, bs, x, t);
-        add_spatial_biases(bs, C, t, blk->conv1.b, NULL, act);
-        conv_forward(&blk->conv2, bs, t, u);
+        const conv_t* last;     /* the conv whose output joins the skip connection (or feeds the SE unit) */
+        if (blk->type == BLK_RESIDUAL) {
+            /* ResidualBlockForward :46-88 */
+            conv_forward(&blk->conv1, bs, x, t);
+            add_spatial_biases(bs, C, t, blk->conv1.b, NULL, act);
+            conv_forward(&blk->conv2, bs, t, u);
+            last = &blk->conv2;
+        } else {
+            /* BottleneckBlockForward :90-162 / NestedBottleneckBlockForward :164-263 */
+            const int I = blk->inner;
+            float* a = (float*)malloc(sizeof(float) * (size_t)I * s);
+            float* c1 = (float*)malloc(sizeof(float) * (size_t)I * s);
+            float* c2 = (float*)malloc(sizeof(float) * (size_t)I * s);
+            conv_forward(&blk->pre, bs, x, a);                          /* pre-bottleneck 1x1 */
+            add_spatial_biases(bs, I, a, blk->pre.b, NULL, act);
+            conv_forward(&blk->conv1, bs, a, c1);
+            add_spatial_biases(bs, I, c1, blk->conv1.b, NULL, act);
+            conv_forward(&blk->conv2, bs, c1, c2);
+            if (blk->type == BLK_BOTTLENECK) {
+                add_spatial_biases(bs, I, c2, blk->conv2.b, NULL, act);                 /* :128-129 no skip */
+            } else {
+                add_spatial_biases(bs, I, c2, blk->conv2.b, a, act);                    /* :218-219 + residual1 */
+                conv_forward(&blk->conv3, bs, c2, c1);
+                add_spatial_biases(bs, I, c1, blk->conv3.b, NULL, act);
+                conv_forward(&blk->conv4, bs, c1, a);
+                add_spatial_biases(bs, I, a, blk->conv4.b, c2, act);                    /* :246-247 + residual1 */
+                float* sw = a; a = c2; c2 = sw;
+            }
+            conv_forward(&blk->post, bs, c2, u);                        /* post-bottleneck 1x1 */
+            last = &blk->post;
+            free(a); free(c1); free(c2);
+        }
         if (blk->apply_se) {
-            add_spatial_biases(bs, C, u, blk->conv2.b, NULL, ACT_IDENTITY);
+            add_spatial_biases(bs, C, u, last->b, NULL, ACT_IDENTITY);
             se_unit(bs, C, blk, u, x, act);
         } else {
-            add_spatial_biases(bs, C, u, blk->conv2.b, x, act);
+            add_spatial_biases(bs, C, u, last->b, x, act);
         }
         float* tmp = x; x = u; u = tmp;
     }

@@ -127,7 +127,7 @@ struct FcLayout {
 };
 struct BlobLayout {
     ConvLayout input;
-    std::vector<ConvLayout> conv1, conv2;
+    std::vector<std::vector<ConvLayout>> bconv;   // per block, loader order (HostBlock::convs)
     std::vector<FcLayout> squeeze, excite;  // per block (unused entries when se_size == 0)
     ConvLayout head;                        // policy + value head-entry 1x1 convs as one single-tap conv, cout = P + V
     FcLayout p_inter, pass, v_inter, misc;
@@ -165,17 +165,23 @@ static FcLayout LayFc(size_t& cur, int in, int out) {
     return f;
 }
 
-static BlobLayout ComputeLayout(int blocks, int C, int P, int V, const std::vector<int>& se) {
+static BlobLayout ComputeLayout(int blocks, int C, int P, int V, const std::vector<int>& se, const std::vector<int>& types,
+                                const std::vector<int>& inner) {
     BlobLayout L;
     size_t cur = 0;
     L.input = LayConv(cur, SB_INPUT_CHANNELS, C);
-    L.conv1.resize(blocks);
-    L.conv2.resize(blocks);
+    L.bconv.resize(blocks);
     L.squeeze.resize(blocks);
     L.excite.resize(blocks);
     for (int b = 0; b < blocks; ++b) {
-        L.conv1[b] = LayConv(cur, C, C);
-        L.conv2[b] = LayConv(cur, C, C);
+        if (types[b] == SB_BLOCK_RESIDUAL) {
+            L.bconv[b] = {LayConv(cur, C, C), LayConv(cur, C, C)};
+        } else {   // pre 1x1, 2 or 4 inner 3x3, post 1x1
+            const int I = inner[b], n3 = types[b] == SB_BLOCK_BOTTLENECK ? 2 : 4;
+            L.bconv[b].push_back(LayConv(cur, C, I, 1));
+            for (int q = 0; q < n3; ++q) L.bconv[b].push_back(LayConv(cur, I, I));
+            L.bconv[b].push_back(LayConv(cur, I, C, 1));
+        }
         if (se[b] > 0) {
             L.squeeze[b] = LayFc(cur, 3 * C, se[b]);
             L.excite[b] = LayFc(cur, se[b], 2 * C);
@@ -223,8 +229,7 @@ static std::vector<uint8_t> PackBlob(const HostNet& n, const BlobLayout& L) {
     uint8_t* p = blob.data();
     PackConv(n.input_conv, L.input, p);
     for (int b = 0; b < n.blocks; ++b) {
-        PackConv(n.tower[b].conv1, L.conv1[b], p);
-        PackConv(n.tower[b].conv2, L.conv2[b], p);
+        for (size_t q = 0; q < n.tower[b].convs.size(); ++q) PackConv(n.tower[b].convs[q], L.bconv[b][q], p);
         if (n.tower[b].se_size > 0) {
             PackFc(n.tower[b].squeeze, L.squeeze[b], p);
             PackFc(n.tower[b].excite, L.excite[b], p);
@@ -277,6 +282,7 @@ struct Slot {
     float* d_out = nullptr;    // [max_batch][kOutFloats]
     float* h_out = nullptr;    // pinned
     ActBuf in, x, t, u;
+    ActBuf ia, ib, ic;         // bottleneck-width buffers (allocated only when the tower has bottleneck blocks)
     ActBuf* trunk = nullptr;   // which buffer holds the tower output after the last forward
     uint8_t* mask = nullptr;
     float* gb = nullptr;       // [max_batch][2C]
@@ -308,7 +314,7 @@ struct Replica {
     int device = -1;
     uint8_t* blob = nullptr;
     DevConv input, head;
-    std::vector<DevConv> conv1, conv2;
+    std::vector<std::vector<DevConv>> bconv;   // per block, loader order
     std::vector<Slot> slots;
     std::vector<Slot> bslots;     // the batcher's own slots (sb_eval), allocated when its workers start
     // Forwards of different slots are chained on the device: H2D / D2H copies of one slot overlap the other slot's
@@ -363,6 +369,8 @@ using namespace sb;
 struct sb_engine {
     HostNet net_shape;  // scalar fields + se sizes only (tensors dropped after packing)
     std::vector<int> se_sizes;
+    std::vector<int> block_types;      // SB_BLOCK_* per block
+    std::vector<int> inner_channels;   // bottleneck width per block (0 for plain residual blocks)
     BlobLayout layout;
     std::vector<Replica> replicas;
     Geom geom;
@@ -414,7 +422,8 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.d_packed);
     cudaFree(s.d_out);
     cudaFreeHost(s.h_out);
-    for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u, &s.pv}) {
+    for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u, &s.pv, &s.ia, &s.ib, &s.ic}) {
+        if (!a->hi) continue;
         if (a->lo != a->hi) cudaFree(a->lo);   // single-pass fp16 mode aliases lo to hi
         cudaFree(a->hi);
     }
@@ -476,6 +485,14 @@ static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int
         AllocAct(s.x, rows, Cp, split);
         AllocAct(s.t, rows, Cp, split);
         AllocAct(s.u, rows, Cp, split);
+        int inner_max = 0;
+        for (int v : e->inner_channels) inner_max = std::max(inner_max, v);
+        if (inner_max > 0) {
+            const int Ip = RoundUp(inner_max, 64);
+            AllocAct(s.ia, rows, Ip, split);
+            AllocAct(s.ib, rows, Ip, split);
+            AllocAct(s.ic, rows, Ip, split);
+        }
         SB_CUDA(cudaMalloc(&s.mask, (size_t)rows));
         SB_CUDA(cudaMemset(s.mask, 0, (size_t)rows));
         SB_CUDA(cudaMalloc(&s.gb, (size_t)e->max_batch * 2 * C * sizeof(float)));
@@ -546,20 +563,19 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     MakeConvMaps(r, r.input);
     r.head.L = e->layout.head;
     MakeConvMaps(r, r.head);
-    r.conv1.resize(blocks);
-    r.conv2.resize(blocks);
+    r.bconv.resize(blocks);
     for (int b = 0; b < blocks; ++b) {
-        r.conv1[b].L = e->layout.conv1[b];
-        r.conv2[b].L = e->layout.conv2[b];
-        MakeConvMaps(r, r.conv1[b]);
-        MakeConvMaps(r, r.conv2[b]);
+        r.bconv[b].resize(e->layout.bconv[b].size());
+        for (size_t q = 0; q < r.bconv[b].size(); ++q) {
+            r.bconv[b][q].L = e->layout.bconv[b][q];
+            MakeConvMaps(r, r.bconv[b][q]);
+        }
     }
     if (blob && e->precision == SB_PRECISION_SIMT_DEBUG) {
         MakeSimtWeights(e, r, r.input, *blob);
         MakeSimtWeights(e, r, r.head, *blob);
         for (int b = 0; b < blocks; ++b) {
-            MakeSimtWeights(e, r, r.conv1[b], *blob);
-            MakeSimtWeights(e, r, r.conv2[b], *blob);
+            for (auto& c : r.bconv[b]) MakeSimtWeights(e, r, c, *blob);
         }
     }
     // dynamic shared memory opt-in, sized for the widest supported net (C = 256) so that engines of different
@@ -585,8 +601,8 @@ static void DestroyReplica(Replica& r) {
     };
     free_conv(r.input);
     free_conv(r.head);
-    for (auto& c : r.conv1) free_conv(c);
-    for (auto& c : r.conv2) free_conv(c);
+    for (auto& blk : r.bconv)
+        for (auto& c : blk) free_conv(c);
     cudaFree(r.blob);
     r.blob = nullptr;
     cudaFree(r.flush_buf);
@@ -738,10 +754,32 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     ActBuf* u = &s.u;
     LaunchConv(e, r, s, r.input, s.in, *x, nullptr, act, n, tm);
     for (int b = 0; b < ns.blocks; ++b) {
-        LaunchConv(e, r, s, r.conv1[b], *x, *t, nullptr, act, n, tm);
         const int se = e->se_sizes[b];
+        const std::vector<DevConv>& cv = r.bconv[b];
+        // the block's last conv joins the skip connection; with an SE unit it is left linear and the skip is
+        // added by se_apply (blas_forward_pipe.cc:73-87,147-161,249-262)
+        const ActBuf* last_res = se > 0 ? nullptr : x;
+        const int last_act = se > 0 ? kIdentity : act;
+        if (e->block_types[b] == SB_BLOCK_RESIDUAL) {
+            // ResidualBlockForward, blas_forward_pipe.cc:46-88
+            LaunchConv(e, r, s, cv[0], *x, *t, nullptr, act, n, tm);
+            LaunchConv(e, r, s, cv[1], *t, *u, last_res, last_act, n, tm);
+        } else if (e->block_types[b] == SB_BLOCK_BOTTLENECK) {
+            // BottleneckBlockForward, blas_forward_pipe.cc:90-162: 1x1 down, 3x3, 3x3, 1x1 up (+ skip)
+            LaunchConv(e, r, s, cv[0], *x, s.ia, nullptr, act, n, tm);
+            LaunchConv(e, r, s, cv[1], s.ia, s.ib, nullptr, act, n, tm);
+            LaunchConv(e, r, s, cv[2], s.ib, s.ic, nullptr, act, n, tm);
+            LaunchConv(e, r, s, cv[3], s.ic, *u, last_res, last_act, n, tm);
+        } else {
+            // NestedBottleneckBlockForward, blas_forward_pipe.cc:164-263: 1x1 down, two inner residual blocks, 1x1 up
+            LaunchConv(e, r, s, cv[0], *x, s.ia, nullptr, act, n, tm);       // a
+            LaunchConv(e, r, s, cv[1], s.ia, s.ib, nullptr, act, n, tm);     // b = act(conv1(a))
+            LaunchConv(e, r, s, cv[2], s.ib, s.ic, &s.ia, act, n, tm);       // c = act(conv2(b) + a)
+            LaunchConv(e, r, s, cv[3], s.ic, s.ib, nullptr, act, n, tm);     // d = act(conv3(c))
+            LaunchConv(e, r, s, cv[4], s.ib, s.ia, &s.ic, act, n, tm);       // e = act(conv4(d) + c)
+            LaunchConv(e, r, s, cv[5], s.ia, *u, last_res, last_act, n, tm);
+        }
         if (se > 0) {
-            LaunchConv(e, r, s, r.conv2[b], *t, *u, nullptr, kIdentity, n, tm);
             const size_t smem = ((size_t)3 * C + se) * sizeof(float);
             se_pool_fc_kernel<<<dim3((C + 31) / 32, n), 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se,
                                                                                 F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
@@ -752,8 +790,6 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
                                           u->hi, u->lo, x->hi, x->lo, split, s.mask, s.gb, g, C, u->rows, n_rows)));
             SB_CUDA(cudaGetLastError());
             e->launches += 2;
-        } else {
-            LaunchConv(e, r, s, r.conv2[b], *t, *u, x, act, n, tm);
         }
         std::swap(x, u);
     }
@@ -856,6 +892,8 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
         e->net_shape.V = net->V;
         e->net_shape.act = net->act;
         e->se_sizes = net->se_sizes();
+        e->block_types = net->block_types();
+        e->inner_channels = net->inner_channels();
     } else {
         e->net_shape.version = shape_only->version;
         e->net_shape.input_channels = shape_only->input_channels;
@@ -865,6 +903,18 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
         e->net_shape.V = shape_only->value_channels;
         e->net_shape.act = shape_only->activation;
         e->se_sizes.assign(shape_only->se_sizes, shape_only->se_sizes + shape_only->blocks);
+        e->block_types.assign(shape_only->blocks, SB_BLOCK_RESIDUAL);
+        e->inner_channels.assign(shape_only->blocks, 0);
+        for (int b = 0; b < shape_only->blocks; ++b) {
+            if (shape_only->block_types) e->block_types[b] = shape_only->block_types[b];
+            const int ty = e->block_types[b];
+            if (ty < SB_BLOCK_RESIDUAL || ty > SB_BLOCK_NESTED_BOTTLENECK) return Fail(nullptr, SB_ERR_INVALID, "unsupported block type");
+            if (ty != SB_BLOCK_RESIDUAL) {
+                const int I = shape_only->inner_channels ? shape_only->inner_channels[b] : 0;
+                if (I < 16 || I > 256 || I % 16 || (I > 128 && I % 32)) return Fail(nullptr, SB_ERR_INVALID, "unsupported bottleneck width");
+                e->inner_channels[b] = I;
+            }
+        }
         const int C = e->net_shape.channels, PV = e->net_shape.P + e->net_shape.V;
         if (C < 16 || C > 256 || C % 16 || (C > 128 && C % 32) || PV % 4 || PV > 64 || e->net_shape.input_channels != SB_INPUT_CHANNELS)
             return Fail(nullptr, SB_ERR_INVALID, "unsupported network shape");
@@ -875,7 +925,8 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
             return Fail(nullptr, SB_ERR_INVALID, "policy and value head channels must be multiples of 8 summing to 16, 32, 48 or 64");
         if (e->net_shape.channels % 8) return Fail(nullptr, SB_ERR_INVALID, "channels must be a multiple of 8");
     }
-    e->layout = ComputeLayout(e->net_shape.blocks, e->net_shape.channels, e->net_shape.P, e->net_shape.V, e->se_sizes);
+    e->layout = ComputeLayout(e->net_shape.blocks, e->net_shape.channels, e->net_shape.P, e->net_shape.V, e->se_sizes,
+                              e->block_types, e->inner_channels);
     try {
         std::vector<uint8_t> blob;
         if (net) blob = PackBlob(*net, e->layout);
@@ -1308,7 +1359,8 @@ int sb_reconfigure(sb_engine* e, int board_size, int max_batch) {
 static int ReloadImpl(sb_engine* e, HostNet& net) {
     StopBatcher(e);
     if (net.blocks != e->net_shape.blocks || net.channels != e->net_shape.channels || net.P != e->net_shape.P ||
-        net.V != e->net_shape.V || net.se_sizes() != e->se_sizes)
+        net.V != e->net_shape.V || net.se_sizes() != e->se_sizes || net.block_types() != e->block_types ||
+        net.inner_channels() != e->inner_channels)
         return Fail(e, SB_ERR_INVALID, "reload requires the same architecture; destroy and create for a new one");
     try {
         e->net_shape.act = net.act;
@@ -1371,9 +1423,20 @@ int sb_get_net_desc(const sb_engine* e, sb_net_desc* d, int* se_sizes, int se_ca
     d->value_channels = e->net_shape.V;
     d->activation = e->net_shape.act;
     d->se_sizes = se_sizes;
+    d->block_types = nullptr;
+    d->inner_channels = nullptr;
     if (se_sizes) {
         if (se_capacity < e->net_shape.blocks) return SB_ERR_INVALID;
         for (int b = 0; b < e->net_shape.blocks; ++b) se_sizes[b] = e->se_sizes[b];
+    }
+    return SB_OK;
+}
+
+int sb_get_block_desc(const sb_engine* e, int* block_types, int* inner_channels, int capacity) {
+    if (!e || capacity < e->net_shape.blocks) return SB_ERR_INVALID;
+    for (int b = 0; b < e->net_shape.blocks; ++b) {
+        if (block_types) block_types[b] = e->block_types[b];
+        if (inner_channels) inner_channels[b] = e->inner_channels[b];
     }
     return SB_OK;
 }

@@ -229,14 +229,20 @@ void Parse(Reader& r, HostNet& net) {
             se = true;
             name = name.substr(0, dash);
         }
-        if (name != "ResidualBlock")
-            throw std::runtime_error("block type '" + name + "' is not supported by sayuri_b200 (ResidualBlock[-SE] only)");
         HostBlock& blk = net.tower[static_cast<size_t>(b)];
-        need(4);
-        ReadConvBn(r, &shapes[off], blk.conv1, v1);
-        off += 2;
-        ReadConvBn(r, &shapes[off], blk.conv2, v1);
-        off += 2;
+        if (name == "ResidualBlock") blk.type = SB_BLOCK_RESIDUAL;
+        else if (name == "BottleneckBlock") blk.type = SB_BLOCK_BOTTLENECK;
+        else if (name == "NestedBottleneckBlock") blk.type = SB_BLOCK_NESTED_BOTTLENECK;
+        else
+            throw std::runtime_error("block type '" + name + "' is not supported by sayuri_b200 (ResidualBlock, BottleneckBlock, NestedBottleneckBlock [-SE] only)");
+        const int nc = HostBlock::NumConvs(blk.type);
+        need(static_cast<size_t>(2 * nc));
+        blk.convs.resize(static_cast<size_t>(nc));
+        for (int q = 0; q < nc; ++q) {
+            ReadConvBn(r, &shapes[off], blk.convs[static_cast<size_t>(q)], v1);
+            off += 2;
+        }
+        blk.inner = blk.type == SB_BLOCK_RESIDUAL ? 0 : blk.convs[0].out;
         if (se) {
             need(2);
             ReadFC(r, shapes[off++], blk.squeeze);
@@ -281,7 +287,17 @@ bool ValidateNet(const HostNet& n, std::string& err) {
     if (!conv_ok(n.input_conv, SB_INPUT_CHANNELS, C, 3)) { err = "the input layers are wrong"; return false; }
     for (int b = 0; b < n.blocks; ++b) {
         const HostBlock& k = n.tower[static_cast<size_t>(b)];
-        if (!conv_ok(k.conv1, C, C, 3) || !conv_ok(k.conv2, C, C, 3)) { err = "residual block " + std::to_string(b + 1) + " is wrong"; return false; }
+        if (k.type < SB_BLOCK_RESIDUAL || k.type > SB_BLOCK_NESTED_BOTTLENECK || static_cast<int>(k.convs.size()) != HostBlock::NumConvs(k.type)) { err = "block " + std::to_string(b + 1) + " has an unsupported type"; return false; }
+        if (k.type == SB_BLOCK_RESIDUAL) {
+            if (!conv_ok(k.convs[0], C, C, 3) || !conv_ok(k.convs[1], C, C, 3)) { err = "residual block " + std::to_string(b + 1) + " is wrong"; return false; }
+        } else {
+            const int I = k.inner;
+            if (I < 16 || I > 256 || I % 16 != 0 || (I > 128 && I % 32 != 0)) { err = "bottleneck channels must be a multiple of 16 in [16, 256] (of 32 above 128)"; return false; }
+            const size_t last = k.convs.size() - 1;
+            if (!conv_ok(k.convs[0], C, I, 1) || !conv_ok(k.convs[last], I, C, 1)) { err = "the outer channels of bottleneck block " + std::to_string(b + 1) + " is wrong"; return false; }
+            for (size_t q = 1; q < last; ++q)
+                if (!conv_ok(k.convs[q], I, I, 3)) { err = "the inner channels of bottleneck block " + std::to_string(b + 1) + " is wrong"; return false; }
+        }
         if (k.se_size > 0 && (!fc_ok(k.squeeze, 3 * C, k.se_size) || !fc_ok(k.excite, k.se_size, 2 * C))) { err = "SE unit of block " + std::to_string(b + 1) + " is wrong"; return false; }
     }
     if (!conv_ok(n.p_hd_conv, C, P, 1) || !fc_ok(n.p_inter_fc, 3 * P, P) || !conv_ok(n.prob_conv, P, 5, 1) || !fc_ok(n.pass_fc, P, 5)) { err = "the policy head is wrong"; return false; }
@@ -346,8 +362,20 @@ bool NetFromAbi(const sb_net_desc* d, const sb_weights* w, HostNet& net, std::st
     net.tower.resize(static_cast<size_t>(net.blocks));
     for (int b = 0; b < net.blocks; ++b) {
         HostBlock& k = net.tower[static_cast<size_t>(b)];
-        conv(k.conv1, C, C, 3);
-        conv(k.conv2, C, C, 3);
+        k.type = d->block_types ? d->block_types[b] : SB_BLOCK_RESIDUAL;
+        if (k.type < SB_BLOCK_RESIDUAL || k.type > SB_BLOCK_NESTED_BOTTLENECK) { err = "unsupported block type in the net description"; return false; }
+        k.inner = k.type == SB_BLOCK_RESIDUAL ? 0 : (d->inner_channels ? d->inner_channels[b] : 0);
+        if (k.type != SB_BLOCK_RESIDUAL && k.inner <= 0) { err = "bottleneck block without inner_channels"; return false; }
+        k.convs.resize(static_cast<size_t>(HostBlock::NumConvs(k.type)));
+        if (k.type == SB_BLOCK_RESIDUAL) {
+            conv(k.convs[0], C, C, 3);
+            conv(k.convs[1], C, C, 3);
+        } else {
+            const size_t last = k.convs.size() - 1;
+            conv(k.convs[0], C, k.inner, 1);
+            for (size_t q = 1; q < last; ++q) conv(k.convs[q], k.inner, k.inner, 3);
+            conv(k.convs[last], k.inner, C, 1);
+        }
         k.se_size = d->se_sizes[b];
         if (k.se_size > 0) {
             fc(k.squeeze, 3 * C, k.se_size);

@@ -144,16 +144,29 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
     if (w.policy_head_type != PolicyHeadType::kNormal) {
         throw std::runtime_error("sayuri_b200: RepLK policy head is not supported");
     }
-    std::vector<int> se(w.residual_blocks, 0);
+    std::vector<int> se(w.residual_blocks, 0), types(w.residual_blocks, SB_BLOCK_RESIDUAL), inner(w.residual_blocks, 0);
     std::vector<sb_tensor> t;
     PushConv(t, w.input_conv);
     for (int b = 0; b < w.residual_blocks; ++b) {
         BlockBasic* blk = w.tower[b].get();
-        if (!blk->IsResidualBlock()) {
-            throw std::runtime_error("sayuri_b200: only ResidualBlock[-SE] towers are supported");
+        if (blk->IsResidualBlock()) {
+            PushConv(t, blk->conv1);
+            PushConv(t, blk->conv2);
+        } else if (blk->IsBottleneckBlock() || blk->IsNestedBottleneckBlock()) {
+            // loader order (loader.cc:416-555): pre 1x1, conv1, conv2 [, conv3, conv4], post 1x1
+            types[b] = blk->IsBottleneckBlock() ? SB_BLOCK_BOTTLENECK : SB_BLOCK_NESTED_BOTTLENECK;
+            inner[b] = blk->bottleneck_channels;
+            PushConv(t, blk->pre_btl_conv);
+            PushConv(t, blk->conv1);
+            PushConv(t, blk->conv2);
+            if (blk->IsNestedBottleneckBlock()) {
+                PushConv(t, blk->conv3);
+                PushConv(t, blk->conv4);
+            }
+            PushConv(t, blk->post_btl_conv);
+        } else {
+            throw std::runtime_error("sayuri_b200: MixerBlock towers are not supported");
         }
-        PushConv(t, blk->conv1);
-        PushConv(t, blk->conv2);
         if (blk->apply_se) {
             se[b] = blk->se_size;
             PushFc(t, blk->squeeze);
@@ -178,6 +191,8 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
     d.value_channels = w.value_head_channels;
     d.activation = static_cast<int>(w.default_act);
     d.se_sizes = se.data();
+    d.block_types = types.data();
+    d.inner_channels = inner.data();
     sb_weights sw{t.data(), (int)t.size()};
     const int precision = GetOption<bool>("fp16") ? SB_PRECISION_FP16 : SB_PRECISION_FP32_SPLIT;
     int rc = sb_create(&engine_, &d, &sw, gpus.empty() ? nullptr : gpus.data(), (int)gpus.size(), board_size_,

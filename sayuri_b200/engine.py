@@ -22,6 +22,10 @@ MAX_INTERSECTIONS = 361
 INPUT_CHANNELS = 43
 PLANE_FLOATS = INPUT_CHANNELS * MAX_INTERSECTIONS
 
+BLOCK_RESIDUAL = 0
+BLOCK_BOTTLENECK = 1
+BLOCK_NESTED_BOTTLENECK = 2
+
 PRECISION_FP32_SPLIT = 0
 PRECISION_FP16 = 1
 PRECISION_SIMT_DEBUG = 2
@@ -33,7 +37,7 @@ _I = ctypes.POINTER(ctypes.c_int)
 class SbNetDesc(ctypes.Structure):
     _fields_ = [("version", ctypes.c_int), ("input_channels", ctypes.c_int), ("blocks", ctypes.c_int),
                 ("channels", ctypes.c_int), ("policy_channels", ctypes.c_int), ("value_channels", ctypes.c_int),
-                ("activation", ctypes.c_int), ("se_sizes", _I)]
+                ("activation", ctypes.c_int), ("se_sizes", _I), ("block_types", _I), ("inner_channels", _I)]
 
 
 class SbTensor(ctypes.Structure):
@@ -77,7 +81,7 @@ ABI_SYMBOLS = [
     "sb_forward_batch", "sb_submit", "sb_wait", "sb_host_alloc", "sb_host_free", "sb_weights_blob",
     "sb_weights_export", "sb_weights_import",
     "sb_weights_checksum", "sb_time_forward", "sb_launch_count", "sb_debug_read_trunk", "sb_conv_stats", "sb_set_option",
-    "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
+    "sb_get_block_desc", "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
 ]
 
 _lib = None
@@ -106,6 +110,7 @@ def load_library():
     for name in ("sb_num_gpus", "sb_num_slots", "sb_max_batch", "sb_board_size"):
         getattr(lib, name).argtypes = [vp]
     lib.sb_get_net_desc.argtypes = [vp, ctypes.POINTER(SbNetDesc), _I, ctypes.c_int]
+    lib.sb_get_block_desc.argtypes = [vp, _I, _I, ctypes.c_int]
     lib.sb_forward_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_F), _I, _I, ctypes.c_void_p]
     lib.sb_submit.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, _I, _I]
     lib.sb_wait.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -197,9 +202,12 @@ class B200ForwardPipe:
         """desc: dict(version, blocks, channels, P, V, activation, se_sizes); tensors: list of float32 arrays in
         loader order with BN folded, or None to leave the weight blob to a later broadcast (weights_blob())."""
         self.destroy()
-        se = (ctypes.c_int * max(len(desc["se_sizes"]), 1))(*desc["se_sizes"])
+        nb = max(len(desc["se_sizes"]), 1)
+        se = (ctypes.c_int * nb)(*desc["se_sizes"])
+        types = (ctypes.c_int * nb)(*desc.get("block_types", [BLOCK_RESIDUAL] * len(desc["se_sizes"])))
+        inner = (ctypes.c_int * nb)(*desc.get("inner_channels", [0] * len(desc["se_sizes"])))
         d = SbNetDesc(desc.get("version", 5), INPUT_CHANNELS, desc["blocks"], desc["channels"], desc["P"], desc["V"],
-                      desc["activation"], se)
+                      desc["activation"], se, types, inner)
         wptr = None
         keep = []
         if tensors is not None:
@@ -244,8 +252,12 @@ class B200ForwardPipe:
         d = SbNetDesc()
         se = (ctypes.c_int * 1024)()
         self._check(self._lib.sb_get_net_desc(self._h, ctypes.byref(d), se, 1024))
+        types = (ctypes.c_int * 1024)()
+        inner = (ctypes.c_int * 1024)()
+        self._check(self._lib.sb_get_block_desc(self._h, types, inner, 1024))
         return dict(version=d.version, blocks=d.blocks, channels=d.channels, P=d.policy_channels, V=d.value_channels,
-                    activation=d.activation, se_sizes=[se[i] for i in range(d.blocks)])
+                    activation=d.activation, se_sizes=[se[i] for i in range(d.blocks)],
+                    block_types=[types[i] for i in range(d.blocks)], inner_channels=[inner[i] for i in range(d.blocks)])
 
     def release(self):
         self.destroy()

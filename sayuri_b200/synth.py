@@ -50,10 +50,23 @@ def synth_tensors(blocks, channels, P, V, seed=0, se_ratio=4, stack=None, activa
     conv(INPUT_CHANNELS, channels, 3)
     bn(channels)
     for name in stack:
-        conv(channels, channels, 3)
-        bn(channels)
-        conv(channels, channels, 3, gain=0.7)
-        bn(channels)
+        base = name.split("-")[0]
+        if base == "ResidualBlock":
+            conv(channels, channels, 3)
+            bn(channels)
+            conv(channels, channels, 3, gain=0.7)
+            bn(channels)
+        elif base in ("BottleneckBlock", "NestedBottleneckBlock"):   # loader.cc:416-555; inner = channels // 2 like network.py:1054
+            inner = channels // 2
+            conv(channels, inner, 1)
+            bn(inner)
+            for _ in range(2 if base == "BottleneckBlock" else 4):
+                conv(inner, inner, 3, gain=1.2)
+                bn(inner)
+            conv(inner, channels, 1, gain=0.7)
+            bn(channels)
+        else:
+            raise ValueError("unknown block type %s" % name)
         if name.endswith("-SE"):
             se = channels // se_ratio
             fc(3 * channels, se)

@@ -35,3 +35,16 @@ def oracle_lib():
     from oracle import oracle_py
     oracle_py.build()
     return oracle_py
+
+
+@pytest.fixture(scope="session")
+def golden_blocks():
+    """Second fixture: BottleneckBlock / NestedBottleneckBlock [-SE] tower, outputs of the
+    UNMODIFIED compiled reference (tests/golden/make_golden.py blocks)."""
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "golden_btl_5bx32.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_blocks_weights():
+    return os.path.join(GOLDEN, "ref_btl_5bx32.bin.txt")

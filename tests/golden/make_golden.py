@@ -40,6 +40,65 @@ CFG = {
 }
 
 
+CFG_BLOCKS = {
+    "NeuralNetwork": {
+        "NNType": "Residual", "MaxBoardSize": 19, "ResidualChannels": 32, "PolicyHeadChannels": 8,
+        "ValueHeadChannels": 8, "SeRatio": 4, "PolicyHeadType": "Normal", "Activation": "mish",
+        "Stack": ["BottleneckBlock-SE", "NestedBottleneckBlock", "ResidualBlock", "NestedBottleneckBlock-SE", "BottleneckBlock"],
+    },
+    "Train": {"TrainDirectory": "x", "StorePath": "x", "UseGPU": False},
+}
+
+
+def randomise_bn(net, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, mod in net.named_modules():
+            if hasattr(mod, "running_mean") and hasattr(mod, "running_var"):
+                mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.2)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) * 1.5 + 0.5)
+                if getattr(mod, "beta", None) is not None:
+                    mod.beta.copy_(torch.randn(mod.beta.shape, generator=g) * 0.1)
+                if getattr(mod, "gamma", None) is not None:
+                    mod.gamma.copy_(torch.rand(mod.gamma.shape, generator=g) * 0.8 + 0.6)
+
+
+def main_blocks():
+    """Second fixture: the optional block families — BottleneckBlock and NestedBottleneckBlock,
+    with and without SE (blas_forward_pipe.cc:90-263) — exported by the reference writer, evaluated by the
+    UNMODIFIED compiled reference (im2col path) and cross-checked against the reference's PyTorch forward."""
+    torch.manual_seed(20260418)
+    np.random.seed(20260418)
+    net = Network(Config(json.dumps(CFG_BLOCKS), is_file=False))
+    net.eval()
+    randomise_bn(net, 9)
+    wbin = os.path.join(HERE, "ref_btl_5bx32.bin.txt")
+    net.transfer_to_bin(wbin)
+    out = {}
+    ref = Reference(wbin, winograd=False)
+    per = 2
+    for bs in (9, 13, 19):
+        x = synth.synth_positions(per, bs, seed=21)
+        out["planes_%d" % bs] = x
+        with torch.no_grad():
+            pred, _ = net(torch.from_numpy(x).reshape(per, 43, bs, bs))
+        prob5 = torch.stack([p[:, :-1] for p in pred[:5]], dim=1).numpy()
+        for i in range(per):
+            off = (i * 2 + bs) % 5
+            r = ref.forward(x[i], bs, offset=off)
+            v = np.concatenate([r["prob"], r["own"], r["misc"]])
+            out["ref_%d_%d" % (bs, i)] = v
+            out["offset_%d_%d" % (bs, i)] = np.int32(off)
+            s = bs * bs
+            d = np.abs(v[:s] - prob5[i, off]).max()
+            d_own = np.abs(np.tanh(v[s:2 * s]) - pred[5].numpy()[i]).max()
+            d_wdl = np.abs(v[2 * s + 1:2 * s + 4] - pred[6].numpy()[i]).max()
+            print("blocks net, bs %2d pos %d: C++ vs torch prob %.2e own %.2e wdl %.2e" % (bs, i, d, d_own, d_wdl))
+            assert max(d, d_own, d_wdl) < 5e-5
+    np.savez_compressed(os.path.join(HERE, "golden_btl_5bx32.npz"), **out)
+    print("wrote", wbin, "golden_btl_5bx32.npz")
+
+
 def main():
     torch.manual_seed(20260417)
     np.random.seed(20260417)
@@ -129,4 +188,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "blocks":
+        main_blocks()      # only the second fixture (the first one stays byte-identical)
+    else:
+        main()
+        main_blocks()

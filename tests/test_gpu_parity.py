@@ -406,3 +406,50 @@ def test_scheduling_knobs_do_not_change_a_single_bit(eng):
                         assert np.array_equal(base[f], other[f]), (prec, n, knob, f)
             finally:
                 pipe.destroy()
+
+
+def test_bottleneck_and_nested_bottleneck_blocks_match_reference_golden(eng, golden_blocks, golden_blocks_weights):
+    """BottleneckBlock[-SE] / NestedBottleneckBlock[-SE] towers (blas_forward_pipe.cc:90-263) against
+    outputs of the UNMODIFIED compiled reference, every board size in one mixed batch, 1e-4."""
+    pipe = eng.B200ForwardPipe().initialize(golden_blocks_weights, 19, 8, gpus=[0])
+    try:
+        d = pipe.net_desc()
+        assert d["block_types"] == [eng.BLOCK_BOTTLENECK, eng.BLOCK_NESTED_BOTTLENECK, eng.BLOCK_RESIDUAL,
+                                    eng.BLOCK_NESTED_BOTTLENECK, eng.BLOCK_BOTTLENECK]
+        assert d["inner_channels"] == [16, 16, 0, 16, 16] and d["se_sizes"] == [8, 0, 0, 8, 0]
+        planes, sizes, offsets, refs = [], [], [], []
+        for bs in SIZES:
+            for i in range(2):
+                planes.append(golden_blocks["planes_%d" % bs][i].ravel())
+                sizes.append(bs)
+                offsets.append(int(golden_blocks["offset_%d_%d" % (bs, i)]))
+                v = golden_blocks["ref_%d_%d" % (bs, i)]
+                s = bs * bs
+                refs.append(dict(prob=v[:s], own=v[s:2 * s], misc=v[2 * s:]))
+        out = pipe.batch_forward(0, planes, sizes, offsets)
+        for o, r, bs in zip(out, refs, sizes):
+            _check(o, r, bs)
+    finally:
+        pipe.destroy()
+
+
+@pytest.mark.parametrize("prec_name", ["fp32_split", "fp16"])
+def test_wide_bottleneck_tower_matches_oracle(eng, oracle_lib, prec_name):
+    """A 128-wide tower mixing all three block families (inner width 64: one 64-channel K block, 1x1 convs as
+    single-tap launches) against the CPU oracle; also through sb_create with explicit block descriptors."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_btl_6bx128.bin")
+    stack = ["NestedBottleneckBlock", "BottleneckBlock-SE", "ResidualBlock", "NestedBottleneckBlock-SE", "BottleneckBlock", "ResidualBlock-SE"]
+    synth.write_synth_net(path, (6, 128, 16, 16), seed=91, stack=stack)
+    prec = eng.PRECISION_FP32_SPLIT if prec_name == "fp32_split" else eng.PRECISION_FP16
+    atol = ATOL if prec_name == "fp32_split" else 5e-2
+    sizes = [19, 9, 13, 19, 19]
+    planes = [synth.synth_positions(1, bs, seed=70 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    orc = oracle_lib.Oracle(path)
+    pipe = eng.B200ForwardPipe().initialize(path, 19, 8, gpus=[0], precision=prec)
+    try:
+        out = pipe.batch_forward(0, planes, sizes, [0, 1, 2, 3, 4])
+        for i, bs in enumerate(sizes):
+            _check(out[i], orc.forward(planes[i], bs, i), bs, atol=atol)
+    finally:
+        pipe.destroy()

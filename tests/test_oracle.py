@@ -33,6 +33,22 @@ def test_oracle_matches_reference_golden(oracle_lib, golden, golden_weights_bin,
             np.testing.assert_allclose(got["misc"], misc, rtol=0, atol=ORACLE_VS_REF_ATOL)
 
 
+def test_oracle_matches_reference_golden_on_bottleneck_blocks(oracle_lib, golden_blocks, golden_blocks_weights):
+    """BottleneckBlock[-SE] and NestedBottleneckBlock[-SE] (blas_forward_pipe.cc:90-263), mixed with a plain
+    ResidualBlock, against the compiled reference's outputs."""
+    o = oracle_lib.Oracle(golden_blocks_weights)
+    assert (o.blocks, o.channels, o.P, o.V, o.act, o.n_se) == (5, 32, 8, 8, 5, 2)
+    for bs in SIZES:
+        x = golden_blocks["planes_%d" % bs]
+        for i in range(PER):
+            off = int(golden_blocks["offset_%d_%d" % (bs, i)])
+            got = o.forward(x[i], bs, offset=off)
+            prob, own, misc = _unpack(golden_blocks["ref_%d_%d" % (bs, i)], bs)
+            np.testing.assert_allclose(got["prob"], prob, rtol=0, atol=ORACLE_VS_REF_ATOL)
+            np.testing.assert_allclose(got["own"], own, rtol=0, atol=ORACLE_VS_REF_ATOL)
+            np.testing.assert_allclose(got["misc"], misc, rtol=0, atol=ORACLE_VS_REF_ATOL)
+
+
 def test_oracle_matches_reference_pytorch_forward(oracle_lib, golden, golden_weights_bin):
     """Second, independent pin: all five policy planes, pass logits and the value outputs of
     train/torch/network.py:1121-1215 (which applies tanh / scaling inside forward)."""
