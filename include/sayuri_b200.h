@@ -43,13 +43,19 @@ typedef enum sb_precision {
                                     of the tensor-core kernel, test use only                               */
 } sb_precision;
 
-/* Tower block families (BlockBasic::Type, src/neural/description.h:88-132).  The Mixer block (depthwise conv + FFN)
- * and the RepLK policy head are not implemented and are rejected at load. */
+/* Tower block families (BlockBasic::Type, src/neural/description.h:88-132). */
 typedef enum sb_block_type {
     SB_BLOCK_RESIDUAL = 0,           /* conv3x3, conv3x3 (+skip)                    blas_forward_pipe.cc:46-88    */
     SB_BLOCK_BOTTLENECK = 1,         /* 1x1 down, 2 x conv3x3, 1x1 up (+skip)       blas_forward_pipe.cc:90-162   */
-    SB_BLOCK_NESTED_BOTTLENECK = 2   /* 1x1 down, 2 inner residual blocks, 1x1 up   blas_forward_pipe.cc:164-263  */
+    SB_BLOCK_NESTED_BOTTLENECK = 2,  /* 1x1 down, 2 inner residual blocks, 1x1 up   blas_forward_pipe.cc:164-263  */
+    SB_BLOCK_MIXER = 3               /* depthwise k x k (+skip), 1x1 FFN up, 1x1 FFN down (+skip)       :265-312  */
 } sb_block_type;
+
+/* PolicyHeadType (src/neural/description.h:158, loader.cc:245-259) */
+typedef enum sb_policy_head_type {
+    SB_POLICY_HEAD_NORMAL = 0,
+    SB_POLICY_HEAD_REPLK = 1         /* + depthwise k x k and 1x1 after the head-entry conv, blas_forward_pipe.cc:443-471 */
+} sb_policy_head_type;
 
 /* Network description == the scalar fields of DNNWeights (src/neural/description.h:164-215). */
 typedef struct sb_net_desc {
@@ -62,7 +68,11 @@ typedef struct sb_net_desc {
     int activation;         /* same ints as enum Activation, src/neural/activation.h:8-17          */
     const int* se_sizes;    /* [blocks]: 0 = no SE unit, >0 = squeeze width of ...-SE               */
     const int* block_types; /* [blocks] sb_block_type, or NULL = all SB_BLOCK_RESIDUAL             */
-    const int* inner_channels; /* [blocks] bottleneck_channels of (Nested)Bottleneck blocks, or NULL */
+    const int* inner_channels; /* [blocks] bottleneck_channels of (Nested)Bottleneck blocks / feedforward_channels of
+                                  Mixer blocks, or NULL                                                              */
+    const int* dw_kernels;  /* [blocks] depthwise filter size of Mixer blocks, or NULL = 7                  */
+    int policy_head_type;   /* sb_policy_head_type                                                 */
+    int policy_dw_kernel;   /* depthwise filter size of the RepLK head (0 = 7)                     */
 } sb_net_desc;
 
 /* One tensor, fp32, caller-owned for the duration of the call only. */
@@ -75,7 +85,8 @@ typedef struct sb_tensor {
  * Weights in the loader's tensor order (src/neural/loader.cc:658-747) AFTER ProcessWeights
  * (loader.cc:775-831): batch-norm already folded, so every layer contributes exactly two tensors
  * {weights, biases}: input conv; per block conv1, conv2 (Bottleneck: pre_btl_conv, conv1, conv2, post_btl_conv;
- * NestedBottleneck: pre_btl_conv, conv1..conv4, post_btl_conv) [, squeeze FC, excite FC]; policy head conv,
+ * NestedBottleneck: pre_btl_conv, conv1..conv4, post_btl_conv; Mixer: dw_conv [C][k][k], conv1, conv2)
+ * [, squeeze FC, excite FC]; policy head conv [, RepLK: p_dw_conv [P][k][k], p_pt_conv],
  * policy intermediate FC, prob conv, pass FC; value head conv, value intermediate FC, ownership conv,
  * misc FC.  Conv weights are UNTRANSFORMED OIHW (ConvLayer::GetWeights, never GetTransformF);
  * FC weights [out][in].
@@ -148,6 +159,7 @@ int sb_max_batch(const sb_engine* e);
 int sb_board_size(const sb_engine* e);
 int sb_get_net_desc(const sb_engine* e, sb_net_desc* desc, int* se_sizes, int se_capacity);
 int sb_get_block_desc(const sb_engine* e, int* block_types, int* inner_channels, int capacity);
+int sb_get_dw_desc(const sb_engine* e, int* dw_kernels, int capacity, int* policy_head_type, int* policy_dw_kernel);
 
 /* ---- the hot path: CudaForwardPipe::BatchForward -> NNGraph::BatchForward, --------------------------
  *      src/neural/cuda/cuda_forward_pipe.cc:32-34,684-1018 (+ FillOutputs :1020-1090);

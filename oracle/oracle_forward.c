@@ -39,12 +39,13 @@ typedef struct {
     float* b;
 } fc_t;
 
-/* description.h:88-132 (BlockBasic): the Mixer block (depthwise conv + FFN) is outside the oracle's scope */
-enum { BLK_RESIDUAL = 0, BLK_BOTTLENECK = 1, BLK_NESTED = 2 };
+/* description.h:88-132 (BlockBasic) */
+enum { BLK_RESIDUAL = 0, BLK_BOTTLENECK = 1, BLK_NESTED = 2, BLK_MIXER = 3 };
 
 typedef struct {
-    int type, inner; /* inner = bottleneck_channels (0 for a plain residual block) */
+    int type, inner; /* inner = bottleneck_channels / feedforward_channels (0 for a plain residual block) */
     conv_t conv1, conv2, conv3, conv4, pre, post;
+    conv_t dw;       /* Mixer: depthwise k x k, w = [C][k][k] (in == 1 marks depthwise) */
     int apply_se, se_size;
     fc_t squeeze, excite;
 } block_t;
@@ -54,6 +55,8 @@ typedef struct oracle_net {
     conv_t input_conv;
     block_t* tower;
     conv_t p_hd_conv;
+    int replk;               /* PolicyHeadType RepLK: depthwise k x k + 1x1 after the head-entry conv */
+    conv_t p_dw_conv, p_pt_conv;
     fc_t p_inter_fc;
     conv_t prob_conv;
     fc_t pass_fc;
@@ -147,8 +150,12 @@ static void fold_bn(conv_t* c, const float* mean, const float* scale) {
 }
 
 static int rd_conv(rd_t* r, const shape_t* sh, conv_t* c, char* err, int errlen) {
-    if (sh->kind != 'C') { snprintf(err, errlen, "expected Convolution layer"); return -1; }
+    if (sh->kind != 'C' && sh->kind != 'D') { snprintf(err, errlen, "expected Convolution layer"); return -1; }
     c->in = sh->d[0]; c->out = sh->d[1]; c->k = sh->d[2];
+    if (sh->kind == 'D') {   /* "DepthwiseConvolution 1 C k" (network.py writer): one k x k filter per channel (convolution.cc:27-62) */
+        if (c->in != 1 && c->in != c->out) { snprintf(err, errlen, "depthwise convolution shape is wrong"); return -1; }
+        c->in = 1;
+    }
     c->w = rd_tensor(r, c->in * c->out * c->k * c->k, err, errlen);
     if (!c->w) return -1;
     c->b = rd_tensor(r, c->out, err, errlen);
@@ -228,8 +235,9 @@ oracle_net* oracle_load(const char* path, char* err, int errlen) {
                 else if (!strcmp(k, "ResidualBlocks")) residual_blocks = atoi(v);
                 else if (!strcmp(k, "PolicyHeadChannels") || !strcmp(k, "PolicyExtract")) P = atoi(v);
                 else if (!strcmp(k, "ValueHeadChannels") || !strcmp(k, "ValueExtract")) V = atoi(v);
-                else if (!strcmp(k, "PolicyHeadType")) {
-                    if (act_from_name(v) < 0 && strcasecmp(v, "normal")) { snprintf(err, errlen, "policy head type %s is outside the oracle's scope", v); goto fail; }
+                else if (!strcmp(k, "PolicyHeadType")) {   /* loader.cc:245-259 */
+                    if (!strcasecmp(v, "replk")) n->replk = 1;
+                    else if (strcasecmp(v, "normal")) { snprintf(err, errlen, "policy head type %s is outside the oracle's scope", v); goto fail; }
                 } else if (!strcmp(k, "ActivationFunction")) {
                     n->act = act_from_name(v);
                     if (n->act < 0) { snprintf(err, errlen, "Unknown activation type."); goto fail; }
@@ -315,7 +323,18 @@ oracle_net* oracle_load(const char* path, char* err, int errlen) {
                 if (blk->pre.k != 1 || blk->post.k != 1 || blk->pre.in != channels || blk->post.out != channels || blk->post.in != blk->inner) { snprintf(err, errlen, "the outer channels of bottleneck block is wrong"); goto fail; }
                 for (int q = 1; q < ns - 1; ++q)
                     if (seq[q]->k != 3 || seq[q]->in != blk->inner || seq[q]->out != blk->inner) { snprintf(err, errlen, "the inner channels of bottleneck block is wrong"); goto fail; }
-            } else { snprintf(err, errlen, "block type %s is outside the oracle's scope (ResidualBlock, BottleneckBlock, NestedBottleneckBlock [-SE])", stack[b]); goto fail; }
+            } else if (!strcmp(stack[b], "MixerBlock")) {
+                /* loader.cc:556-607: depthwise k x k + bn, 1x1 C->F + bn, 1x1 F->C + bn */
+                blk->type = BLK_MIXER;
+                if (rd_conv_bn(&r, &shapes[off], &blk->dw, v1, err, errlen)) goto fail;
+                off += 2;
+                if (rd_conv_bn(&r, &shapes[off], &blk->conv1, v1, err, errlen)) goto fail;
+                off += 2;
+                if (rd_conv_bn(&r, &shapes[off], &blk->conv2, v1, err, errlen)) goto fail;
+                off += 2;
+                blk->inner = blk->conv1.out;
+                if (blk->dw.in != 1 || blk->dw.out != channels || blk->conv1.k != 1 || blk->conv2.k != 1 || blk->conv1.in != channels || blk->conv2.in != blk->inner || blk->conv2.out != channels) { snprintf(err, errlen, "the channels of mixer block is wrong"); goto fail; }
+            } else { snprintf(err, errlen, "block type %s is outside the oracle's scope", stack[b]); goto fail; }
             if (se) {
                 if (rd_fc(&r, &shapes[off], &blk->squeeze, err, errlen)) goto fail;
                 off += 1;
@@ -329,6 +348,13 @@ oracle_net* oracle_load(const char* path, char* err, int errlen) {
         /* policy head, loader.cc:684-729 */
         if (rd_conv_bn(&r, &shapes[off], &n->p_hd_conv, v1, err, errlen)) goto fail;
         off += 2;
+        if (n->replk) {   /* loader.cc:691-702 */
+            if (rd_conv_bn(&r, &shapes[off], &n->p_dw_conv, v1, err, errlen)) goto fail;
+            off += 2;
+            if (rd_conv_bn(&r, &shapes[off], &n->p_pt_conv, v1, err, errlen)) goto fail;
+            off += 2;
+            if (n->p_dw_conv.in != 1 || n->p_dw_conv.out != P || n->p_pt_conv.k != 1 || n->p_pt_conv.in != P || n->p_pt_conv.out != P) { snprintf(err, errlen, "the RepLK policy head is wrong"); goto fail; }
+        }
         if (rd_fc(&r, &shapes[off++], &n->p_inter_fc, err, errlen)) goto fail;
         if (rd_conv(&r, &shapes[off++], &n->prob_conv, err, errlen)) goto fail;
         if (rd_fc(&r, &shapes[off++], &n->pass_fc, err, errlen)) goto fail;
@@ -361,12 +387,12 @@ void oracle_free(oracle_net* n) {
     if (n->tower) {
         for (int b = 0; b < n->blocks; ++b) {
             free_conv(&n->tower[b].conv1); free_conv(&n->tower[b].conv2); free_conv(&n->tower[b].conv3);
-            free_conv(&n->tower[b].conv4); free_conv(&n->tower[b].pre); free_conv(&n->tower[b].post);
+            free_conv(&n->tower[b].conv4); free_conv(&n->tower[b].pre); free_conv(&n->tower[b].post); free_conv(&n->tower[b].dw);
             free_fc(&n->tower[b].squeeze); free_fc(&n->tower[b].excite);
         }
         free(n->tower);
     }
-    free_conv(&n->p_hd_conv); free_fc(&n->p_inter_fc); free_conv(&n->prob_conv); free_fc(&n->pass_fc);
+    free_conv(&n->p_hd_conv); free_conv(&n->p_dw_conv); free_conv(&n->p_pt_conv); free_fc(&n->p_inter_fc); free_conv(&n->prob_conv); free_fc(&n->pass_fc);
     free_conv(&n->v_hd_conv); free_fc(&n->v_inter_fc); free_conv(&n->v_ownership); free_fc(&n->v_misc);
     free(n);
 }
@@ -390,14 +416,18 @@ int oracle_get_tensor(const oracle_net* n, int idx, int which, const float** out
 #define EMIT_FC(f) do { if (i++ == idx) { *out = which ? (f).b : (f).w; return which ? (f).out : (f).out * (f).in; } } while (0)
     EMIT_CONV(n->input_conv);
     for (int b = 0; b < n->blocks; ++b) {
-        if (n->tower[b].type != BLK_RESIDUAL) EMIT_CONV(n->tower[b].pre);
+        const int ty = n->tower[b].type;
+        if (ty == BLK_MIXER) EMIT_CONV(n->tower[b].dw);
+        if (ty == BLK_BOTTLENECK || ty == BLK_NESTED) EMIT_CONV(n->tower[b].pre);
         EMIT_CONV(n->tower[b].conv1);
         EMIT_CONV(n->tower[b].conv2);
-        if (n->tower[b].type == BLK_NESTED) { EMIT_CONV(n->tower[b].conv3); EMIT_CONV(n->tower[b].conv4); }
-        if (n->tower[b].type != BLK_RESIDUAL) EMIT_CONV(n->tower[b].post);
+        if (ty == BLK_NESTED) { EMIT_CONV(n->tower[b].conv3); EMIT_CONV(n->tower[b].conv4); }
+        if (ty == BLK_BOTTLENECK || ty == BLK_NESTED) EMIT_CONV(n->tower[b].post);
         if (n->tower[b].apply_se) { EMIT_FC(n->tower[b].squeeze); EMIT_FC(n->tower[b].excite); }
     }
-    EMIT_CONV(n->p_hd_conv); EMIT_FC(n->p_inter_fc); EMIT_CONV(n->prob_conv); EMIT_FC(n->pass_fc);
+    EMIT_CONV(n->p_hd_conv);
+    if (n->replk) { EMIT_CONV(n->p_dw_conv); EMIT_CONV(n->p_pt_conv); }
+    EMIT_FC(n->p_inter_fc); EMIT_CONV(n->prob_conv); EMIT_FC(n->pass_fc);
     EMIT_CONV(n->v_hd_conv); EMIT_FC(n->v_inter_fc); EMIT_CONV(n->v_ownership); EMIT_FC(n->v_misc);
 #undef EMIT_CONV
 #undef EMIT_FC
@@ -461,6 +491,36 @@ static void add_spatial_biases(int bs, int channels, float* x, const float* bias
             x[(size_t)c * s + i] = activate(v, act);
         }
     }
+}
+
+/* DepthwiseConvolution::Forward, convolution.cc:27-62: per-channel k x k cross-correlation, zero outside the board. */
+static void dwconv_forward(const conv_t* c, int bs, const float* in, float* out) {
+    const int s = bs * bs, k = c->k, pad = k / 2;
+    for (int ch = 0; ch < c->out; ++ch) {
+        const float* ip = in + (size_t)ch * s;
+        const float* wp = c->w + (size_t)ch * k * k;
+        for (int y = 0; y < bs; ++y)
+            for (int x = 0; x < bs; ++x) {
+                float v = 0.f;
+                for (int ky = 0; ky < k; ++ky)
+                    for (int kx = 0; kx < k; ++kx) {
+                        const int yy = y + ky - pad, xx = x + kx - pad;
+                        if (yy >= 0 && yy < bs && xx >= 0 && xx < bs) v += ip[yy * bs + xx] * wp[ky * k + kx];
+                    }
+                out[(size_t)ch * s + y * bs + x] = v;
+            }
+    }
+}
+
+/* AddSpatialBiasesPost::Forward, biases.cc:47-77: activation FIRST, then the residual. */
+static void add_spatial_biases_post(int bs, int channels, float* x, const float* bias, const float* residual, int act) {
+    const int s = bs * bs;
+    for (int c = 0; c < channels; ++c)
+        for (int i = 0; i < s; ++i) {
+            float v = activate(x[(size_t)c * s + i] + bias[c], act);
+            if (residual) v += residual[(size_t)c * s + i];
+            x[(size_t)c * s + i] = v;
+        }
 }
 
 /* FullyConnect::Forward, fullyconnect.cc:7-19 + AddVectorBiases biases.cc:79-89 */
@@ -551,6 +611,26 @@ int oracle_forward_trace(const oracle_net* n, const float* planes, int bs, int o
     for (int b = 0; b < n->blocks; ++b) {
         const block_t* blk = &n->tower[b];
         const conv_t* last;     /* the conv whose output joins the skip connection (or feeds the SE unit) */
+        if (blk->type == BLK_MIXER) {
+            /* MixerBlockForward :265-312: y = act(dw(x) + b) + x ; out = conv2(act(conv1(y))) (+ y, act) */
+            const int F = blk->inner;
+            float* f = (float*)malloc(sizeof(float) * (size_t)F * s);
+            dwconv_forward(&blk->dw, bs, x, t);
+            add_spatial_biases_post(bs, C, t, blk->dw.b, x, act);
+            conv_forward(&blk->conv1, bs, t, f);
+            add_spatial_biases(bs, F, f, blk->conv1.b, NULL, act);
+            conv_forward(&blk->conv2, bs, f, u);
+            free(f);
+            /* the skip of this block (and of its SE unit, :408-420) is y, not x */
+            if (blk->apply_se) {
+                add_spatial_biases(bs, C, u, blk->conv2.b, NULL, ACT_IDENTITY);
+                se_unit(bs, C, blk, u, t, act);
+            } else {
+                add_spatial_biases(bs, C, u, blk->conv2.b, t, act);
+            }
+            float* tmp = x; x = u; u = tmp;
+            continue;
+        }
         if (blk->type == BLK_RESIDUAL) {
             /* ResidualBlockForward :46-88 */
             conv_forward(&blk->conv1, bs, x, t);
@@ -600,6 +680,14 @@ int oracle_forward_trace(const oracle_net* n, const float* planes, int bs, int o
     float pass[5], misc[15];
     conv_forward(&n->p_hd_conv, bs, x, p);
     add_spatial_biases(bs, P, p, n->p_hd_conv.b, NULL, act);
+    if (n->replk) {   /* :443-471: depthwise k x k (+bias, act), then 1x1 P->P (+bias, act) */
+        float* pb = (float*)malloc(sizeof(float) * (size_t)P * s);
+        dwconv_forward(&n->p_dw_conv, bs, p, pb);
+        add_spatial_biases(bs, P, pb, n->p_dw_conv.b, NULL, act);
+        conv_forward(&n->p_pt_conv, bs, pb, p);
+        add_spatial_biases(bs, P, p, n->p_pt_conv.b, NULL, act);
+        free(pb);
+    }
     global_pool(bs, P, p, ppool);
     fc_forward(&n->p_inter_fc, ppool, pint, act);
     add_spatial_biases(bs, P, p, pint, NULL, ACT_IDENTITY); /* :483-484 per-channel add, no activation */

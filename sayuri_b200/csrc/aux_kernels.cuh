@@ -286,6 +286,69 @@ __global__ void se_apply_kernel(__half* __restrict__ u_hi, __half* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// dwconv: DepthwiseConvolution::Forward (convolution.cc:27-62) + bias + activation on the C8 canvas, optionally
+// followed by "+ input" (AddSpatialBiasesPost, biases.cc:47-77: activation FIRST, then the residual) — the first
+// stage of a Mixer block (blas_forward_pipe.cc:265-285) and the depthwise stage of the RepLK policy head
+// (:443-457).  One thread per (canvas row, 8-channel chunk); the k x k taps of a chunk sit in shared memory; taps
+// are bounds-checked against the sample's own board (a shift of more than one cell can land in a neighbouring
+// board row or sample, which the one-cell zero halo does not cover).  w: fp32 [C][k*k], k odd <= 15.
+template <int ACT>
+__global__ void __launch_bounds__(128)
+dwconv_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
+              __half* __restrict__ out_lo, bool split, const float* __restrict__ w, const float* __restrict__ bias,
+              const int* __restrict__ board_sizes, Geom g, int n, int n_rows, int R_in, int R_out, int k, bool add_input) {
+    __shared__ float sw[15 * 15 * 8];
+    __shared__ float sb8[8];
+    const int chunk = blockIdx.y;
+    const int kk = k * k;
+    for (int i = threadIdx.x; i < kk * 8; i += blockDim.x) {
+        const int tap = i >> 3, c = i & 7;
+        sw[i] = w[(size_t)(chunk * 8 + c) * kk + tap];
+    }
+    if (threadIdx.x < 8) sb8[threadIdx.x] = bias[chunk * 8 + threadIdx.x];
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int b = r / g.SS, rem = r - b * g.SS;
+    const int y = rem / g.P, x = rem - y * g.P;
+    const int bs = b < n ? board_sizes[b] : 0;
+    const bool live = (y < bs) && (x < bs);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int row = kGuardRows + r;
+    if (live) {
+        const int pad = k >> 1;
+        for (int ky = 0; ky < k; ++ky) {
+            const int yy = y + ky - pad;
+            if ((unsigned)yy >= (unsigned)bs) continue;
+            for (int kx = 0; kx < k; ++kx) {
+                const int xx = x + kx - pad;
+                if ((unsigned)xx >= (unsigned)bs) continue;
+                float v[8];
+                const size_t off = act_index(row + (ky - pad) * g.P + (kx - pad), chunk * 8, R_in);
+                load8(in_hi + off, in_lo + off, split, v);
+                const float* wt = sw + (ky * k + kx) * 8;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += v[i] * wt[i];   // same tap order as the reference loop
+            }
+        }
+        float self[8];
+        if (add_input) {
+            const size_t off = act_index(row, chunk * 8, R_in);
+            load8(in_hi + off, in_lo + off, split, self);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i] = activate_t<ACT>(acc[i] + sb8[i]);
+            if (add_input) acc[i] += self[i];
+        }
+    }
+    const size_t off = act_index(row, chunk * 8, R_out);
+    store8(out_hi + off, out_lo + off, split, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // (The two head-entry 1x1 convolutions, blas_forward_pipe.cc:430-442,513-522, run as ONE single-tap launch of
 // the tensor-core conv kernel with the policy and value filters concatenated: pv[row][0:P] policy, [P:P+V] value.)
 struct HeadWeights {

@@ -469,11 +469,16 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     }
                     split16(v, oh, ol, SPLIT);
                     if ((p.dbg & 1) && oh[0] != 0x12345678u) continue;
-                    *reinterpret_cast<uint4*>(p.out_hi + o0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-                    *reinterpret_cast<uint4*>(p.out_hi + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-                    if (SPLIT) {
-                        *reinterpret_cast<uint4*>(p.out_lo + o0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-                        *reinterpret_cast<uint4*>(p.out_lo + o1) = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+                    // cout may be a multiple of 8 only (weight rows are zero-padded to 16): channels >= cout belong to
+                    // somebody else (the value half of the head buffer behind a RepLK 1x1) and are not written
+                    const int ch0 = w.n0 + cbase + c0;
+                    if (ch0 < p.cout) {
+                        *reinterpret_cast<uint4*>(p.out_hi + o0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                        if (SPLIT) *reinterpret_cast<uint4*>(p.out_lo + o0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                    }
+                    if (ch0 + 8 < p.cout) {
+                        *reinterpret_cast<uint4*>(p.out_hi + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+                        if (SPLIT) *reinterpret_cast<uint4*>(p.out_lo + o1) = make_uint4(ol[4], ol[5], ol[6], ol[7]);
                     }
                 }
             }

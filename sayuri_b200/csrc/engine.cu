@@ -118,8 +118,12 @@ static CUtensorMap MakeActMap3(const void* base, int R, int chunks) {
 // ------------------------------------------------------------------------------------------------
 // Weight blob: every device-resident parameter of one replica, packed once on the host.
 struct ConvLayout {
-    int cin = 0, cinp = 0, cout = 0, kh = 0, bn = 0, ntiles = 0, taps = 9;
+    int cin = 0, cinp = 0, cout = 0, coutp = 0, kh = 0, bn = 0, ntiles = 0, taps = 9;
     size_t w_hi = 0, w_lo = 0, bias = 0;  // byte offsets into the blob
+};
+struct DwLayout {   // depthwise k x k filters, fp32 [ch][k*k], + bias [ch]
+    int ch = 0, k = 0;
+    size_t w = 0, b = 0;
 };
 struct FcLayout {
     int in = 0, out = 0;
@@ -127,7 +131,10 @@ struct FcLayout {
 };
 struct BlobLayout {
     ConvLayout input;
-    std::vector<std::vector<ConvLayout>> bconv;   // per block, loader order (HostBlock::convs)
+    std::vector<std::vector<ConvLayout>> bconv;   // per block, loader order (HostBlock::convs; a Mixer's depthwise conv is in bdw)
+    std::vector<DwLayout> bdw;                    // per block: Mixer depthwise filters (k == 0 otherwise)
+    DwLayout p_dw;                                // RepLK policy head (k == 0 for the Normal head)
+    ConvLayout p_pt;
     std::vector<FcLayout> squeeze, excite;  // per block (unused entries when se_size == 0)
     ConvLayout head;                        // policy + value head-entry 1x1 convs as one single-tap conv, cout = P + V
     FcLayout p_inter, pass, v_inter, misc;
@@ -147,14 +154,29 @@ static ConvLayout LayConv(size_t& cur, int cin, int cout, int taps = 9) {
     c.cin = cin;
     c.cinp = RoundUp(cin, 64);
     c.cout = cout;
+    c.coutp = RoundUp(cout, 16);   // weight rows are zero-padded to the UMMA N granule; the epilogue stores only cout
     c.kh = c.cinp / 64;
-    c.bn = cout <= 128 ? cout : cout / 2;
-    c.ntiles = cout / c.bn;
-    const size_t mat = (size_t)cout * taps * c.cinp * sizeof(__half);
+    c.bn = 16;
+    for (int bn = 128; bn >= 16; bn -= 16) {   // widest N tile (multiple of 16, <= 128) that divides the width
+        if (c.coutp % bn == 0) {
+            c.bn = bn;
+            break;
+        }
+    }
+    c.ntiles = c.coutp / c.bn;
+    const size_t mat = (size_t)c.coutp * taps * c.cinp * sizeof(__half);
     c.w_hi = Take(cur, mat);
     c.w_lo = Take(cur, mat);
-    c.bias = Take(cur, (size_t)cout * sizeof(float));
+    c.bias = Take(cur, (size_t)c.coutp * sizeof(float));
     return c;
+}
+static DwLayout LayDw(size_t& cur, int ch, int k) {
+    DwLayout d;
+    d.ch = ch;
+    d.k = k;
+    d.w = Take(cur, (size_t)ch * k * k * sizeof(float));
+    d.b = Take(cur, (size_t)ch * sizeof(float));
+    return d;
 }
 static FcLayout LayFc(size_t& cur, int in, int out) {
     FcLayout f;
@@ -166,16 +188,20 @@ static FcLayout LayFc(size_t& cur, int in, int out) {
 }
 
 static BlobLayout ComputeLayout(int blocks, int C, int P, int V, const std::vector<int>& se, const std::vector<int>& types,
-                                const std::vector<int>& inner) {
+                                const std::vector<int>& inner, const std::vector<int>& dwk, int replk_kernel) {
     BlobLayout L;
     size_t cur = 0;
     L.input = LayConv(cur, SB_INPUT_CHANNELS, C);
     L.bconv.resize(blocks);
+    L.bdw.resize(blocks);
     L.squeeze.resize(blocks);
     L.excite.resize(blocks);
     for (int b = 0; b < blocks; ++b) {
         if (types[b] == SB_BLOCK_RESIDUAL) {
             L.bconv[b] = {LayConv(cur, C, C), LayConv(cur, C, C)};
+        } else if (types[b] == SB_BLOCK_MIXER) {   // depthwise k x k, 1x1 C -> F, 1x1 F -> C
+            L.bdw[b] = LayDw(cur, C, dwk[b]);
+            L.bconv[b] = {LayConv(cur, C, inner[b], 1), LayConv(cur, inner[b], C, 1)};
         } else {   // pre 1x1, 2 or 4 inner 3x3, post 1x1
             const int I = inner[b], n3 = types[b] == SB_BLOCK_BOTTLENECK ? 2 : 4;
             L.bconv[b].push_back(LayConv(cur, C, I, 1));
@@ -188,6 +214,10 @@ static BlobLayout ComputeLayout(int blocks, int C, int P, int V, const std::vect
         }
     }
     L.head = LayConv(cur, C, P + V, 1);
+    if (replk_kernel > 0) {
+        L.p_dw = LayDw(cur, P, replk_kernel);
+        L.p_pt = LayConv(cur, P, P, 1);
+    }
     L.p_inter = LayFc(cur, 3 * P, P);
     L.pass = LayFc(cur, P, 5);
     L.v_inter = LayFc(cur, 3 * V, 3 * V);
@@ -219,6 +249,10 @@ static void PackConv(const HostConv& hc, const ConvLayout& L, uint8_t* blob) {
     }
     std::memcpy(blob + L.bias, hc.b.data(), (size_t)L.cout * sizeof(float));
 }
+static void PackDw(const HostConv& hc, const DwLayout& L, uint8_t* blob) {
+    std::memcpy(blob + L.w, hc.w.data(), hc.w.size() * sizeof(float));
+    std::memcpy(blob + L.b, hc.b.data(), hc.b.size() * sizeof(float));
+}
 static void PackFc(const HostFC& f, const FcLayout& L, uint8_t* blob) {
     std::memcpy(blob + L.w, f.w.data(), f.w.size() * sizeof(float));
     std::memcpy(blob + L.b, f.b.data(), f.b.size() * sizeof(float));
@@ -229,7 +263,9 @@ static std::vector<uint8_t> PackBlob(const HostNet& n, const BlobLayout& L) {
     uint8_t* p = blob.data();
     PackConv(n.input_conv, L.input, p);
     for (int b = 0; b < n.blocks; ++b) {
-        for (size_t q = 0; q < n.tower[b].convs.size(); ++q) PackConv(n.tower[b].convs[q], L.bconv[b][q], p);
+        const bool mixer = n.tower[b].type == SB_BLOCK_MIXER;
+        if (mixer) PackDw(n.tower[b].convs[0], L.bdw[b], p);
+        for (size_t q = mixer ? 1 : 0; q < n.tower[b].convs.size(); ++q) PackConv(n.tower[b].convs[q], L.bconv[b][q - (mixer ? 1 : 0)], p);
         if (n.tower[b].se_size > 0) {
             PackFc(n.tower[b].squeeze, L.squeeze[b], p);
             PackFc(n.tower[b].excite, L.excite[b], p);
@@ -246,6 +282,10 @@ static std::vector<uint8_t> PackBlob(const HostNet& n, const BlobLayout& L) {
         head.b = n.p_hd_conv.b;
         head.b.insert(head.b.end(), n.v_hd_conv.b.begin(), n.v_hd_conv.b.end());
         PackConv(head, L.head, p);
+    }
+    if (n.replk) {
+        PackDw(n.p_dw_conv, L.p_dw, p);
+        PackConv(n.p_pt_conv, L.p_pt, p);
     }
     PackFc(n.p_inter_fc, L.p_inter, p);
     PackFc(n.pass_fc, L.pass, p);
@@ -282,7 +322,8 @@ struct Slot {
     float* d_out = nullptr;    // [max_batch][kOutFloats]
     float* h_out = nullptr;    // pinned
     ActBuf in, x, t, u;
-    ActBuf ia, ib, ic;         // bottleneck-width buffers (allocated only when the tower has bottleneck blocks)
+    ActBuf ia, ib, ic;         // bottleneck / feed-forward width buffers (allocated only when the tower needs them)
+    ActBuf pq;                 // RepLK policy head: depthwise output (P channels, padded to 64)
     ActBuf* trunk = nullptr;   // which buffer holds the tower output after the last forward
     uint8_t* mask = nullptr;
     float* gb = nullptr;       // [max_batch][2C]
@@ -313,7 +354,7 @@ struct DevConv {
 struct Replica {
     int device = -1;
     uint8_t* blob = nullptr;
-    DevConv input, head;
+    DevConv input, head, p_pt;
     std::vector<std::vector<DevConv>> bconv;   // per block, loader order
     std::vector<Slot> slots;
     std::vector<Slot> bslots;     // the batcher's own slots (sb_eval), allocated when its workers start
@@ -370,7 +411,9 @@ struct sb_engine {
     HostNet net_shape;  // scalar fields + se sizes only (tensors dropped after packing)
     std::vector<int> se_sizes;
     std::vector<int> block_types;      // SB_BLOCK_* per block
-    std::vector<int> inner_channels;   // bottleneck width per block (0 for plain residual blocks)
+    std::vector<int> inner_channels;   // bottleneck / feed-forward width per block (0 for plain residual blocks)
+    std::vector<int> dw_kernels;       // Mixer depthwise filter size per block (0 otherwise)
+    int replk_kernel = 0;              // RepLK policy head depthwise filter size (0 = Normal head)
     BlobLayout layout;
     std::vector<Replica> replicas;
     Geom geom;
@@ -422,7 +465,7 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.d_packed);
     cudaFree(s.d_out);
     cudaFreeHost(s.h_out);
-    for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u, &s.pv, &s.ia, &s.ib, &s.ic}) {
+    for (ActBuf* a : {&s.in, &s.x, &s.t, &s.u, &s.pv, &s.ia, &s.ib, &s.ic, &s.pq}) {
         if (!a->hi) continue;
         if (a->lo != a->hi) cudaFree(a->lo);   // single-pass fp16 mode aliases lo to hi
         cudaFree(a->hi);
@@ -493,6 +536,7 @@ static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int
             AllocAct(s.ib, rows, Ip, split);
             AllocAct(s.ic, rows, Ip, split);
         }
+        if (e->replk_kernel > 0) AllocAct(s.pq, rows, 64, split);
         SB_CUDA(cudaMalloc(&s.mask, (size_t)rows));
         SB_CUDA(cudaMemset(s.mask, 0, (size_t)rows));
         SB_CUDA(cudaMalloc(&s.gb, (size_t)e->max_batch * 2 * C * sizeof(float)));
@@ -517,14 +561,14 @@ static void AllocSlots(sb_engine* e, Replica& r) { AllocSlotVec(e, r, r.slots, e
 
 static void MakeConvMaps(const Replica& r, DevConv& c) {
     const int K = c.L.taps * c.L.cinp;
-    c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, c.L.bn);
-    c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, c.L.bn);
+    c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.coutp, K, c.L.bn);
+    c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.coutp, K, c.L.bn);
     c.levels = 0;
     for (int lv = 0; lv < 4; ++lv) {
         const int bn = c.L.bn >> lv;
         if (bn < 16 || bn % 16 || (bn << lv) != c.L.bn) break;    // UMMA N (M = 256) must be a multiple of 16
-        c.tm2_hi[lv] = MakeMap2D(r.blob + c.L.w_hi, c.L.cout, K, bn / 2);
-        c.tm2_lo[lv] = MakeMap2D(r.blob + c.L.w_lo, c.L.cout, K, bn / 2);
+        c.tm2_hi[lv] = MakeMap2D(r.blob + c.L.w_hi, c.L.coutp, K, bn / 2);
+        c.tm2_lo[lv] = MakeMap2D(r.blob + c.L.w_lo, c.L.coutp, K, bn / 2);
         c.levels = lv + 1;
     }
     for (int lv = c.levels; lv < 4; ++lv) {
@@ -563,6 +607,10 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     MakeConvMaps(r, r.input);
     r.head.L = e->layout.head;
     MakeConvMaps(r, r.head);
+    if (e->layout.p_dw.k > 0) {
+        r.p_pt.L = e->layout.p_pt;
+        MakeConvMaps(r, r.p_pt);
+    }
     r.bconv.resize(blocks);
     for (int b = 0; b < blocks; ++b) {
         r.bconv[b].resize(e->layout.bconv[b].size());
@@ -574,6 +622,7 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     if (blob && e->precision == SB_PRECISION_SIMT_DEBUG) {
         MakeSimtWeights(e, r, r.input, *blob);
         MakeSimtWeights(e, r, r.head, *blob);
+        if (e->layout.p_dw.k > 0) MakeSimtWeights(e, r, r.p_pt, *blob);
         for (int b = 0; b < blocks; ++b) {
             for (auto& c : r.bconv[b]) MakeSimtWeights(e, r, c, *blob);
         }
@@ -601,6 +650,7 @@ static void DestroyReplica(Replica& r) {
     };
     free_conv(r.input);
     free_conv(r.head);
+    free_conv(r.p_pt);
     for (auto& blk : r.bconv)
         for (auto& c : blk) free_conv(c);
     cudaFree(r.blob);
@@ -665,10 +715,10 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
             int level = 0;
             const int max_pairs = r.sm_count / 2;
             while (e->small_batch_split && level + 1 < c.levels && level < 2 &&
-                   n_super * (c.L.cout / (c.L.bn >> (level + 1))) <= max_pairs)
+                   n_super * (c.L.coutp / (c.L.bn >> (level + 1))) <= max_pairs)
                 ++level;
             p.bn = c.L.bn >> level;
-            p.n_ntiles = c.L.cout / p.bn;
+            p.n_ntiles = c.L.coutp / p.bn;
             const int items2 = n_super * p.n_ntiles;
             // fp16 rung, one N tile, <= 18 weight stages per item: weights stay resident in shared memory
             p.resident = (e->resident_weights && !Split(e) && p.n_ntiles == 1 && c.L.kh * c.L.taps <= Conv2Cfg<false>::kNumBStages &&
@@ -723,6 +773,17 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
     }
 }
 
+static void LaunchDw(sb_engine* e, Slot& s, const DwLayout& d, const uint8_t* blob, const ActBuf& in, ActBuf& out, int act,
+                     bool add_input, int n, int n_rows) {
+    const dim3 grid((n_rows + 127) / 128, d.ch / 8);
+    const float* w = reinterpret_cast<const float*>(blob + d.w);
+    const float* b = reinterpret_cast<const float*>(blob + d.b);
+    SB_DISPATCH_ACT(act, ACT, (dwconv_kernel<ACT><<<grid, 128, 0, s.stream>>>(in.hi, in.lo, out.hi, out.lo, Split(e), w, b, s.d_meta,
+                                                                              e->geom, n, n_rows, in.rows, out.rows, d.k, add_input)));
+    SB_CUDA(cudaGetLastError());
+    e->launches++;
+}
+
 // Everything between "inputs are in d_in / d_meta" and "outputs are in d_out", on the slot's stream.
 static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* tm = nullptr) {
     const HostNet& ns = e->net_shape;
@@ -760,7 +821,14 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         // added by se_apply (blas_forward_pipe.cc:73-87,147-161,249-262)
         const ActBuf* last_res = se > 0 ? nullptr : x;
         const int last_act = se > 0 ? kIdentity : act;
-        if (e->block_types[b] == SB_BLOCK_RESIDUAL) {
+        const ActBuf* se_skip = x;
+        if (e->block_types[b] == SB_BLOCK_MIXER) {
+            // MixerBlockForward, blas_forward_pipe.cc:265-312: y = act(dw(x) + b) + x ; out = ffn2(act(ffn1(y))) (+ y)
+            LaunchDw(e, s, L.bdw[b], r.blob, *x, *t, act, true, n, n_rows);
+            LaunchConv(e, r, s, cv[0], *t, s.ia, nullptr, act, n, tm);
+            LaunchConv(e, r, s, cv[1], s.ia, *u, se > 0 ? nullptr : t, last_act, n, tm);
+            se_skip = t;   // the skip of this block and of its SE unit is y
+        } else if (e->block_types[b] == SB_BLOCK_RESIDUAL) {
             // ResidualBlockForward, blas_forward_pipe.cc:46-88
             LaunchConv(e, r, s, cv[0], *x, *t, nullptr, act, n, tm);
             LaunchConv(e, r, s, cv[1], *t, *u, last_res, last_act, n, tm);
@@ -787,7 +855,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
             SB_CUDA(cudaGetLastError());
             const size_t total = (size_t)n_rows * (C / 8);
             SB_DISPATCH_ACT(act, ACT, (se_apply_kernel<ACT><<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(
-                                          u->hi, u->lo, x->hi, x->lo, split, s.mask, s.gb, g, C, u->rows, n_rows)));
+                                          u->hi, u->lo, se_skip->hi, se_skip->lo, split, s.mask, s.gb, g, C, u->rows, n_rows)));
             SB_CUDA(cudaGetLastError());
             e->launches += 2;
         }
@@ -796,6 +864,12 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     s.trunk = x;
     // heads: the two head-entry 1x1 convs as one single-tap tensor-core launch
     LaunchConv(e, r, s, r.head, *x, s.pv, nullptr, act, n, nullptr);
+    if (e->replk_kernel > 0) {
+        // RepLK policy head, blas_forward_pipe.cc:443-471: depthwise k x k (+bias, act) on the P policy channels, then a
+        // 1x1 P -> P (+bias, act) written back over the policy channels of pv (the V value channels stay untouched)
+        LaunchDw(e, s, L.p_dw, r.blob, s.pv, s.pq, act, false, n, n_rows);
+        LaunchConv(e, r, s, r.p_pt, s.pq, s.pv, nullptr, act, n, nullptr);
+    }
     HeadWeights hw;
     hw.p_inter_w = F(L.p_inter.w);
     hw.p_inter_b = F(L.p_inter.b);
@@ -894,6 +968,8 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
         e->se_sizes = net->se_sizes();
         e->block_types = net->block_types();
         e->inner_channels = net->inner_channels();
+        e->dw_kernels = net->dw_kernels();
+        e->replk_kernel = net->replk ? net->p_dw_conv.k : 0;
     } else {
         e->net_shape.version = shape_only->version;
         e->net_shape.input_channels = shape_only->input_channels;
@@ -905,15 +981,29 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
         e->se_sizes.assign(shape_only->se_sizes, shape_only->se_sizes + shape_only->blocks);
         e->block_types.assign(shape_only->blocks, SB_BLOCK_RESIDUAL);
         e->inner_channels.assign(shape_only->blocks, 0);
+        e->dw_kernels.assign(shape_only->blocks, 0);
         for (int b = 0; b < shape_only->blocks; ++b) {
             if (shape_only->block_types) e->block_types[b] = shape_only->block_types[b];
             const int ty = e->block_types[b];
-            if (ty < SB_BLOCK_RESIDUAL || ty > SB_BLOCK_NESTED_BOTTLENECK) return Fail(nullptr, SB_ERR_INVALID, "unsupported block type");
+            if (ty < SB_BLOCK_RESIDUAL || ty > SB_BLOCK_MIXER) return Fail(nullptr, SB_ERR_INVALID, "unsupported block type");
             if (ty != SB_BLOCK_RESIDUAL) {
                 const int I = shape_only->inner_channels ? shape_only->inner_channels[b] : 0;
-                if (I < 16 || I > 256 || I % 16 || (I > 128 && I % 32)) return Fail(nullptr, SB_ERR_INVALID, "unsupported bottleneck width");
+                bool tiles = false;
+                for (int bn = 128; bn >= 16; bn -= 16) tiles = tiles || (I >= 16 && I <= 256 && I % 16 == 0 && I % bn == 0);
+                if (!tiles) return Fail(nullptr, SB_ERR_INVALID, "unsupported bottleneck / feed-forward width");
                 e->inner_channels[b] = I;
             }
+            if (ty == SB_BLOCK_MIXER) {
+                const int kk = shape_only->dw_kernels ? shape_only->dw_kernels[b] : 7;
+                if (kk < 3 || kk > 15 || !(kk & 1)) return Fail(nullptr, SB_ERR_INVALID, "unsupported depthwise kernel size");
+                e->dw_kernels[b] = kk;
+            }
+        }
+        if (shape_only->policy_head_type == SB_POLICY_HEAD_REPLK) {
+            e->replk_kernel = shape_only->policy_dw_kernel > 0 ? shape_only->policy_dw_kernel : 7;
+            if (e->replk_kernel < 3 || e->replk_kernel > 15 || !(e->replk_kernel & 1)) return Fail(nullptr, SB_ERR_INVALID, "unsupported depthwise kernel size");
+        } else if (shape_only->policy_head_type != SB_POLICY_HEAD_NORMAL) {
+            return Fail(nullptr, SB_ERR_INVALID, "unsupported policy head type");
         }
         const int C = e->net_shape.channels, PV = e->net_shape.P + e->net_shape.V;
         if (C < 16 || C > 256 || C % 16 || (C > 128 && C % 32) || PV % 4 || PV > 64 || e->net_shape.input_channels != SB_INPUT_CHANNELS)
@@ -926,7 +1016,7 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
         if (e->net_shape.channels % 8) return Fail(nullptr, SB_ERR_INVALID, "channels must be a multiple of 8");
     }
     e->layout = ComputeLayout(e->net_shape.blocks, e->net_shape.channels, e->net_shape.P, e->net_shape.V, e->se_sizes,
-                              e->block_types, e->inner_channels);
+                              e->block_types, e->inner_channels, e->dw_kernels, e->replk_kernel);
     try {
         std::vector<uint8_t> blob;
         if (net) blob = PackBlob(*net, e->layout);
@@ -1360,7 +1450,8 @@ static int ReloadImpl(sb_engine* e, HostNet& net) {
     StopBatcher(e);
     if (net.blocks != e->net_shape.blocks || net.channels != e->net_shape.channels || net.P != e->net_shape.P ||
         net.V != e->net_shape.V || net.se_sizes() != e->se_sizes || net.block_types() != e->block_types ||
-        net.inner_channels() != e->inner_channels)
+        net.inner_channels() != e->inner_channels || net.dw_kernels() != e->dw_kernels ||
+        (net.replk ? net.p_dw_conv.k : 0) != e->replk_kernel)
         return Fail(e, SB_ERR_INVALID, "reload requires the same architecture; destroy and create for a new one");
     try {
         e->net_shape.act = net.act;
@@ -1425,10 +1516,22 @@ int sb_get_net_desc(const sb_engine* e, sb_net_desc* d, int* se_sizes, int se_ca
     d->se_sizes = se_sizes;
     d->block_types = nullptr;
     d->inner_channels = nullptr;
+    d->dw_kernels = nullptr;
+    d->policy_head_type = e->replk_kernel > 0 ? SB_POLICY_HEAD_REPLK : SB_POLICY_HEAD_NORMAL;
+    d->policy_dw_kernel = e->replk_kernel;
     if (se_sizes) {
         if (se_capacity < e->net_shape.blocks) return SB_ERR_INVALID;
         for (int b = 0; b < e->net_shape.blocks; ++b) se_sizes[b] = e->se_sizes[b];
     }
+    return SB_OK;
+}
+
+int sb_get_dw_desc(const sb_engine* e, int* dw_kernels, int capacity, int* policy_head_type, int* policy_dw_kernel) {
+    if (!e || (dw_kernels && capacity < e->net_shape.blocks)) return SB_ERR_INVALID;
+    if (dw_kernels)
+        for (int b = 0; b < e->net_shape.blocks; ++b) dw_kernels[b] = e->dw_kernels[b];
+    if (policy_head_type) *policy_head_type = e->replk_kernel > 0 ? SB_POLICY_HEAD_REPLK : SB_POLICY_HEAD_NORMAL;
+    if (policy_dw_kernel) *policy_dw_kernel = e->replk_kernel;
     return SB_OK;
 }
 

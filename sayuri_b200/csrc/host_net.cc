@@ -95,10 +95,15 @@ int ActFromName(const std::string& name) {  // activation.h:19-41
 }
 
 void ReadConv(Reader& r, const Shape& s, HostConv& c) {
-    if (s.kind != 'C') throw std::runtime_error("expected a Convolution layer in the struct list");
+    if (s.kind != 'C' && s.kind != 'D') throw std::runtime_error("expected a Convolution layer in the struct list");
     c.in = s.d[0];
     c.out = s.d[1];
     c.k = s.d[2];
+    c.depthwise = s.kind == 'D';
+    if (c.depthwise) {   // "DepthwiseConvolution 1 C k" (network.py writer)
+        if (c.in != 1 && c.in != c.out) throw std::runtime_error("depthwise convolution shape is wrong");
+        c.in = 1;
+    }
     c.w = r.Tensor(static_cast<size_t>(c.in) * c.out * c.k * c.k);
     c.b = r.Tensor(static_cast<size_t>(c.out));
 }
@@ -110,7 +115,7 @@ void ReadConvBn(Reader& r, const Shape* s, HostConv& c, bool v1) {
     if (s[1].kind != 'B' || s[1].d[0] != c.out) throw std::runtime_error("expected BatchNorm after Convolution");
     std::vector<float> mean = r.Tensor(static_cast<size_t>(c.out));
     std::vector<float> sd = r.Tensor(static_cast<size_t>(c.out));
-    const size_t stride = static_cast<size_t>(c.in) * c.k * c.k;
+    const size_t stride = static_cast<size_t>(c.in) * c.k * c.k;   // k*k for a depthwise layer (in == 1)
     for (int o = 0; o < c.out; ++o) {
         const float scale = v1 ? 1.0f / std::sqrt(sd[o] + 1e-5f) : 1.0f / sd[o];
         c.b[o] -= mean[o];
@@ -184,8 +189,11 @@ void Parse(Reader& r, HostNet& net) {
     net.input_channels = SB_INPUT_CHANNELS;
     if (get("InputChannels").empty() || std::stoi(get("InputChannels")) != net.input_channels)
         throw std::runtime_error("the number of input channels is wrong");
-    if (!get("PolicyHeadType").empty() && Lower(get("PolicyHeadType")) != "normal")
-        throw std::runtime_error("policy head type '" + get("PolicyHeadType") + "' is not supported by sayuri_b200 (Normal only)");
+    if (!get("PolicyHeadType").empty()) {   // loader.cc:245-259
+        const std::string t = Lower(get("PolicyHeadType"));
+        if (t == "replk") net.replk = true;
+        else if (t != "normal") throw std::runtime_error("policy head type '" + get("PolicyHeadType") + "' is not supported by sayuri_b200");
+    }
     net.act = get("ActivationFunction").empty() ? 1 /* relu, loader.cc:261-265 */ : ActFromName(get("ActivationFunction"));
     if (get("ResidualBlocks").empty() || get("ResidualChannels").empty()) throw std::runtime_error("missing ResidualBlocks/ResidualChannels");
     net.blocks = std::stoi(get("ResidualBlocks"));
@@ -233,8 +241,9 @@ void Parse(Reader& r, HostNet& net) {
         if (name == "ResidualBlock") blk.type = SB_BLOCK_RESIDUAL;
         else if (name == "BottleneckBlock") blk.type = SB_BLOCK_BOTTLENECK;
         else if (name == "NestedBottleneckBlock") blk.type = SB_BLOCK_NESTED_BOTTLENECK;
+        else if (name == "MixerBlock") blk.type = SB_BLOCK_MIXER;
         else
-            throw std::runtime_error("block type '" + name + "' is not supported by sayuri_b200 (ResidualBlock, BottleneckBlock, NestedBottleneckBlock [-SE] only)");
+            throw std::runtime_error("block type '" + name + "' is not supported by sayuri_b200");
         const int nc = HostBlock::NumConvs(blk.type);
         need(static_cast<size_t>(2 * nc));
         blk.convs.resize(static_cast<size_t>(nc));
@@ -242,7 +251,7 @@ void Parse(Reader& r, HostNet& net) {
             ReadConvBn(r, &shapes[off], blk.convs[static_cast<size_t>(q)], v1);
             off += 2;
         }
-        blk.inner = blk.type == SB_BLOCK_RESIDUAL ? 0 : blk.convs[0].out;
+        blk.inner = blk.type == SB_BLOCK_RESIDUAL ? 0 : blk.type == SB_BLOCK_MIXER ? blk.convs[1].out : blk.convs[0].out;
         if (se) {
             need(2);
             ReadFC(r, shapes[off++], blk.squeeze);
@@ -250,9 +259,15 @@ void Parse(Reader& r, HostNet& net) {
             blk.se_size = blk.squeeze.out;
         }
     }
-    need(10);
+    need(net.replk ? 14 : 10);
     ReadConvBn(r, &shapes[off], net.p_hd_conv, v1);
     off += 2;
+    if (net.replk) {   // loader.cc:691-702
+        ReadConvBn(r, &shapes[off], net.p_dw_conv, v1);
+        off += 2;
+        ReadConvBn(r, &shapes[off], net.p_pt_conv, v1);
+        off += 2;
+    }
     ReadFC(r, shapes[off++], net.p_inter_fc);
     ReadConv(r, shapes[off++], net.prob_conv);
     ReadFC(r, shapes[off++], net.pass_fc);
@@ -270,8 +285,18 @@ void Parse(Reader& r, HostNet& net) {
 
 bool ValidateNet(const HostNet& n, std::string& err) {
     auto conv_ok = [](const HostConv& c, int in, int out, int k) {
-        return c.in == in && c.out == out && c.k == k && c.w.size() == static_cast<size_t>(in) * out * k * k &&
+        return !c.depthwise && c.in == in && c.out == out && c.k == k && c.w.size() == static_cast<size_t>(in) * out * k * k &&
                c.b.size() == static_cast<size_t>(out);
+    };
+    auto dw_ok = [](const HostConv& c, int ch) {
+        return c.depthwise && c.in == 1 && c.out == ch && c.k >= 3 && c.k <= 15 && (c.k & 1) &&
+               c.w.size() == static_cast<size_t>(ch) * c.k * c.k && c.b.size() == static_cast<size_t>(ch);
+    };
+    auto width_ok = [](int w) {   // a conv output width the tensor-core kernel can tile: N tiles of a multiple of 16, <= 128
+        if (w < 16 || w > 256 || w % 16 != 0) return false;
+        for (int bn = 128; bn >= 16; bn -= 16)
+            if (w % bn == 0) return true;
+        return false;
     };
     auto fc_ok = [](const HostFC& f, int in, int out) {
         return f.in == in && f.out == out && f.w.size() == static_cast<size_t>(in) * out && f.b.size() == static_cast<size_t>(out);
@@ -281,18 +306,22 @@ bool ValidateNet(const HostNet& n, std::string& err) {
     if (n.input_channels != SB_INPUT_CHANNELS) { err = "the number of input channels is wrong"; return false; }
     if (n.act < 0 || n.act > 7) { err = "Unknown activation type."; return false; }
     if (C < 16 || C > 256 || C % 16 != 0) { err = "residual channels must be a multiple of 16 in [16, 256]"; return false; }
-    if (C > 128 && C % 32 != 0) { err = "residual channels above 128 must be a multiple of 32"; return false; }
+    if (!width_ok(C)) { err = "residual channels above 128 must tile into N <= 128 (multiple of 16)"; return false; }
     if (P < 4 || V < 4 || (P + V) % 4 != 0 || P + V > 64) { err = "policy + value head channels must be a multiple of 4 and <= 64"; return false; }
     if (n.blocks < 0 || static_cast<int>(n.tower.size()) != n.blocks) { err = "tower size mismatch"; return false; }
     if (!conv_ok(n.input_conv, SB_INPUT_CHANNELS, C, 3)) { err = "the input layers are wrong"; return false; }
     for (int b = 0; b < n.blocks; ++b) {
         const HostBlock& k = n.tower[static_cast<size_t>(b)];
-        if (k.type < SB_BLOCK_RESIDUAL || k.type > SB_BLOCK_NESTED_BOTTLENECK || static_cast<int>(k.convs.size()) != HostBlock::NumConvs(k.type)) { err = "block " + std::to_string(b + 1) + " has an unsupported type"; return false; }
+        if (k.type < SB_BLOCK_RESIDUAL || k.type > SB_BLOCK_MIXER || static_cast<int>(k.convs.size()) != HostBlock::NumConvs(k.type)) { err = "block " + std::to_string(b + 1) + " has an unsupported type"; return false; }
         if (k.type == SB_BLOCK_RESIDUAL) {
             if (!conv_ok(k.convs[0], C, C, 3) || !conv_ok(k.convs[1], C, C, 3)) { err = "residual block " + std::to_string(b + 1) + " is wrong"; return false; }
+        } else if (k.type == SB_BLOCK_MIXER) {
+            const int F = k.inner;
+            if (!width_ok(F)) { err = "feed-forward channels of mixer block " + std::to_string(b + 1) + " (" + std::to_string(F) + ") cannot be tiled: need a multiple of 16 <= 256 with a divisor <= 128 that is a multiple of 16"; return false; }
+            if (!dw_ok(k.convs[0], C) || !conv_ok(k.convs[1], C, F, 1) || !conv_ok(k.convs[2], F, C, 1)) { err = "the channels of mixer block " + std::to_string(b + 1) + " is wrong"; return false; }
         } else {
             const int I = k.inner;
-            if (I < 16 || I > 256 || I % 16 != 0 || (I > 128 && I % 32 != 0)) { err = "bottleneck channels must be a multiple of 16 in [16, 256] (of 32 above 128)"; return false; }
+            if (!width_ok(I)) { err = "bottleneck channels must be a multiple of 16 in [16, 256] that tiles into N <= 128"; return false; }
             const size_t last = k.convs.size() - 1;
             if (!conv_ok(k.convs[0], C, I, 1) || !conv_ok(k.convs[last], I, C, 1)) { err = "the outer channels of bottleneck block " + std::to_string(b + 1) + " is wrong"; return false; }
             for (size_t q = 1; q < last; ++q)
@@ -300,6 +329,7 @@ bool ValidateNet(const HostNet& n, std::string& err) {
         }
         if (k.se_size > 0 && (!fc_ok(k.squeeze, 3 * C, k.se_size) || !fc_ok(k.excite, k.se_size, 2 * C))) { err = "SE unit of block " + std::to_string(b + 1) + " is wrong"; return false; }
     }
+    if (n.replk && (P % 8 != 0 || !dw_ok(n.p_dw_conv, P) || !conv_ok(n.p_pt_conv, P, P, 1))) { err = "the RepLK policy head is wrong"; return false; }
     if (!conv_ok(n.p_hd_conv, C, P, 1) || !fc_ok(n.p_inter_fc, 3 * P, P) || !conv_ok(n.prob_conv, P, 5, 1) || !fc_ok(n.pass_fc, P, 5)) { err = "the policy head is wrong"; return false; }
     if (!conv_ok(n.v_hd_conv, C, V, 1) || !fc_ok(n.v_inter_fc, 3 * V, 3 * V) || !conv_ok(n.v_ownership, V, 1, 1) || !fc_ok(n.v_misc, 3 * V, 15)) { err = "the value head is wrong"; return false; }
     return true;
@@ -352,6 +382,11 @@ bool NetFromAbi(const sb_net_desc* d, const sb_weights* w, HostNet& net, std::st
         take(c.w, static_cast<size_t>(in) * out * k * k);
         take(c.b, static_cast<size_t>(out));
     };
+    auto dwconv = [&](HostConv& c, int ch, int k) {
+        c.in = 1; c.out = ch; c.k = k; c.depthwise = true;
+        take(c.w, static_cast<size_t>(ch) * k * k);
+        take(c.b, static_cast<size_t>(ch));
+    };
     auto fc = [&](HostFC& f, int in, int out) {
         f.in = in; f.out = out;
         take(f.w, static_cast<size_t>(in) * out);
@@ -363,13 +398,19 @@ bool NetFromAbi(const sb_net_desc* d, const sb_weights* w, HostNet& net, std::st
     for (int b = 0; b < net.blocks; ++b) {
         HostBlock& k = net.tower[static_cast<size_t>(b)];
         k.type = d->block_types ? d->block_types[b] : SB_BLOCK_RESIDUAL;
-        if (k.type < SB_BLOCK_RESIDUAL || k.type > SB_BLOCK_NESTED_BOTTLENECK) { err = "unsupported block type in the net description"; return false; }
+        if (k.type < SB_BLOCK_RESIDUAL || k.type > SB_BLOCK_MIXER) { err = "unsupported block type in the net description"; return false; }
         k.inner = k.type == SB_BLOCK_RESIDUAL ? 0 : (d->inner_channels ? d->inner_channels[b] : 0);
-        if (k.type != SB_BLOCK_RESIDUAL && k.inner <= 0) { err = "bottleneck block without inner_channels"; return false; }
+        if (k.type != SB_BLOCK_RESIDUAL && k.inner <= 0) { err = "bottleneck / mixer block without inner_channels"; return false; }
         k.convs.resize(static_cast<size_t>(HostBlock::NumConvs(k.type)));
         if (k.type == SB_BLOCK_RESIDUAL) {
             conv(k.convs[0], C, C, 3);
             conv(k.convs[1], C, C, 3);
+        } else if (k.type == SB_BLOCK_MIXER) {
+            const int kk = d->dw_kernels ? d->dw_kernels[b] : 7;
+            if (kk < 3 || kk > 15 || !(kk & 1)) { err = "unsupported depthwise kernel size"; return false; }
+            dwconv(k.convs[0], C, kk);
+            conv(k.convs[1], C, k.inner, 1);
+            conv(k.convs[2], k.inner, C, 1);
         } else {
             const size_t last = k.convs.size() - 1;
             conv(k.convs[0], C, k.inner, 1);
@@ -383,6 +424,14 @@ bool NetFromAbi(const sb_net_desc* d, const sb_weights* w, HostNet& net, std::st
         }
     }
     conv(net.p_hd_conv, C, P, 1);
+    net.replk = d->policy_head_type == SB_POLICY_HEAD_REPLK;
+    if (d->policy_head_type != SB_POLICY_HEAD_NORMAL && !net.replk) { err = "unsupported policy head type"; return false; }
+    if (net.replk) {
+        const int kk = d->policy_dw_kernel > 0 ? d->policy_dw_kernel : 7;
+        if (kk < 3 || kk > 15 || !(kk & 1)) { err = "unsupported depthwise kernel size"; return false; }
+        dwconv(net.p_dw_conv, P, kk);
+        conv(net.p_pt_conv, P, P, 1);
+    }
     fc(net.p_inter_fc, 3 * P, P);
     conv(net.prob_conv, P, 5, 1);
     fc(net.pass_fc, P, 5);

@@ -141,10 +141,9 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
     }
 
     DNNWeights& w = *weights_;
-    if (w.policy_head_type != PolicyHeadType::kNormal) {
-        throw std::runtime_error("sayuri_b200: RepLK policy head is not supported");
-    }
-    std::vector<int> se(w.residual_blocks, 0), types(w.residual_blocks, SB_BLOCK_RESIDUAL), inner(w.residual_blocks, 0);
+    const bool replk = w.policy_head_type == PolicyHeadType::kRepLK;
+    std::vector<int> se(w.residual_blocks, 0), types(w.residual_blocks, SB_BLOCK_RESIDUAL), inner(w.residual_blocks, 0),
+        dwk(w.residual_blocks, 0);
     std::vector<sb_tensor> t;
     PushConv(t, w.input_conv);
     for (int b = 0; b < w.residual_blocks; ++b) {
@@ -164,8 +163,16 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
                 PushConv(t, blk->conv4);
             }
             PushConv(t, blk->post_btl_conv);
+        } else if (blk->IsMixerBlock()) {
+            // loader order (loader.cc:556-607): depthwise k x k, ffn1 1x1, ffn2 1x1
+            types[b] = SB_BLOCK_MIXER;
+            inner[b] = blk->feedforward_channels;
+            dwk[b] = blk->dw_conv.GetFilter();
+            PushConv(t, blk->dw_conv);
+            PushConv(t, blk->conv1);
+            PushConv(t, blk->conv2);
         } else {
-            throw std::runtime_error("sayuri_b200: MixerBlock towers are not supported");
+            throw std::runtime_error("sayuri_b200: unknown tower block type");
         }
         if (blk->apply_se) {
             se[b] = blk->se_size;
@@ -174,6 +181,10 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
         }
     }
     PushConv(t, w.p_hd_conv);
+    if (replk) {   // loader.cc:691-702
+        PushConv(t, w.p_dw_conv);
+        PushConv(t, w.p_pt_conv);
+    }
     PushFc(t, w.p_inter_fc);
     PushConv(t, w.prob_conv);
     PushFc(t, w.pass_fc);
@@ -193,6 +204,9 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
     d.se_sizes = se.data();
     d.block_types = types.data();
     d.inner_channels = inner.data();
+    d.dw_kernels = dwk.data();
+    d.policy_head_type = replk ? SB_POLICY_HEAD_REPLK : SB_POLICY_HEAD_NORMAL;
+    d.policy_dw_kernel = replk ? w.p_dw_conv.GetFilter() : 0;
     sb_weights sw{t.data(), (int)t.size()};
     const int precision = GetOption<bool>("fp16") ? SB_PRECISION_FP16 : SB_PRECISION_FP32_SPLIT;
     int rc = sb_create(&engine_, &d, &sw, gpus.empty() ? nullptr : gpus.data(), (int)gpus.size(), board_size_,

@@ -25,6 +25,9 @@ PLANE_FLOATS = INPUT_CHANNELS * MAX_INTERSECTIONS
 BLOCK_RESIDUAL = 0
 BLOCK_BOTTLENECK = 1
 BLOCK_NESTED_BOTTLENECK = 2
+BLOCK_MIXER = 3
+POLICY_HEAD_NORMAL = 0
+POLICY_HEAD_REPLK = 1
 
 PRECISION_FP32_SPLIT = 0
 PRECISION_FP16 = 1
@@ -37,7 +40,8 @@ _I = ctypes.POINTER(ctypes.c_int)
 class SbNetDesc(ctypes.Structure):
     _fields_ = [("version", ctypes.c_int), ("input_channels", ctypes.c_int), ("blocks", ctypes.c_int),
                 ("channels", ctypes.c_int), ("policy_channels", ctypes.c_int), ("value_channels", ctypes.c_int),
-                ("activation", ctypes.c_int), ("se_sizes", _I), ("block_types", _I), ("inner_channels", _I)]
+                ("activation", ctypes.c_int), ("se_sizes", _I), ("block_types", _I), ("inner_channels", _I),
+                ("dw_kernels", _I), ("policy_head_type", ctypes.c_int), ("policy_dw_kernel", ctypes.c_int)]
 
 
 class SbTensor(ctypes.Structure):
@@ -81,7 +85,7 @@ ABI_SYMBOLS = [
     "sb_forward_batch", "sb_submit", "sb_wait", "sb_host_alloc", "sb_host_free", "sb_weights_blob",
     "sb_weights_export", "sb_weights_import",
     "sb_weights_checksum", "sb_time_forward", "sb_launch_count", "sb_debug_read_trunk", "sb_conv_stats", "sb_set_option",
-    "sb_get_block_desc", "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
+    "sb_get_block_desc", "sb_get_dw_desc", "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
 ]
 
 _lib = None
@@ -111,6 +115,7 @@ def load_library():
         getattr(lib, name).argtypes = [vp]
     lib.sb_get_net_desc.argtypes = [vp, ctypes.POINTER(SbNetDesc), _I, ctypes.c_int]
     lib.sb_get_block_desc.argtypes = [vp, _I, _I, ctypes.c_int]
+    lib.sb_get_dw_desc.argtypes = [vp, _I, ctypes.c_int, _I, _I]
     lib.sb_forward_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_F), _I, _I, ctypes.c_void_p]
     lib.sb_submit.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, _I, _I]
     lib.sb_wait.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -206,8 +211,10 @@ class B200ForwardPipe:
         se = (ctypes.c_int * nb)(*desc["se_sizes"])
         types = (ctypes.c_int * nb)(*desc.get("block_types", [BLOCK_RESIDUAL] * len(desc["se_sizes"])))
         inner = (ctypes.c_int * nb)(*desc.get("inner_channels", [0] * len(desc["se_sizes"])))
+        dwk = (ctypes.c_int * nb)(*desc.get("dw_kernels", [0] * len(desc["se_sizes"])))
         d = SbNetDesc(desc.get("version", 5), INPUT_CHANNELS, desc["blocks"], desc["channels"], desc["P"], desc["V"],
-                      desc["activation"], se, types, inner)
+                      desc["activation"], se, types, inner, dwk, desc.get("policy_head_type", POLICY_HEAD_NORMAL),
+                      desc.get("policy_dw_kernel", 0))
         wptr = None
         keep = []
         if tensors is not None:
@@ -255,7 +262,12 @@ class B200ForwardPipe:
         types = (ctypes.c_int * 1024)()
         inner = (ctypes.c_int * 1024)()
         self._check(self._lib.sb_get_block_desc(self._h, types, inner, 1024))
-        return dict(version=d.version, blocks=d.blocks, channels=d.channels, P=d.policy_channels, V=d.value_channels,
+        dwk = (ctypes.c_int * 1024)()
+        pht = ctypes.c_int(0)
+        pdk = ctypes.c_int(0)
+        self._check(self._lib.sb_get_dw_desc(self._h, dwk, 1024, ctypes.byref(pht), ctypes.byref(pdk)))
+        return dict(dw_kernels=[dwk[i] for i in range(d.blocks)], policy_head_type=pht.value, policy_dw_kernel=pdk.value,
+                    version=d.version, blocks=d.blocks, channels=d.channels, P=d.policy_channels, V=d.value_channels,
                     activation=d.activation, se_sizes=[se[i] for i in range(d.blocks)],
                     block_types=[types[i] for i in range(d.blocks)], inner_channels=[inner[i] for i in range(d.blocks)])
 

@@ -25,7 +25,8 @@ def default_stack(blocks, se_every=3):
     return ["ResidualBlock-SE" if (b + 1) % se_every == 0 else "ResidualBlock" for b in range(blocks)]
 
 
-def synth_tensors(blocks, channels, P, V, seed=0, se_ratio=4, stack=None, activation="mish"):
+def synth_tensors(blocks, channels, P, V, seed=0, se_ratio=4, stack=None, activation="mish", policy_head="Normal",
+                  dw_kernel=7):
     """Random tensors in loader order (loader.cc:658-747): list of (struct_line, [tensor, tensor])."""
     rng = np.random.default_rng(seed)
     stack = stack or default_stack(blocks)
@@ -36,6 +37,11 @@ def synth_tensors(blocks, channels, P, V, seed=0, se_ratio=4, stack=None, activa
         w = rng.normal(0.0, std, size=(cout, cin, k, k)).astype(np.float32)
         b = rng.normal(0.0, 0.05, size=(cout,)).astype(np.float32)
         layers.append(("Convolution %d %d %d" % (cin, cout, k), [w, b]))
+
+    def dwconv(c, k, gain=1.2):   # "DepthwiseConvolution 1 C k", weights [C][1][k][k] (network.py writer)
+        w = rng.normal(0.0, gain / k, size=(c, 1, k, k)).astype(np.float32)
+        b = rng.normal(0.0, 0.05, size=(c,)).astype(np.float32)
+        layers.append(("DepthwiseConvolution 1 %d %d" % (c, k), [w, b]))
 
     def bn(c):
         mean = rng.normal(0.0, 0.1, size=(c,)).astype(np.float32)
@@ -65,6 +71,14 @@ def synth_tensors(blocks, channels, P, V, seed=0, se_ratio=4, stack=None, activa
                 bn(inner)
             conv(inner, channels, 1, gain=0.7)
             bn(channels)
+        elif base == "MixerBlock":   # loader.cc:556-607; ffn = 1.5 x channels like network.py:881
+            ffn = int(1.5 * channels)
+            dwconv(channels, dw_kernel)
+            bn(channels)
+            conv(channels, ffn, 1)
+            bn(ffn)
+            conv(ffn, channels, 1, gain=0.7)
+            bn(channels)
         else:
             raise ValueError("unknown block type %s" % name)
         if name.endswith("-SE"):
@@ -73,6 +87,11 @@ def synth_tensors(blocks, channels, P, V, seed=0, se_ratio=4, stack=None, activa
             fc(se, 2 * channels)
     conv(channels, P, 1)
     bn(P)
+    if policy_head == "RepLK":   # loader.cc:691-702
+        dwconv(P, dw_kernel)
+        bn(P)
+        conv(P, P, 1)
+        bn(P)
     fc(3 * P, P)
     conv(P, POLICY_OUTS, 1)
     fc(P, POLICY_OUTS)
@@ -81,7 +100,7 @@ def synth_tensors(blocks, channels, P, V, seed=0, se_ratio=4, stack=None, activa
     fc(3 * V, 3 * V)
     conv(V, 1, 1)
     fc(3 * V, VALUE_MISC)
-    info = dict(blocks=blocks, channels=channels, P=P, V=V, stack=stack, activation=activation)
+    info = dict(blocks=blocks, channels=channels, P=P, V=V, stack=stack, activation=activation, policy_head=policy_head)
     return info, layers
 
 
@@ -91,7 +110,7 @@ def write_weights(path, info, layers, binary=True, version=5):
             "FloatType %s" % ("float32bin" if binary else "float32"),
             "InputChannels %d" % INPUT_CHANNELS, "ResidualChannels %d" % info["channels"],
             "ResidualBlocks %d" % info["blocks"], "PolicyHeadChannels %d" % info["P"],
-            "ValueHeadChannels %d" % info["V"], "ValueMisc %d" % VALUE_MISC, "PolicyHeadType Normal",
+            "ValueHeadChannels %d" % info["V"], "ValueMisc %d" % VALUE_MISC, "PolicyHeadType %s" % info.get("policy_head", "Normal"),
             "ActivationFunction %s" % info["activation"], "end info", "get stack"]
     head += list(info["stack"]) + ["end stack", "get struct"]
     head += [name for name, _ in layers] + ["end struct", "get parameters"]
@@ -108,9 +127,11 @@ def write_weights(path, info, layers, binary=True, version=5):
         f.write(b"end main")
 
 
-def write_synth_net(path, name_or_shape, seed=0, binary=True, activation="mish", stack=None):
+def write_synth_net(path, name_or_shape, seed=0, binary=True, activation="mish", stack=None, policy_head="Normal",
+                    dw_kernel=7):
     shape = NETS[name_or_shape] if isinstance(name_or_shape, str) else name_or_shape
-    info, layers = synth_tensors(*shape, seed=seed, activation=activation, stack=stack)
+    info, layers = synth_tensors(*shape, seed=seed, activation=activation, stack=stack, policy_head=policy_head,
+                                 dw_kernel=dw_kernel)
     write_weights(path, info, layers, binary=binary)
     return info
 

@@ -48,3 +48,16 @@ def golden_blocks():
 @pytest.fixture(scope="session")
 def golden_blocks_weights():
     return os.path.join(GOLDEN, "ref_btl_5bx32.bin.txt")
+
+
+@pytest.fixture(scope="session")
+def golden_mixer():
+    """Third fixture: MixerBlock[-SE] tower (depthwise 7x7 / 5x5 + FFN) with the RepLK policy head, outputs of the
+    UNMODIFIED compiled reference (tests/golden/make_golden.py blocks)."""
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "golden_mix_4bx32.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_mixer_weights():
+    return os.path.join(GOLDEN, "ref_mix_4bx32.bin.txt")

@@ -50,6 +50,16 @@ CFG_BLOCKS = {
 }
 
 
+CFG_MIXER = {
+    "NeuralNetwork": {
+        "NNType": "Residual", "MaxBoardSize": 19, "ResidualChannels": 32, "PolicyHeadChannels": 8,
+        "ValueHeadChannels": 8, "SeRatio": 4, "PolicyHeadType": {"Type": "RepLK", "KernelSize": 7}, "Activation": "mish",
+        "Stack": ["MixerBlock", "MixerBlock-SE", "ResidualBlock", {"Block": "MixerBlock", "Args": {"KernelSize": 5}}],
+    },
+    "Train": {"TrainDirectory": "x", "StorePath": "x", "UseGPU": False},
+}
+
+
 def randomise_bn(net, seed):
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
@@ -64,21 +74,26 @@ def randomise_bn(net, seed):
 
 
 def main_blocks():
-    """Second fixture: the optional block families — BottleneckBlock and NestedBottleneckBlock,
+    _fixture(CFG_BLOCKS, "btl_5bx32", 20260418, 9, 21)
+    _fixture(CFG_MIXER, "mix_4bx32", 20260419, 10, 22)
+
+
+def _fixture(cfg, tag, seed, bn_seed, pos_seed):
+    """Second and third fixtures: the optional block families — BottleneckBlock and NestedBottleneckBlock,
     with and without SE (blas_forward_pipe.cc:90-263) — exported by the reference writer, evaluated by the
     UNMODIFIED compiled reference (im2col path) and cross-checked against the reference's PyTorch forward."""
-    torch.manual_seed(20260418)
-    np.random.seed(20260418)
-    net = Network(Config(json.dumps(CFG_BLOCKS), is_file=False))
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    net = Network(Config(json.dumps(cfg), is_file=False))
     net.eval()
-    randomise_bn(net, 9)
-    wbin = os.path.join(HERE, "ref_btl_5bx32.bin.txt")
+    randomise_bn(net, bn_seed)
+    wbin = os.path.join(HERE, "ref_%s.bin.txt" % tag)
     net.transfer_to_bin(wbin)
     out = {}
     ref = Reference(wbin, winograd=False)
     per = 2
     for bs in (9, 13, 19):
-        x = synth.synth_positions(per, bs, seed=21)
+        x = synth.synth_positions(per, bs, seed=pos_seed)
         out["planes_%d" % bs] = x
         with torch.no_grad():
             pred, _ = net(torch.from_numpy(x).reshape(per, 43, bs, bs))
@@ -93,10 +108,10 @@ def main_blocks():
             d = np.abs(v[:s] - prob5[i, off]).max()
             d_own = np.abs(np.tanh(v[s:2 * s]) - pred[5].numpy()[i]).max()
             d_wdl = np.abs(v[2 * s + 1:2 * s + 4] - pred[6].numpy()[i]).max()
-            print("blocks net, bs %2d pos %d: C++ vs torch prob %.2e own %.2e wdl %.2e" % (bs, i, d, d_own, d_wdl))
+            print("%s net, bs %2d pos %d: C++ vs torch prob %.2e own %.2e wdl %.2e" % (tag, bs, i, d, d_own, d_wdl))
             assert max(d, d_own, d_wdl) < 5e-5
-    np.savez_compressed(os.path.join(HERE, "golden_btl_5bx32.npz"), **out)
-    print("wrote", wbin, "golden_btl_5bx32.npz")
+    np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % tag), **out)
+    print("wrote", wbin, "golden_%s.npz" % tag)
 
 
 def main():

@@ -59,7 +59,7 @@ def test_loader_errors_are_reported_before_touching_cuda(eng, tmp_path):
         pipe.initialize(str(tmp_path / "missing.txt"), 19, 8)
     info, layers = synth.synth_tensors(1, 32, 8, 8, seed=0, stack=["ResidualBlock"])
     p = tmp_path / "bad.txt"
-    synth.write_weights(str(p), dict(info, stack=["MixerBlock"]), layers)
+    synth.write_weights(str(p), dict(info, stack=["TransformerBlock"]), layers)
     with pytest.raises(RuntimeError, match="not supported by sayuri_b200"):
         pipe.initialize(str(p), 19, 8)
     synth.write_weights(str(p), dict(info, stack=["NestedBottleneckBlock"]), layers)   # stack and struct disagree

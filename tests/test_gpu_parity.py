@@ -453,3 +453,50 @@ def test_wide_bottleneck_tower_matches_oracle(eng, oracle_lib, prec_name):
             _check(out[i], orc.forward(planes[i], bs, i), bs, atol=atol)
     finally:
         pipe.destroy()
+
+
+def test_mixer_blocks_and_replk_head_match_reference_golden(eng, golden_mixer, golden_mixer_weights):
+    """Rest of SURVEY.md §8 a22: MixerBlock[-SE] (depthwise 7x7 / 5x5 + FFN, blas_forward_pipe.cc:265-312) and the RepLK
+    policy head (:443-471) against outputs of the UNMODIFIED compiled reference, mixed board sizes in one batch."""
+    pipe = eng.B200ForwardPipe().initialize(golden_mixer_weights, 19, 8, gpus=[0])
+    try:
+        d = pipe.net_desc()
+        assert d["block_types"] == [eng.BLOCK_MIXER, eng.BLOCK_MIXER, eng.BLOCK_RESIDUAL, eng.BLOCK_MIXER]
+        assert d["inner_channels"] == [48, 48, 0, 48] and d["dw_kernels"] == [7, 7, 0, 5]
+        assert d["policy_head_type"] == eng.POLICY_HEAD_REPLK and d["policy_dw_kernel"] == 7
+        planes, sizes, offsets, refs = [], [], [], []
+        for bs in SIZES:
+            for i in range(2):
+                planes.append(golden_mixer["planes_%d" % bs][i].ravel())
+                sizes.append(bs)
+                offsets.append(int(golden_mixer["offset_%d_%d" % (bs, i)]))
+                v = golden_mixer["ref_%d_%d" % (bs, i)]
+                s = bs * bs
+                refs.append(dict(prob=v[:s], own=v[s:2 * s], misc=v[2 * s:]))
+        out = pipe.batch_forward(0, planes, sizes, offsets)
+        for o, r, bs in zip(out, refs, sizes):
+            _check(o, r, bs)
+    finally:
+        pipe.destroy()
+
+
+@pytest.mark.parametrize("prec_name", ["fp32_split", "fp16"])
+def test_wide_mixer_tower_with_replk_head_matches_oracle(eng, oracle_lib, prec_name):
+    """128-wide Mixer tower (feed-forward width 192 = two N tiles of 96, depthwise 7x7) with P = 24 behind a RepLK head
+    (the 1x1 P -> P writes 24 of 32 padded output columns and must leave the value channels alone)."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_mix_4bx128.bin")
+    stack = ["MixerBlock", "MixerBlock-SE", "BottleneckBlock", "MixerBlock"]
+    synth.write_synth_net(path, (4, 128, 24, 24), seed=93, stack=stack, policy_head="RepLK")
+    prec = eng.PRECISION_FP32_SPLIT if prec_name == "fp32_split" else eng.PRECISION_FP16
+    atol = ATOL if prec_name == "fp32_split" else 5e-2
+    sizes = [19, 9, 13, 19]
+    planes = [synth.synth_positions(1, bs, seed=80 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    orc = oracle_lib.Oracle(path)
+    pipe = eng.B200ForwardPipe().initialize(path, 19, 4, gpus=[0], precision=prec)
+    try:
+        out = pipe.batch_forward(0, planes, sizes, [0, 1, 2, 3])
+        for i, bs in enumerate(sizes):
+            _check(out[i], orc.forward(planes[i], bs, i), bs, atol=atol)
+    finally:
+        pipe.destroy()

@@ -49,6 +49,22 @@ def test_oracle_matches_reference_golden_on_bottleneck_blocks(oracle_lib, golden
             np.testing.assert_allclose(got["misc"], misc, rtol=0, atol=ORACLE_VS_REF_ATOL)
 
 
+def test_oracle_matches_reference_golden_on_mixer_blocks_and_replk_head(oracle_lib, golden_mixer, golden_mixer_weights):
+    """MixerBlock[-SE] (blas_forward_pipe.cc:265-312: depthwise k x k, AddSpatialBiasesPost, 1x1 FFN) with kernel
+    sizes 7 and 5, and the RepLK policy head (:443-471), against the compiled reference's outputs."""
+    o = oracle_lib.Oracle(golden_mixer_weights)
+    assert (o.blocks, o.channels, o.P, o.V, o.act, o.n_se) == (4, 32, 8, 8, 5, 1)
+    for bs in SIZES:
+        x = golden_mixer["planes_%d" % bs]
+        for i in range(PER):
+            off = int(golden_mixer["offset_%d_%d" % (bs, i)])
+            got = o.forward(x[i], bs, offset=off)
+            prob, own, misc = _unpack(golden_mixer["ref_%d_%d" % (bs, i)], bs)
+            np.testing.assert_allclose(got["prob"], prob, rtol=0, atol=ORACLE_VS_REF_ATOL)
+            np.testing.assert_allclose(got["own"], own, rtol=0, atol=ORACLE_VS_REF_ATOL)
+            np.testing.assert_allclose(got["misc"], misc, rtol=0, atol=ORACLE_VS_REF_ATOL)
+
+
 def test_oracle_matches_reference_pytorch_forward(oracle_lib, golden, golden_weights_bin):
     """Second, independent pin: all five policy planes, pass logits and the value outputs of
     train/torch/network.py:1121-1215 (which applies tanh / scaling inside forward)."""
