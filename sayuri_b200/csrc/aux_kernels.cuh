@@ -297,17 +297,39 @@ __global__ void __launch_bounds__(128)
 dwconv_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
               __half* __restrict__ out_lo, bool split, const float* __restrict__ w, const float* __restrict__ bias,
               const int* __restrict__ board_sizes, Geom g, int n, int n_rows, int R_in, int R_out, int k, bool add_input) {
-    __shared__ float sw[15 * 15 * 8];
-    __shared__ float sb8[8];
+    // Shared memory: the k*k taps of this 8-channel chunk, and the input rows [r0 - halo, r0 + 128 + halo) of the chunk
+    // converted to fp32 once (hi + lo), halo = (k/2) * (P + 1) rows: every tap of every thread is then one 32-byte
+    // shared-memory read instead of two global loads and a conversion.
+    extern __shared__ float dw_smem[];
     const int chunk = blockIdx.y;
-    const int kk = k * k;
+    const int kk = k * k, pad = k >> 1;
+    const int halo = pad * (g.P + 1);
+    const int tile_rows = 128 + 2 * halo;
+    float* sw = dw_smem;                     // [kk][8]
+    float* sb8 = sw + kk * 8;                // [8]
+    float* tile = sb8 + 8;                   // [tile_rows][8]
     for (int i = threadIdx.x; i < kk * 8; i += blockDim.x) {
         const int tap = i >> 3, c = i & 7;
         sw[i] = w[(size_t)(chunk * 8 + c) * kk + tap];
     }
     if (threadIdx.x < 8) sb8[threadIdx.x] = bias[chunk * 8 + threadIdx.x];
+    const int r0 = blockIdx.x * 128;
+    for (int t = threadIdx.x; t < tile_rows; t += blockDim.x) {
+        const int grow = kGuardRows + r0 - halo + t;    // global canvas row of tile row t
+        float v[8];
+        if (grow >= 0 && grow < R_in) {
+            const size_t off = act_index(grow, chunk * 8, R_in);
+            load8(in_hi + off, in_lo + off, split, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        float4* dst = reinterpret_cast<float4*>(tile + t * 8);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
     __syncthreads();
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = r0 + threadIdx.x;
     if (r >= n_rows) return;
     const int b = r / g.SS, rem = r - b * g.SS;
     const int y = rem / g.P, x = rem - y * g.P;
@@ -316,35 +338,35 @@ dwconv_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const int row = kGuardRows + r;
     if (live) {
-        const int pad = k >> 1;
+        const int t0 = threadIdx.x + halo;          // this thread's own row inside the tile
         for (int ky = 0; ky < k; ++ky) {
             const int yy = y + ky - pad;
             if ((unsigned)yy >= (unsigned)bs) continue;
             for (int kx = 0; kx < k; ++kx) {
                 const int xx = x + kx - pad;
                 if ((unsigned)xx >= (unsigned)bs) continue;
-                float v[8];
-                const size_t off = act_index(row + (ky - pad) * g.P + (kx - pad), chunk * 8, R_in);
-                load8(in_hi + off, in_lo + off, split, v);
-                const float* wt = sw + (ky * k + kx) * 8;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += v[i] * wt[i];   // same tap order as the reference loop
+                const float4* src = reinterpret_cast<const float4*>(tile + (t0 + (ky - pad) * g.P + (kx - pad)) * 8);
+                const float4 a = src[0], c4 = src[1];
+                const float* wt = sw + (ky * k + kx) * 8;   // same tap order as the reference loop
+                acc[0] += a.x * wt[0];
+                acc[1] += a.y * wt[1];
+                acc[2] += a.z * wt[2];
+                acc[3] += a.w * wt[3];
+                acc[4] += c4.x * wt[4];
+                acc[5] += c4.y * wt[5];
+                acc[6] += c4.z * wt[6];
+                acc[7] += c4.w * wt[7];
             }
         }
-        float self[8];
-        if (add_input) {
-            const size_t off = act_index(row, chunk * 8, R_in);
-            load8(in_hi + off, in_lo + off, split, self);
-        }
+        const float* self = tile + t0 * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             acc[i] = activate_t<ACT>(acc[i] + sb8[i]);
             if (add_input) acc[i] += self[i];
         }
     }
-    const size_t off = act_index(row, chunk * 8, R_out);
+    const size_t off = act_index(kGuardRows + r, chunk * 8, R_out);
     store8(out_hi + off, out_lo + off, split, acc);
 }
 

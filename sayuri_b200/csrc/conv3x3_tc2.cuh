@@ -51,7 +51,13 @@ struct Conv2Cfg {
     static constexpr int kOffBias = kOffBar + 512;
     static constexpr int kSmemBytes = kOffBias + 256 * 4 + 1024;
     static constexpr int kTmemCols = 512;
-    static constexpr int kThreads = 384;
+    // Epilogue column parts per TMEM lane quadrant = epilogue warps per scheduler.  2 on both rungs: 4 parts (16 epilogue
+    // warps, 640 threads) measured 2 % SLOWER on the fp16 rung (265 k vs 271 k evals/s) and 13 % slower on 1x1-conv
+    // heavy towers — after the resident-weight change that rung is bound by the tensor core's operand reads from
+    // shared memory (~95 cycles per N=128 MMA instead of 64), not by the epilogue.
+    static constexpr int kEpiParts = 2;
+    static constexpr int kThreads = 128 + kEpiParts * 128;
+    static constexpr int kMaxGroups = 128 / kEpiParts / 16;   // 16-column groups per epilogue thread (BN <= 128)
     static_assert(kNumBStages <= 18 && kNumSlabs <= 4, "barrier block layout");
     static_assert(kSlabPartBytes % 1024 == 0, "slab parts must keep the weight stages 1024-byte aligned");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
@@ -147,7 +153,7 @@ __device__ __forceinline__ ConvUnit conv_unit(int u, const ConvParams& p) {
 }
 
 template <bool SPLIT, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<SPLIT>::kThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                    const __grid_constant__ CUtensorMap tmWq_hi, const __grid_constant__ CUtensorMap tmWq_lo,
@@ -187,7 +193,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tmem_full + 8 * i, 1);
-            mbar_init(tmem_empty + 8 * i, 16);  // 8 epilogue warps x 2 CTAs
+            mbar_init(tmem_empty + 8 * i, 2 * 4 * Cfg::kEpiParts);  // every epilogue warp of both CTAs
         }
         for (int i = 0; i < Cfg::kNumBStages; ++i) {
             mbar_init(b_full + 8 * i, 1);
@@ -355,11 +361,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: 8 warps; warp%4 = TMEM lane quadrant, (warp-4)/4 = column half =====================
-        // Two warps per scheduler: each thread owns half an accumulator row (BN/2 columns, 64 registers), so
+        // ===================== epilogue: 4 * kEpiParts warps; warp%4 = TMEM lane quadrant, (warp-4)/4 = column part =====================
+        // kEpiParts warps per scheduler: each thread owns 1/kEpiParts of an accumulator row (<= 64 / 32 registers), so
         // the dependent ALU/MUFU chains of one warp are hidden behind the other.
         const int q = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int part = (warp - 4) >> 2;                      // which column part of the accumulator row
         const bool stats = p.stats != nullptr;
         uint32_t j = 0;
         long long t_wait_full = 0, t_drain = 0;
@@ -369,9 +375,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
             const ConvUnit w = conv_unit(item, p);
             const int st = w.st;
-            const int c_split = ((w.bn >> 1) + 15) & ~15;          // column split, rounded to the 16-column ld granule
-            const int cbase = half ? c_split : 0;
-            const int HC = half ? w.bn - c_split : c_split;        // columns of this thread (multiple of 16, may be 0)
+            // columns of this thread: w.bn split into kEpiParts runs rounded to the 16-column ld granule (may be 0)
+            const int c_run = ((w.bn + Cfg::kEpiParts - 1) / Cfg::kEpiParts + 15) & ~15;
+            const int cbase = min(part * c_run, w.bn);
+            const int HC = min(c_run, w.bn - cbase);
             const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
 
             // Everything the epilogue needs from global memory is requested BEFORE waiting for the accumulators: the
@@ -401,10 +408,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
             const uint32_t t_main = lane_base + (SPLIT ? as * 2 * BN : as * BN) + cbase;
             const uint32_t t_lo = t_main + BN;
-            float acc[64];
+            float acc[Cfg::kMaxGroups * 16];
             const long long t_d0 = stats ? clock64() : 0;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < Cfg::kMaxGroups; ++g) {
                 if (g * 16 < HC) {
                     uint32_t r[16];
                     tmem_ld16(t_main + g * 16, r);
@@ -427,7 +434,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (stats) t_drain += clock64() - t_d0;
 
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < Cfg::kMaxGroups; ++g) {
                 if (g * 16 < HC) {
                     const int c0 = g * 16;
                     const size_t o0 = off + (size_t)(c0 >> 3) * chunk_stride, o1 = o0 + chunk_stride;

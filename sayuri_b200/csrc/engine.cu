@@ -739,7 +739,7 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
             // launched with the programmatic-stream-serialization attribute: see pdl_wait() in conv3x3_tc2.cuh
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid2);
-            cfg.blockDim = dim3(384);
+            cfg.blockDim = dim3(Split(e) ? Conv2Cfg<true>::kThreads : Conv2Cfg<false>::kThreads);
             cfg.stream = s.stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -778,7 +778,9 @@ static void LaunchDw(sb_engine* e, Slot& s, const DwLayout& d, const uint8_t* bl
     const dim3 grid((n_rows + 127) / 128, d.ch / 8);
     const float* w = reinterpret_cast<const float*>(blob + d.w);
     const float* b = reinterpret_cast<const float*>(blob + d.b);
-    SB_DISPATCH_ACT(act, ACT, (dwconv_kernel<ACT><<<grid, 128, 0, s.stream>>>(in.hi, in.lo, out.hi, out.lo, Split(e), w, b, s.d_meta,
+    const int halo = (d.k / 2) * (e->geom.P + 1);
+    const size_t smem = ((size_t)d.k * d.k * 8 + 8 + (size_t)(128 + 2 * halo) * 8) * sizeof(float);
+    SB_DISPATCH_ACT(act, ACT, (dwconv_kernel<ACT><<<grid, 128, smem, s.stream>>>(in.hi, in.lo, out.hi, out.lo, Split(e), w, b, s.d_meta,
                                                                               e->geom, n, n_rows, in.rows, out.rows, d.k, add_input)));
     SB_CUDA(cudaGetLastError());
     e->launches++;
