@@ -175,7 +175,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     constexpr uint32_t kNA = Cfg::kNumSlabs;
     // resident weights: the ring is exactly one item's worth of stages, filled once, never recycled
     const bool resident = p.resident != 0;
-    const uint32_t kNB = resident ? (uint32_t)(p.kh * p.ntaps * Cfg::kParts) : (uint32_t)Cfg::kNumBStages;
+    // a weight stage holds this CTA's N-half of one [BN][64] block: 8 KB slots for BN <= 128, 16 KB (two slots) for the
+    // N = 256 tiles of the fp16 rung, which therefore has half as many stages in the same ring
+    const uint32_t stage_stride = BN > 128 ? 2u * Cfg::kBStageBytes : (uint32_t)Cfg::kBStageBytes;
+    const uint32_t kNB = resident ? (uint32_t)(p.kh * p.ntaps * Cfg::kParts)
+                                  : (uint32_t)(Cfg::kNumBStages * Cfg::kBStageBytes) / stage_stride;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -261,7 +265,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         if (elect_one()) {
                             const uint32_t full0 = mapa_u32(b_full + 8 * s, 0);
                             if (leader) mbar_arrive_expect_tx(b_full + 8 * s, 2u * (uint32_t)HB * 128u);
-                            tma2_load_2d(bst_addr + s * Cfg::kBStageBytes,
+                            tma2_load_2d(bst_addr + s * stage_stride,
                                          whole ? (part ? &tmW_lo : &tmW_hi) : (part ? &tmWq_lo : &tmWq_hi),
                                          tap * (KH * 64) + h * 64, w.n0 + (int)rank * HB, full0);
                         }
@@ -310,7 +314,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             if (!(p.dbg & 16) && !(resident && j > 0)) mbar_wait(b_full + 8 * bs, bph, p.err, 5);
                             if (stats) t_wait_b += clock64() - t0;
                             tc_fence_after();
-                            const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
+                            const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * stage_stride);
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
@@ -332,7 +336,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             if (!(p.dbg & 16) && !(resident && j > 0)) mbar_wait(b_full + 8 * bs, bph, p.err, 6);
                             if (stats) t_wait_b += clock64() - t0;
                             tc_fence_after();
-                            const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * Cfg::kBStageBytes);
+                            const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * stage_stride);
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) umma2_f16(d_lo, ad0 + kAStep * k, bd0 + 2 * k, idesc, 1u);
@@ -375,117 +379,127 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
             const ConvUnit w = conv_unit(item, p);
             const int st = w.st;
-            // columns of this thread: w.bn split into kEpiParts runs rounded to the 16-column ld granule (may be 0)
+            // columns of this thread: w.bn split into kEpiParts runs rounded to the 16-column ld granule (may be 0);
+            // a run longer than 64 columns (N = 256 tiles of the fp16 rung) is processed in passes of 64
             const int c_run = ((w.bn + Cfg::kEpiParts - 1) / Cfg::kEpiParts + 15) & ~15;
             const int cbase = min(part * c_run, w.bn);
             const int HC = min(c_run, w.bn - cbase);
+            const int n_pass = max(1, (HC + 63) >> 6);
             const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
 
-            // Everything the epilogue needs from global memory is requested BEFORE waiting for the accumulators: the
-            // mask byte and the residual pieces of the first 16-column group; the pieces of group g+1 are requested
-            // while group g is being computed (a load issued at its point of use stalled ~1 us four times per item).
             const int row = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 + q * 32 + lane;
             const bool live = p.mask[row] != 0;
             const bool has_res = live && p.res_hi != nullptr && !(p.dbg & 1);
             const size_t chunk_stride = (size_t)p.rows * 8;
-            const size_t off = act_index(row, w.n0 + cbase, p.rows);
-            uint4 rh[2][2], rl[2][2];
-            rh[0][0] = rh[0][1] = rh[1][0] = rh[1][1] = make_uint4(0u, 0u, 0u, 0u);
-            rl[0][0] = rl[0][1] = rl[1][0] = rl[1][1] = make_uint4(0u, 0u, 0u, 0u);
-            if (has_res && HC > 0) {
-                rh[0][0] = *reinterpret_cast<const uint4*>(p.res_hi + off);
-                rh[0][1] = *reinterpret_cast<const uint4*>(p.res_hi + off + chunk_stride);
-                if (SPLIT) {
-                    rl[0][0] = *reinterpret_cast<const uint4*>(p.res_lo + off);
-                    rl[0][1] = *reinterpret_cast<const uint4*>(p.res_lo + off + chunk_stride);
-                }
-            }
-
-            const long long t0 = stats ? clock64() : 0;
-            mbar_wait(tmem_full + 8 * as, aph, p.err, 7);
-            if (stats) t_wait_full += clock64() - t0;
-            tc_fence_after();
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-            const uint32_t t_main = lane_base + (SPLIT ? as * 2 * BN : as * BN) + cbase;
-            const uint32_t t_lo = t_main + BN;
-            float acc[Cfg::kMaxGroups * 16];
-            const long long t_d0 = stats ? clock64() : 0;
-#pragma unroll
-            for (int g = 0; g < Cfg::kMaxGroups; ++g) {
-                if (g * 16 < HC) {
-                    uint32_t r[16];
-                    tmem_ld16(t_main + g * 16, r);
+
+            for (int pass = 0; pass < n_pass; ++pass) {
+                const int pbase = cbase + pass * 64;            // first column of this pass inside the N tile
+                const int PC = min(64, HC - pass * 64);         // columns of this pass (multiple of 16, may be 0)
+                // Everything the epilogue needs from global memory is requested BEFORE waiting for the accumulators:
+                // the mask byte and the residual pieces of the first 16-column group; the pieces of group g+1 are
+                // requested while group g is computed (a load issued at its point of use stalled ~1 us per group).
+                const size_t off = act_index(row, w.n0 + pbase, p.rows);
+                uint4 rh[2][2], rl[2][2];
+                rh[0][0] = rh[0][1] = rh[1][0] = rh[1][1] = make_uint4(0u, 0u, 0u, 0u);
+                rl[0][0] = rl[0][1] = rl[1][0] = rl[1][1] = make_uint4(0u, 0u, 0u, 0u);
+                if (has_res && PC > 0) {
+                    rh[0][0] = *reinterpret_cast<const uint4*>(p.res_hi + off);
+                    rh[0][1] = *reinterpret_cast<const uint4*>(p.res_hi + off + chunk_stride);
                     if (SPLIT) {
-                        uint32_t r2[16];
-                        tmem_ld16(t_lo + g * 16, r2);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
-                    } else {
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]);
+                        rl[0][0] = *reinterpret_cast<const uint4*>(p.res_lo + off);
+                        rl[0][1] = *reinterpret_cast<const uint4*>(p.res_lo + off + chunk_stride);
                     }
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(empty0 + 8 * as);   // accumulator stage is free again
-            if (stats) t_drain += clock64() - t_d0;
-
+                if (pass == 0) {
+                    const long long t0 = stats ? clock64() : 0;
+                    mbar_wait(tmem_full + 8 * as, aph, p.err, 7);
+                    if (stats) t_wait_full += clock64() - t0;
+                    tc_fence_after();
+                }
+                const uint32_t t_main = lane_base + (SPLIT ? as * 2 * BN : as * BN) + pbase;
+                const uint32_t t_lo = t_main + BN;
+                float acc[Cfg::kMaxGroups * 16];
+                const long long t_d0 = stats ? clock64() : 0;
 #pragma unroll
-            for (int g = 0; g < Cfg::kMaxGroups; ++g) {
-                if (g * 16 < HC) {
-                    const int c0 = g * 16;
-                    const size_t o0 = off + (size_t)(c0 >> 3) * chunk_stride, o1 = o0 + chunk_stride;
-                    if (has_res && (g + 1) * 16 < HC) {   // next group's residual pieces
-                        const size_t n0 = o0 + 2 * chunk_stride, n1 = n0 + chunk_stride;
-                        rh[(g + 1) & 1][0] = *reinterpret_cast<const uint4*>(p.res_hi + n0);
-                        rh[(g + 1) & 1][1] = *reinterpret_cast<const uint4*>(p.res_hi + n1);
+                for (int g = 0; g < Cfg::kMaxGroups; ++g) {
+                    if (g * 16 < PC) {
+                        uint32_t r[16];
+                        tmem_ld16(t_main + g * 16, r);
                         if (SPLIT) {
-                            rl[(g + 1) & 1][0] = *reinterpret_cast<const uint4*>(p.res_lo + n0);
-                            rl[(g + 1) & 1][1] = *reinterpret_cast<const uint4*>(p.res_lo + n1);
+                            uint32_t r2[16];
+                            tmem_ld16(t_lo + g * 16, r2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+                        } else {
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]);
                         }
                     }
-                    float v[16];
+                }
+                if (pass == n_pass - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(empty0 + 8 * as);   // accumulator stage is free again
+                }
+                if (stats) t_drain += clock64() - t_d0;
+
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[w.n0 + cbase + c0 + i];
-                    if (has_res) {
-                        const __half* hh0 = reinterpret_cast<const __half*>(&rh[g & 1][0]);
-                        const __half* hh1 = reinterpret_cast<const __half*>(&rh[g & 1][1]);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            v[i] += __half2float(hh0[i]);
-                            v[8 + i] += __half2float(hh1[i]);
-                        }
-                        if (SPLIT) {
-                            const __half* ll0 = reinterpret_cast<const __half*>(&rl[g & 1][0]);
-                            const __half* ll1 = reinterpret_cast<const __half*>(&rl[g & 1][1]);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                v[i] += __half2float(ll0[i]);
-                                v[8 + i] += __half2float(ll1[i]);
+                for (int g = 0; g < Cfg::kMaxGroups; ++g) {
+                    if (g * 16 < PC) {
+                        const int c0 = g * 16;
+                        const size_t o0 = off + (size_t)(c0 >> 3) * chunk_stride, o1 = o0 + chunk_stride;
+                        if (has_res && (g + 1) * 16 < PC) {   // next group's residual pieces
+                            const size_t n0 = o0 + 2 * chunk_stride, n1 = n0 + chunk_stride;
+                            rh[(g + 1) & 1][0] = *reinterpret_cast<const uint4*>(p.res_hi + n0);
+                            rh[(g + 1) & 1][1] = *reinterpret_cast<const uint4*>(p.res_hi + n1);
+                            if (SPLIT) {
+                                rl[(g + 1) & 1][0] = *reinterpret_cast<const uint4*>(p.res_lo + n0);
+                                rl[(g + 1) & 1][1] = *reinterpret_cast<const uint4*>(p.res_lo + n1);
                             }
                         }
-                    }
-                    uint32_t oh[8], ol[8];
-                    if (!(p.dbg & 2)) activate16<ACT>(v);
-                    if (!live) {   // select, not multiply: garbage rows may hold NaN
+                        float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-                    }
-                    split16(v, oh, ol, SPLIT);
-                    if ((p.dbg & 1) && oh[0] != 0x12345678u) continue;
-                    // cout may be a multiple of 8 only (weight rows are zero-padded to 16): channels >= cout belong to
-                    // somebody else (the value half of the head buffer behind a RepLK 1x1) and are not written
-                    const int ch0 = w.n0 + cbase + c0;
-                    if (ch0 < p.cout) {
-                        *reinterpret_cast<uint4*>(p.out_hi + o0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-                        if (SPLIT) *reinterpret_cast<uint4*>(p.out_lo + o0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-                    }
-                    if (ch0 + 8 < p.cout) {
-                        *reinterpret_cast<uint4*>(p.out_hi + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-                        if (SPLIT) *reinterpret_cast<uint4*>(p.out_lo + o1) = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+                        for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[w.n0 + pbase + c0 + i];
+                        if (has_res) {
+                            const __half* hh0 = reinterpret_cast<const __half*>(&rh[g & 1][0]);
+                            const __half* hh1 = reinterpret_cast<const __half*>(&rh[g & 1][1]);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                v[i] += __half2float(hh0[i]);
+                                v[8 + i] += __half2float(hh1[i]);
+                            }
+                            if (SPLIT) {
+                                const __half* ll0 = reinterpret_cast<const __half*>(&rl[g & 1][0]);
+                                const __half* ll1 = reinterpret_cast<const __half*>(&rl[g & 1][1]);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    v[i] += __half2float(ll0[i]);
+                                    v[8 + i] += __half2float(ll1[i]);
+                                }
+                            }
+                        }
+                        uint32_t oh[8], ol[8];
+                        if (!(p.dbg & 2)) activate16<ACT>(v);
+                        if (!live) {   // select, not multiply: garbage rows may hold NaN
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                        }
+                        split16(v, oh, ol, SPLIT);
+                        if ((p.dbg & 1) && oh[0] != 0x12345678u) continue;
+                        // cout may be a multiple of 8 only (weight rows are zero-padded to 16): channels >= cout belong to
+                        // somebody else (the value half of the head buffer behind a RepLK 1x1) and are not written
+                        const int ch0 = w.n0 + pbase + c0;
+                        if (ch0 < p.cout) {
+                            *reinterpret_cast<uint4*>(p.out_hi + o0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                            if (SPLIT) *reinterpret_cast<uint4*>(p.out_lo + o0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                        }
+                        if (ch0 + 8 < p.cout) {
+                            *reinterpret_cast<uint4*>(p.out_hi + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+                            if (SPLIT) *reinterpret_cast<uint4*>(p.out_lo + o1) = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+                        }
                     }
                 }
             }

@@ -347,7 +347,8 @@ struct DevConv {
     // CTA-pair kernel: box [(bn >> level) / 2][64] = one CTA's half of an N tile of width bn >> level.  Level 0 is the
     // throughput shape; levels 1-2 spread small batches over more CTA pairs and serve the tail-wave half units.
     CUtensorMap tm2_hi[4], tm2_lo[4];
-    int levels = 1;               // usable N widths: bn >> 0 .. bn >> (levels - 1), each a multiple of 16
+    int levels = 1;               // usable N widths: bn0 >> 0 .. bn0 >> (levels - 1), each a multiple of 16
+    int bn0 = 0;                  // widest N tile of the CTA-pair kernel for this layer (L.bn, or 256 on the fp16 rung)
     float* wT = nullptr;  // fp32 [9*cinp][cout], SIMT debug only
 };
 
@@ -426,6 +427,7 @@ struct sb_engine {
     int desc_swap = 0;
     int conv_dbg = 0;
     int conv_impl = 2;   // 1 = single-CTA conv3x3_tc, 2 = CTA-pair conv3x3_tc2 (default)
+    int wide_n = 1;              // fp16 rung: N = 256 tiles for 256-wide layers (read at engine creation / reload)
     int resident_weights = 1;    // fp16 rung: keep a C <= 128 layer's weights in shared memory for the whole launch
     int chain_forwards = 1;      // forwards of different slots of a replica run back to back, never interleaved
     int small_batch_split = 1;   // narrower N tiles when a batch does not fill one wave of CTA pairs
@@ -559,14 +561,18 @@ static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int
 
 static void AllocSlots(sb_engine* e, Replica& r) { AllocSlotVec(e, r, r.slots, e->n_slots); }
 
-static void MakeConvMaps(const Replica& r, DevConv& c) {
+static void MakeConvMaps(const Replica& r, DevConv& c, bool wide_n) {
     const int K = c.L.taps * c.L.cinp;
     c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.coutp, K, c.L.bn);
     c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.coutp, K, c.L.bn);
+    // CTA-pair kernel, fp16 rung: a layer wider than 128 (up to 256) runs as ONE N tile (the accumulators of the fp16
+    // rung leave room in TMEM: 2 stages x N <= 512 columns): the activation slab is loaded, and read from shared memory
+    // by the tensor core, once instead of once per narrow tile (20bx256: 43 k -> 60 k evals/s)
+    c.bn0 = (wide_n && c.L.coutp > 128 && c.L.coutp <= 256) ? c.L.coutp : c.L.bn;
     c.levels = 0;
     for (int lv = 0; lv < 4; ++lv) {
-        const int bn = c.L.bn >> lv;
-        if (bn < 16 || bn % 16 || (bn << lv) != c.L.bn) break;    // UMMA N (M = 256) must be a multiple of 16
+        const int bn = c.bn0 >> lv;
+        if (bn < 16 || bn % 16 || (bn << lv) != c.bn0) break;    // UMMA N (M = 256) must be a multiple of 16
         c.tm2_hi[lv] = MakeMap2D(r.blob + c.L.w_hi, c.L.coutp, K, bn / 2);
         c.tm2_lo[lv] = MakeMap2D(r.blob + c.L.w_lo, c.L.coutp, K, bn / 2);
         c.levels = lv + 1;
@@ -604,19 +610,20 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     if (blob) SB_CUDA(cudaMemcpy(r.blob, blob->data(), e->layout.bytes, cudaMemcpyHostToDevice));
     const int blocks = e->net_shape.blocks;
     r.input.L = e->layout.input;
-    MakeConvMaps(r, r.input);
+    const bool wide_n = !Split(e) && e->wide_n;
+    MakeConvMaps(r, r.input, wide_n);
     r.head.L = e->layout.head;
-    MakeConvMaps(r, r.head);
+    MakeConvMaps(r, r.head, wide_n);
     if (e->layout.p_dw.k > 0) {
         r.p_pt.L = e->layout.p_pt;
-        MakeConvMaps(r, r.p_pt);
+        MakeConvMaps(r, r.p_pt, wide_n);
     }
     r.bconv.resize(blocks);
     for (int b = 0; b < blocks; ++b) {
         r.bconv[b].resize(e->layout.bconv[b].size());
         for (size_t q = 0; q < r.bconv[b].size(); ++q) {
             r.bconv[b][q].L = e->layout.bconv[b][q];
-            MakeConvMaps(r, r.bconv[b][q]);
+            MakeConvMaps(r, r.bconv[b][q], wide_n);
         }
     }
     if (blob && e->precision == SB_PRECISION_SIMT_DEBUG) {
@@ -715,9 +722,9 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
             int level = 0;
             const int max_pairs = r.sm_count / 2;
             while (e->small_batch_split && level + 1 < c.levels && level < 2 &&
-                   n_super * (c.L.coutp / (c.L.bn >> (level + 1))) <= max_pairs)
+                   n_super * (c.L.coutp / (c.bn0 >> (level + 1))) <= max_pairs)
                 ++level;
-            p.bn = c.L.bn >> level;
+            p.bn = c.bn0 >> level;
             p.n_ntiles = c.L.coutp / p.bn;
             const int items2 = n_super * p.n_ntiles;
             // fp16 rung, one N tile, <= 18 weight stages per item: weights stay resident in shared memory
@@ -1797,6 +1804,10 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     }
     if (!std::strcmp(key, "pack_threads")) {
         e->pack_threads = std::max(1, value);
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "wide_n")) {   // takes effect at the next weight (re)load, when the tensor maps are rebuilt
+        e->wide_n = value ? 1 : 0;
         return SB_OK;
     }
     if (!std::strcmp(key, "resident_weights")) {
