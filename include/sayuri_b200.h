@@ -225,8 +225,9 @@ uint64_t sb_weights_checksum(sb_engine* e, int gpu);   /* FNV-1a of the blob, to
 
 /* Re-run the forward of the batch last submitted to (gpu, slot), inputs resident in HBM, `iters` times;
  * ms_each[i] = device time of iteration i.  flush_l2 != 0 writes a buffer larger than L2 between
- * iterations.  conv_ms / conv_launches (optional) receive the summed device time and the count of
- * conv3x3 launches measured with events around each launch in one extra, separate pass. */
+ * iterations.  conv_ms / conv_launches (optional) receive the device time and the count of the convolution-kernel
+ * launches of one forward, measured in extra passes (median of 5) as forward time minus the time of the other kernels,
+ * which are bracketed with events (the conv launches keep their back-to-back overlap). */
 int sb_time_forward(sb_engine* e, int gpu, int slot, int iters, int flush_l2, float* ms_each,
                     float* conv_ms, int* conv_launches);
 long long sb_launch_count(const sb_engine* e);  /* kernels launched by this engine so far */

@@ -668,20 +668,26 @@ static void DestroyReplica(Replica& r) {
 
 // ------------------------------------------------------------------------------------------------
 // Forward orchestration
+// Profiling pass of sb_time_forward: event pairs around every group of NON-convolution kernels of one forward, so that
+// the convolution launches keep their back-to-back programmatic-dependent-launch overlap exactly as in a normal step;
+// time of the conv kernel = duration of the forward - sum of the bracketed groups.
 struct ConvTimer {
-    std::vector<cudaEvent_t> ev;  // pairs
+    std::vector<cudaEvent_t> ev;  // pairs around the other kernels
     bool on = false;
+    int conv_launches = 0;
+    void Mark(cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t a;
+        SB_CUDA(cudaEventCreate(&a));
+        SB_CUDA(cudaEventRecord(a, st));
+        ev.push_back(a);
+    }
 };
 
 static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, const ActBuf& in, ActBuf& out,
                        const ActBuf* res, int act, int n, ConvTimer* tm) {
     const int n_super = e->geom.n_super(n);
-    if (tm && tm->on) {
-        cudaEvent_t a;
-        SB_CUDA(cudaEventCreate(&a));
-        SB_CUDA(cudaEventRecord(a, s.stream));
-        tm->ev.push_back(a);
-    }
+    if (tm && tm->on) tm->conv_launches++;
     if (e->precision == SB_PRECISION_SIMT_DEBUG) {
         dim3 grid((n_super * kSuperRows + 7) / 8, (c.L.cout + 31) / 32), block(32, 8);
         conv3x3_simt_kernel<<<grid, block, 0, s.stream>>>(in.hi, in.lo, true, c.L.cinp, c.wT,
@@ -772,12 +778,6 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
     }
     SB_CUDA(cudaGetLastError());
     e->launches++;
-    if (tm && tm->on) {
-        cudaEvent_t b;
-        SB_CUDA(cudaEventCreate(&b));
-        SB_CUDA(cudaEventRecord(b, s.stream));
-        tm->ev.push_back(b);
-    }
 }
 
 static void LaunchDw(sb_engine* e, Slot& s, const DwLayout& d, const uint8_t* blob, const ActBuf& in, ActBuf& out, int act,
@@ -806,6 +806,8 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     auto F = [&](size_t off) { return reinterpret_cast<const float*>(r.blob + off); };
 
     e->conv_counter = 0;
+    auto mark = [&]() { if (tm) tm->Mark(s.stream); };   // brackets groups of non-convolution kernels (profiling pass)
+    mark();
     {   // input planes -> canvas
         const int threads = n_rows * 8;
         if (s.packed) {
@@ -819,6 +821,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         SB_CUDA(cudaGetLastError());
         e->launches++;
     }
+    mark();
     ActBuf* x = &s.x;
     ActBuf* t = &s.t;
     ActBuf* u = &s.u;
@@ -833,7 +836,9 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         const ActBuf* se_skip = x;
         if (e->block_types[b] == SB_BLOCK_MIXER) {
             // MixerBlockForward, blas_forward_pipe.cc:265-312: y = act(dw(x) + b) + x ; out = ffn2(act(ffn1(y))) (+ y)
+            mark();
             LaunchDw(e, s, L.bdw[b], r.blob, *x, *t, act, true, n, n_rows);
+            mark();
             LaunchConv(e, r, s, cv[0], *t, s.ia, nullptr, act, n, tm);
             LaunchConv(e, r, s, cv[1], s.ia, *u, se > 0 ? nullptr : t, last_act, n, tm);
             se_skip = t;   // the skip of this block and of its SE unit is y
@@ -857,6 +862,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
             LaunchConv(e, r, s, cv[5], s.ia, *u, last_res, last_act, n, tm);
         }
         if (se > 0) {
+            mark();
             const size_t smem = ((size_t)3 * C + se) * sizeof(float);
             se_pool_fc_kernel<<<dim3((C + 31) / 32, n), 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se,
                                                                                 F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
@@ -867,17 +873,20 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
                                           u->hi, u->lo, se_skip->hi, se_skip->lo, split, s.mask, s.gb, g, C, u->rows, n_rows)));
             SB_CUDA(cudaGetLastError());
             e->launches += 2;
+            mark();
         }
         std::swap(x, u);
     }
     s.trunk = x;
     // heads: the two head-entry 1x1 convs as one single-tap tensor-core launch
-    LaunchConv(e, r, s, r.head, *x, s.pv, nullptr, act, n, nullptr);
+    LaunchConv(e, r, s, r.head, *x, s.pv, nullptr, act, n, tm);
     if (e->replk_kernel > 0) {
         // RepLK policy head, blas_forward_pipe.cc:443-471: depthwise k x k (+bias, act) on the P policy channels, then a
         // 1x1 P -> P (+bias, act) written back over the policy channels of pv (the V value channels stay untouched)
+        mark();
         LaunchDw(e, s, L.p_dw, r.blob, s.pv, s.pq, act, false, n, n_rows);
-        LaunchConv(e, r, s, r.p_pt, s.pq, s.pv, nullptr, act, n, nullptr);
+        mark();
+        LaunchConv(e, r, s, r.p_pt, s.pq, s.pv, nullptr, act, n, tm);
     }
     HeadWeights hw;
     hw.p_inter_w = F(L.p_inter.w);
@@ -892,6 +901,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     hw.prob_b = F(L.prob_b);
     hw.own_w = F(L.own_w);
     hw.own_b = F(L.own_b);
+    mark();
     {
         const int PV = P + V;
         const size_t smem = ((size_t)3 * P + 3 * V + P + 3 * V) * sizeof(float);
@@ -903,6 +913,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         SB_CUDA(cudaGetLastError());
     }
     e->launches += 2;
+    mark();
 }
 
 // Enqueue one forward on the slot's stream, ordered after the forward enqueued last on the same replica.
@@ -1719,19 +1730,31 @@ int sb_time_forward(sb_engine* e, int gpu, int slot, int iters, int flush_l2, fl
             if (ms_each) ms_each[i] = ms;
         }
         if (conv_ms || conv_launches) {
-            ConvTimer tm;
-            tm.on = true;
-            EnqueueForward(e, r, s, s.n, &tm);
-            CheckSlotError(s, cudaStreamSynchronize(s.stream), "profiled forward");
-            float total = 0.f;
-            for (size_t i = 0; i + 1 < tm.ev.size(); i += 2) {
-                float ms = 0.f;
-                SB_CUDA(cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]));
-                total += ms;
+            // conv kernel time = forward time - time of the bracketed non-convolution kernel groups, median of 5 passes
+            std::vector<float> samples;
+            int launches = 0;
+            for (int pass = 0; pass < 5; ++pass) {
+                ConvTimer tm;
+                tm.on = true;
+                if (flush_l2) SB_CUDA(cudaMemsetAsync(r.flush_buf, pass & 0xff, r.flush_bytes, s.stream));
+                SB_CUDA(cudaEventRecord(s.ev_a, s.stream));
+                EnqueueForward(e, r, s, s.n, &tm);
+                SB_CUDA(cudaEventRecord(s.ev_b, s.stream));
+                CheckSlotError(s, cudaStreamSynchronize(s.stream), "profiled forward");
+                float total = 0.f, others = 0.f;
+                SB_CUDA(cudaEventElapsedTime(&total, s.ev_a, s.ev_b));
+                for (size_t i = 0; i + 1 < tm.ev.size(); i += 2) {
+                    float ms = 0.f;
+                    SB_CUDA(cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]));
+                    others += ms;
+                }
+                samples.push_back(total - others);
+                launches = tm.conv_launches;
+                for (cudaEvent_t ev : tm.ev) cudaEventDestroy(ev);
             }
-            if (conv_ms) *conv_ms = total;
-            if (conv_launches) *conv_launches = (int)(tm.ev.size() / 2);
-            for (cudaEvent_t ev : tm.ev) cudaEventDestroy(ev);
+            std::sort(samples.begin(), samples.end());
+            if (conv_ms) *conv_ms = samples[samples.size() / 2];
+            if (conv_launches) *conv_launches = launches;
         }
     } catch (const CudaError& ce) {
         return Fail(e, SB_ERR_CUDA, ce.msg);
