@@ -132,7 +132,7 @@ __device__ __forceinline__ void pool_slice_c8(const __half* __restrict__ hi, con
     if (part < parts) {
         const int per = (SS + parts - 1) / parts;
         const int r_end = min(SS, (part + 1) * per);
-#pragma unroll 4
+#pragma unroll 8
         for (int r = part * per + lane; r < r_end; r += 32) {
             const bool live = mask[row0 + r] != 0;
             float v[8];
@@ -189,24 +189,50 @@ __device__ __forceinline__ bool last_cta_of_sample(int* counter, int n_ctas, int
     return last;
 }
 
+// Small fully-connected layer y = W x (+ b) for the per-sample tails: 8 adjacent lanes share one output and stride its
+// inputs (a 32-byte run per step), all outputs of a pass are computed concurrently by the 256 threads, a fixed 3-step
+// shuffle tree finishes each output.  (One warp per output with the outputs of a warp in sequence made these tails
+// 11 us of pure latency per sample.)  x in shared memory; calls `emit(o, sum)` from the first lane of each output.
+template <typename Emit>
+__device__ __forceinline__ void fc_tail_8lanes(const float* __restrict__ w, const float* x, int in, int out, Emit emit) {
+    const int sub = threadIdx.x & 7;
+    for (int o0 = 0; o0 < out; o0 += 32) {
+        const int o = o0 + (threadIdx.x >> 3);
+        float acc = 0.f;
+        if (o < out) {
+            const float* wr = w + (size_t)o * in;
+            for (int i = sub; i < in; i += 8) acc += wr[i] * x[i];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (o < out && sub == 0) emit(o, acc);
+    }
+}
+
 // se_pool_fc: GlobalPooling<false> + squeeze FC + excite FC of SEUnit::Forward
 // (/root/reference/src/neural/blas/se_unit.cc:9-37,70-90; GPU twins cuda_kernels.cu:241-321 and the
-// cuBLAS FCs cuda_layers.cc:975-1017).  grid (C/32, n): every CTA pools 32 channels of one sample into
-// pooled[n][2C] (sums, maxima); the sample's last CTA then runs the two FCs and writes sigmoid(gamma) and
-// beta, gb[n][2C].  Mean divides by the sample's own n^2, (n-14)/10 uses the sample's own n.
+// cuBLAS FCs cuda_layers.cc:975-1017).  grid (C/64, n): every CTA pools 64 channels of one sample into
+// pooled[n][2C] (sums, maxima); the sample's last CTA (threadfence + counter) then runs the two FCs and writes
+// sigmoid(gamma) and beta, gb[n][2C].  Mean divides by the sample's own n^2, (n-14)/10 uses the sample's own n.
+// (Letting that last CTA also apply the SE scaling to its sample — one launch less — measured SLOWER: 95 us vs 54 us
+// per SE unit at batch 256, one CTA per sample is too little parallelism for a 157 MB pass.)
+template <int ACT>
 __global__ void __launch_bounds__(256)
 se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_lo, bool split,
-                  const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int C, int R,
-                  int se, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                  const float* __restrict__ b2, int act, float* pooled, int* counters, float* __restrict__ gb) {
+                  const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int C, int R, int se,
+                  const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                  const float* __restrict__ b2, float* pooled, int* counters, float* __restrict__ gb, int dbg) {
     extern __shared__ float sm[];
     __shared__ float s_part[128];
     __shared__ float s_sum[64], s_max[64];
     __shared__ int s_flag;
     const int b = blockIdx.y;
-    const int chunk0 = blockIdx.x * 4;
-    const int ncl = min(4, (C >> 3) - chunk0);
-    pool_slice_c8(u_hi, u_lo, split, mask, kGuardRows + b * g.SS, g.SS, R, chunk0, ncl, s_part, s_sum, s_max);
+    const int chunk0 = blockIdx.x * 8;          // 8 chunks = 64 channels per CTA: 2 CTAs per sample at C = 128, so that
+    const int ncl = min(8, (C >> 3) - chunk0);  // the whole grid is resident at once (48 registers: 5 CTAs per SM)
+    const int row0 = kGuardRows + b * g.SS;
+    if (!(dbg & 512)) pool_slice_c8(u_hi, u_lo, split, mask, row0, g.SS, R, chunk0, ncl, s_part, s_sum, s_max);
+    if (dbg & 256) return;
     const int tid = threadIdx.x;
     if (tid < ncl * 8) {
         pooled[(size_t)b * 2 * C + chunk0 * 8 + tid] = s_sum[tid];
@@ -226,34 +252,12 @@ se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_
         pool[2 * C + c] = pv[C + c];
     }
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int o = warp; o < se; o += 8) {        // squeeze: 3C -> se, activation
-        float acc = 0.f;
-        for (int i = lane; i < 3 * C; i += 32) acc += w1[(size_t)o * 3 * C + i] * pool[i];
-        acc = warp_sum(acc);
-        if (lane == 0) hid[o] = activate(acc + b1[o], act);
-    }
+    fc_tail_8lanes(w1, pool, 3 * C, se, [&](int o, float v) { hid[o] = activate_t<ACT>(v + b1[o]); });   // squeeze, activation
     __syncthreads();
-    const bool vec4 = (se & 3) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0;
-    for (int o = tid; o < 2 * C; o += 256) {     // excite: se -> 2C, identity
-        float acc = 0.f;
-        if (vec4) {   // one 16-byte load per 4 weights, all independent (same summation order as the scalar loop)
-            const float4* wr = reinterpret_cast<const float4*>(w2 + (size_t)o * se);
-#pragma unroll 4
-            for (int i = 0; i < (se >> 2); ++i) {
-                const float4 w = wr[i];
-                acc += w.x * hid[4 * i];
-                acc += w.y * hid[4 * i + 1];
-                acc += w.z * hid[4 * i + 2];
-                acc += w.w * hid[4 * i + 3];
-            }
-        } else {
-            for (int i = 0; i < se; ++i) acc += w2[(size_t)o * se + i] * hid[i];
-        }
-        acc += b2[o];
-        if (o < C) acc = 1.0f / (1.0f + expf(-acc));   // gamma = sigmoid, se_unit.cc:103
-        gb[(size_t)b * 2 * C + o] = acc;
-    }
+    fc_tail_8lanes(w2, hid, se, 2 * C, [&](int o, float v) {                                             // excite, identity
+        v += b2[o];
+        gb[(size_t)b * 2 * C + o] = o < C ? 1.0f / (1.0f + expf(-v)) : v;   // gamma = sigmoid, se_unit.cc:103
+    });
 }
 
 // se_apply: x' = act(sigmoid(gamma) * u + beta + skip) on board cells, 0 elsewhere
@@ -388,18 +392,27 @@ struct HeadWeights {
     const float* own_b;      // [1]
 };
 
-// head_pool_fc: GlobalPooling<false> of the policy planes, GlobalPooling<true> of the value planes
-// (se_unit.cc:9-68) and the four small FCs (blas_forward_pipe.cc:473-481,501-507,524-532,549-555).
-// grid (ceil((P+V)/32), n): every CTA pools up to 32 channels of the head-entry conv output pv (C8: P policy + V value
-// channels) of one sample; the sample's last CTA runs the FCs.  Writes pint[n][P], pass5[n][5], misc15[n][15].
+// Per-sample output record handed back through the C ABI (sb_output in include/sayuri_b200.h).
+constexpr int kOutFloats = 2 * kMaxIntersections + 8;
+
+// head_fused: everything behind the head-entry convolution in ONE launch:
+//   GlobalPooling<false> of the policy planes, GlobalPooling<true> of the value planes (se_unit.cc:9-68), the four small
+//   FCs (blas_forward_pipe.cc:473-481,501-507,524-532,549-555), policy_conv += intermediate (:483-484), the P->5 and V->1
+//   1x1 convs (:487-499,535-547) and FillOutputs (:597-618).
+// grid (ceil((P+V)/32), n): every CTA pools up to 32 channels of pv (C8: P policy + V value channels) of one sample;
+// the sample's LAST CTA runs the FCs and then writes the sample's output record: only the requested policy channel
+// `offset` is evaluated, outputs are in the sample's NATIVE n x n order (the crop of batch_forward_pipe.cc:48-67) and
+// zero-filled up to 361, misc values gathered to {pass[offset], wdl0..2, stm(3), final_score(8), q_error(13),
+// score_error(14)}.
 __global__ void __launch_bounds__(256)
-head_pool_fc_kernel(const __half* __restrict__ pv_hi, const __half* __restrict__ pv_lo, bool split, int R,
-                    const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes, Geom g, int P, int V,
-                    HeadWeights hw, int act, float* pooled, int* counters, float* __restrict__ pint,
-                    float* __restrict__ pass5, float* __restrict__ misc15) {
+head_fused_kernel(const __half* __restrict__ pv_hi, const __half* __restrict__ pv_lo, bool split, int R,
+                  const uint8_t* __restrict__ mask, const int* __restrict__ board_sizes,
+                  const int* __restrict__ offsets, Geom g, int P, int V, HeadWeights hw, int act, float* pooled,
+                  int* counters, float* __restrict__ out) {
     extern __shared__ float sm[];
     __shared__ float s_part[128];
     __shared__ float s_sum[64], s_max[64];
+    __shared__ float s_pass[5], s_misc[15];
     __shared__ int s_flag;
     const int PV = P + V;
     const int b = blockIdx.y, bs = board_sizes[b];
@@ -433,95 +446,53 @@ head_pool_fc_kernel(const __half* __restrict__ pv_hi, const __half* __restrict__
         }
     }
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int o = warp; o < P + 3 * V; o += 8) {
-        if (o < P) {
-            float acc = 0.f;
-            for (int i = lane; i < 3 * P; i += 32) acc += hw.p_inter_w[o * 3 * P + i] * ppool[i];
-            acc = warp_sum(acc);
-            if (lane == 0) {
-                const float r = activate(acc + hw.p_inter_b[o], act);
-                spint[o] = r;
-                pint[(size_t)b * P + o] = r;
-            }
-        } else {
-            const int ov = o - P;
-            float acc = 0.f;
-            for (int i = lane; i < 3 * V; i += 32) acc += hw.v_inter_w[ov * 3 * V + i] * vpool[i];
-            acc = warp_sum(acc);
-            if (lane == 0) svint[ov] = activate(acc + hw.v_inter_b[ov], act);
-        }
-    }
+    fc_tail_8lanes(hw.p_inter_w, ppool, 3 * P, P, [&](int o, float v) { spint[o] = activate(v + hw.p_inter_b[o], act); });
+    fc_tail_8lanes(hw.v_inter_w, vpool, 3 * V, 3 * V, [&](int o, float v) { svint[o] = activate(v + hw.v_inter_b[o], act); });
     __syncthreads();
-    for (int o = warp; o < 20; o += 8) {
-        if (o < 5) {
-            float acc = 0.f;
-            for (int i = lane; i < P; i += 32) acc += hw.pass_w[o * P + i] * spint[i];
-            acc = warp_sum(acc);
-            if (lane == 0) pass5[(size_t)b * 5 + o] = acc + hw.pass_b[o];
-        } else {
-            const int om = o - 5;
-            float acc = 0.f;
-            for (int i = lane; i < 3 * V; i += 32) acc += hw.misc_w[om * 3 * V + i] * svint[i];
-            acc = warp_sum(acc);
-            if (lane == 0) misc15[(size_t)b * 15 + om] = acc + hw.misc_b[om];
-        }
-    }
-}
+    fc_tail_8lanes(hw.pass_w, spint, P, 5, [&](int o, float v) { s_pass[o] = v + hw.pass_b[o]; });
+    fc_tail_8lanes(hw.misc_w, svint, 3 * V, 15, [&](int o, float v) { s_misc[o] = v + hw.misc_b[o]; });
+    __syncthreads();
 
-// Per-sample output record handed back through the C ABI (sb_output in include/sayuri_b200.h).
-constexpr int kOutFloats = 2 * kMaxIntersections + 8;
-
-// head_out: policy_conv += intermediate (blas_forward_pipe.cc:483-484), the P->5 and V->1 1x1 convs
-// (:487-499,535-547) and FillOutputs (:597-618): only the requested policy channel `offset` is
-// evaluated, outputs are written in the sample's NATIVE n x n order (the crop of
-// batch_forward_pipe.cc:48-67) and zero-filled up to 361, misc values are gathered to
-// {pass[offset], wdl0..2, stm(3), final_score(8), q_error(13), score_error(14)}.
-__global__ void __launch_bounds__(384)
-head_out_kernel(const __half* __restrict__ pv_hi, const __half* __restrict__ pv_lo, bool split, int R,
-                const int* __restrict__ board_sizes, const int* __restrict__ offsets, Geom g, int P, int V, HeadWeights hw,
-                const float* __restrict__ pint, const float* __restrict__ pass5,
-                const float* __restrict__ misc15, float* __restrict__ out) {
-    const int b = blockIdx.x, i = threadIdx.x;
-    const int bs = board_sizes[b], off = offsets[b];
+    const int off = offsets[b];
     float* o = out + (size_t)b * kOutFloats;
-    if (i < kMaxIntersections) {
-        float prob = 0.f, own = 0.f;
-        if (i < bs * bs) {
-            const int y = i / bs, x = i - y * bs;
-            const int row = g.row(b, y, x);
-            prob = hw.prob_b[off];
-            own = hw.own_b[0];
-            for (int c0 = 0; c0 < P + V; c0 += 8) {     // P and V are multiples of 8: a chunk is all-policy or all-value
-                float v[8];
-                const size_t idx = act_index(row, c0, R);
-                load8(pv_hi + idx, pv_lo + idx, split, v);
-                if (c0 < P) {
+    for (int i = tid; i < kMaxIntersections + 8; i += 256) {
+        if (i < kMaxIntersections) {
+            float prob = 0.f, own = 0.f;
+            if (i < bs * bs) {
+                const int y = i / bs, x = i - y * bs;
+                const int row = g.row(b, y, x);
+                prob = hw.prob_b[off];
+                own = hw.own_b[0];
+                for (int c0 = 0; c0 < PV; c0 += 8) {     // P and V are multiples of 8: a chunk is all-policy or all-value
+                    float v[8];
+                    const size_t idx = act_index(row, c0, R);
+                    load8(pv_hi + idx, pv_lo + idx, split, v);
+                    if (c0 < P) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) prob += hw.prob_w[off * P + c0 + k] * (v[k] + pint[(size_t)b * P + c0 + k]);
-                } else {
+                        for (int k = 0; k < 8; ++k) prob += hw.prob_w[off * P + c0 + k] * (v[k] + spint[c0 + k]);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) own += hw.own_w[c0 - P + k] * v[k];
+                        for (int k = 0; k < 8; ++k) own += hw.own_w[c0 - P + k] * v[k];
+                    }
                 }
             }
+            o[i] = prob;
+            o[kMaxIntersections + i] = own;
+        } else {
+            const int k = i - kMaxIntersections;
+            float v;
+            switch (k) {
+                case 0: v = s_pass[off]; break;
+                case 1: v = s_misc[0]; break;
+                case 2: v = s_misc[1]; break;
+                case 3: v = s_misc[2]; break;
+                case 4: v = s_misc[3]; break;
+                case 5: v = s_misc[8]; break;
+                case 6: v = s_misc[13]; break;
+                default: v = s_misc[14]; break;
+            }
+            o[2 * kMaxIntersections + k] = v;
         }
-        o[i] = prob;
-        o[kMaxIntersections + i] = own;
-    } else if (i < kMaxIntersections + 8) {
-        const int k = i - kMaxIntersections;
-        const float* m = misc15 + (size_t)b * 15;
-        float v;
-        switch (k) {
-            case 0: v = pass5[(size_t)b * 5 + off]; break;
-            case 1: v = m[0]; break;
-            case 2: v = m[1]; break;
-            case 3: v = m[2]; break;
-            case 4: v = m[3]; break;
-            case 5: v = m[8]; break;
-            case 6: v = m[13]; break;
-            default: v = m[14]; break;
-        }
-        o[2 * kMaxIntersections + k] = v;
     }
 }
 

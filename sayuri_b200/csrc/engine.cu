@@ -18,6 +18,7 @@
 #include <climits>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -864,9 +865,10 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         if (se > 0) {
             mark();
             const size_t smem = ((size_t)3 * C + se) * sizeof(float);
-            se_pool_fc_kernel<<<dim3((C + 31) / 32, n), 256, smem, s.stream>>>(u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se,
-                                                                                F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
-                                                                                F(L.excite[b].b), act, s.pooled, s.counters, s.gb);
+            SB_DISPATCH_ACT(act, ACT, (se_pool_fc_kernel<ACT><<<dim3((C + 63) / 64, n), 256, smem, s.stream>>>(
+                                          u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se, F(L.squeeze[b].w),
+                                          F(L.squeeze[b].b), F(L.excite[b].w), F(L.excite[b].b), s.pooled, s.counters, s.gb,
+                                          e->conv_dbg)));
             SB_CUDA(cudaGetLastError());
             const size_t total = (size_t)n_rows * (C / 8);
             SB_DISPATCH_ACT(act, ACT, (se_apply_kernel<ACT><<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(
@@ -905,14 +907,11 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     {
         const int PV = P + V;
         const size_t smem = ((size_t)3 * P + 3 * V + P + 3 * V) * sizeof(float);
-        head_pool_fc_kernel<<<dim3((PV + 31) / 32, n), 256, smem, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, s.mask, d_sizes, g, P, V,
-                                                                              hw, act, s.pooled, s.counters, s.pint, s.pass5, s.misc15);
-        SB_CUDA(cudaGetLastError());
-        head_out_kernel<<<n, 384, 0, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, d_sizes, d_offsets, g, P, V, hw, s.pint,
-                                                 s.pass5, s.misc15, s.d_out);
+        head_fused_kernel<<<dim3((PV + 31) / 32, n), 256, smem, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, s.mask, d_sizes, d_offsets, g,
+                                                                            P, V, hw, act, s.pooled, s.counters, s.d_out);
         SB_CUDA(cudaGetLastError());
     }
-    e->launches += 2;
+    e->launches += 1;
     mark();
 }
 
@@ -1743,11 +1742,14 @@ int sb_time_forward(sb_engine* e, int gpu, int slot, int iters, int flush_l2, fl
                 CheckSlotError(s, cudaStreamSynchronize(s.stream), "profiled forward");
                 float total = 0.f, others = 0.f;
                 SB_CUDA(cudaEventElapsedTime(&total, s.ev_a, s.ev_b));
+                const bool verbose = pass == 4 && std::getenv("SB_PROFILE_GROUPS") != nullptr;
                 for (size_t i = 0; i + 1 < tm.ev.size(); i += 2) {
                     float ms = 0.f;
                     SB_CUDA(cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]));
                     others += ms;
+                    if (verbose) std::fprintf(stderr, "sb_time_forward: non-conv group %zu: %.1f us\n", i / 2, ms * 1e3f);
                 }
+                if (verbose) std::fprintf(stderr, "sb_time_forward: forward %.1f us, other kernels %.1f us\n", total * 1e3f, others * 1e3f);
                 samples.push_back(total - others);
                 launches = tm.conv_launches;
                 for (cudaEvent_t ev : tm.ev) cudaEventDestroy(ev);
