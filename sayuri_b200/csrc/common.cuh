@@ -30,6 +30,7 @@ constexpr int kMaxBoard = 19;    // /root/reference/src/game/types.h:5-7 (MAX_BO
 constexpr int kMaxIntersections = kMaxBoard * kMaxBoard;
 constexpr int kInputChannels = 43;   // /root/reference/src/neural/network_basic.h:10
 constexpr int kInputChannelsPadded = 64;
+constexpr int kMaxConvWidth = 512;   // widest conv output (Mixer feed-forward width of a 256-wide net is 384); bias staging in smem
 
 // element (row, c) of a C8 tensor with R rows
 __host__ __device__ inline size_t act_index(int row, int c, int R) {

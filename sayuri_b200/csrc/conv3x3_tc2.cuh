@@ -49,7 +49,7 @@ struct Conv2Cfg {
     static constexpr int kOffB = kNumSlabs * kSlabBytes;
     static constexpr int kOffBar = kOffB + kNumBStages * kBStageBytes;
     static constexpr int kOffBias = kOffBar + 512;
-    static constexpr int kSmemBytes = kOffBias + 256 * 4 + 1024;
+    static constexpr int kSmemBytes = kOffBias + kMaxConvWidth * 4 + 1024;
     static constexpr int kTmemCols = 512;
     // Epilogue column parts per TMEM lane quadrant = epilogue warps per scheduler.  2 on both rungs: 4 parts (16 epilogue
     // warps, 640 threads) measured 2 % SLOWER on the fp16 rung (265 k vs 271 k evals/s) and 13 % slower on 1x1-conv
@@ -188,7 +188,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int n_items = p.n_units;   // whole items + half units of the tail wave (conv_unit)
 
-    for (int i = threadIdx.x; i < p.cout && i < 256; i += blockDim.x) sbias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.cout && i < kMaxConvWidth; i += blockDim.x) sbias[i] = p.bias[i];
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < (int)kNA; ++i) {

@@ -1007,9 +1007,7 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
             if (ty < SB_BLOCK_RESIDUAL || ty > SB_BLOCK_MIXER) return Fail(nullptr, SB_ERR_INVALID, "unsupported block type");
             if (ty != SB_BLOCK_RESIDUAL) {
                 const int I = shape_only->inner_channels ? shape_only->inner_channels[b] : 0;
-                bool tiles = false;
-                for (int bn = 128; bn >= 16; bn -= 16) tiles = tiles || (I >= 16 && I <= 256 && I % 16 == 0 && I % bn == 0);
-                if (!tiles) return Fail(nullptr, SB_ERR_INVALID, "unsupported bottleneck / feed-forward width");
+                if (I < 8 || I > 512 || I % 8) return Fail(nullptr, SB_ERR_INVALID, "unsupported bottleneck / feed-forward width");
                 e->inner_channels[b] = I;
             }
             if (ty == SB_BLOCK_MIXER) {

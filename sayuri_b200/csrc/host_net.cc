@@ -292,12 +292,9 @@ bool ValidateNet(const HostNet& n, std::string& err) {
         return c.depthwise && c.in == 1 && c.out == ch && c.k >= 3 && c.k <= 15 && (c.k & 1) &&
                c.w.size() == static_cast<size_t>(ch) * c.k * c.k && c.b.size() == static_cast<size_t>(ch);
     };
-    auto width_ok = [](int w) {   // a conv output width the tensor-core kernel can tile: N tiles of a multiple of 16, <= 128
-        if (w < 16 || w > 256 || w % 16 != 0) return false;
-        for (int bn = 128; bn >= 16; bn -= 16)
-            if (w % bn == 0) return true;
-        return false;
-    };
+    // inner widths (bottleneck / feed-forward): any multiple of 8 up to 512 — weight rows are zero-padded to the UMMA
+    // N granule (16) and the epilogue stores only the real channels; the tower width itself stays a multiple of 16 <= 256
+    auto width_ok = [](int w) { return w >= 8 && w <= 512 && w % 8 == 0; };
     auto fc_ok = [](const HostFC& f, int in, int out) {
         return f.in == in && f.out == out && f.w.size() == static_cast<size_t>(in) * out && f.b.size() == static_cast<size_t>(out);
     };
@@ -306,7 +303,7 @@ bool ValidateNet(const HostNet& n, std::string& err) {
     if (n.input_channels != SB_INPUT_CHANNELS) { err = "the number of input channels is wrong"; return false; }
     if (n.act < 0 || n.act > 7) { err = "Unknown activation type."; return false; }
     if (C < 16 || C > 256 || C % 16 != 0) { err = "residual channels must be a multiple of 16 in [16, 256]"; return false; }
-    if (!width_ok(C)) { err = "residual channels above 128 must tile into N <= 128 (multiple of 16)"; return false; }
+    if (C > 256) { err = "residual channels above 256 are not supported"; return false; }
     if (P < 4 || V < 4 || (P + V) % 4 != 0 || P + V > 64) { err = "policy + value head channels must be a multiple of 4 and <= 64"; return false; }
     if (n.blocks < 0 || static_cast<int>(n.tower.size()) != n.blocks) { err = "tower size mismatch"; return false; }
     if (!conv_ok(n.input_conv, SB_INPUT_CHANNELS, C, 3)) { err = "the input layers are wrong"; return false; }
@@ -317,11 +314,11 @@ bool ValidateNet(const HostNet& n, std::string& err) {
             if (!conv_ok(k.convs[0], C, C, 3) || !conv_ok(k.convs[1], C, C, 3)) { err = "residual block " + std::to_string(b + 1) + " is wrong"; return false; }
         } else if (k.type == SB_BLOCK_MIXER) {
             const int F = k.inner;
-            if (!width_ok(F)) { err = "feed-forward channels of mixer block " + std::to_string(b + 1) + " (" + std::to_string(F) + ") cannot be tiled: need a multiple of 16 <= 256 with a divisor <= 128 that is a multiple of 16"; return false; }
+            if (!width_ok(F)) { err = "feed-forward channels of mixer block " + std::to_string(b + 1) + " (" + std::to_string(F) + ") must be a multiple of 8 in [8, 512]"; return false; }
             if (!dw_ok(k.convs[0], C) || !conv_ok(k.convs[1], C, F, 1) || !conv_ok(k.convs[2], F, C, 1)) { err = "the channels of mixer block " + std::to_string(b + 1) + " is wrong"; return false; }
         } else {
             const int I = k.inner;
-            if (!width_ok(I)) { err = "bottleneck channels must be a multiple of 16 in [16, 256] that tiles into N <= 128"; return false; }
+            if (!width_ok(I)) { err = "bottleneck channels must be a multiple of 8 in [8, 512]"; return false; }
             const size_t last = k.convs.size() - 1;
             if (!conv_ok(k.convs[0], C, I, 1) || !conv_ok(k.convs[last], I, C, 1)) { err = "the outer channels of bottleneck block " + std::to_string(b + 1) + " is wrong"; return false; }
             for (size_t q = 1; q < last; ++q)
