@@ -500,3 +500,38 @@ def test_wide_mixer_tower_with_replk_head_matches_oracle(eng, oracle_lib, prec_n
             _check(out[i], orc.forward(planes[i], bs, i), bs, atol=atol)
     finally:
         pipe.destroy()
+
+
+def test_batcher_stress_every_result_is_the_callers_own(eng, golden_weights_bin):
+    """64 threads hammer sb_eval with 24 different positions for ~4 000 calls in total, tiny batches and a short timer,
+    so batches close by both paths thousands of times: every returned record must be bit-identical to the reference
+    record of the position that was passed in (no cross-talk between ring entries, no stale batch re-use)."""
+    import threading
+    from sayuri_b200 import synth
+    n_pos = 24
+    sizes = [(19, 13, 9)[i % 3] for i in range(n_pos)]
+    planes = [synth.synth_positions(1, bs, seed=3000 + i)[0].ravel().copy() for i, bs in enumerate(sizes)]
+    offs = [i % 5 for i in range(n_pos)]
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 16, gpus=[0])
+    try:
+        ref = np.concatenate([pipe.batch_forward(0, planes[i:i + 12], sizes[i:i + 12], offs[i:i + 12]) for i in (0, 12)])
+        pipe.batcher_config(batch_size=5, wait_us=50)
+        bad = []
+
+        def worker(t):
+            rng = np.random.default_rng(t)
+            for _ in range(64):
+                i = int(rng.integers(n_pos))
+                o = pipe.eval(planes[i], sizes[i], offs[i])
+                if not (np.array_equal(o["probabilities"], ref[i]["probabilities"]) and np.array_equal(o["ownership"], ref[i]["ownership"])
+                        and o["pass_probability"] == ref[i]["pass_probability"] and o["board_size"] == sizes[i] and o["offset"] == offs[i]):
+                    bad.append((t, i))
+
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(64)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not bad, bad[:5]
+        st = pipe.batcher_stats()
+        assert st["positions"] == 64 * 64 and st["full"] > 0 and st["timer"] > 0
+    finally:
+        pipe.destroy()
