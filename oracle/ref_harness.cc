@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "config.h"
+#include "game/symmetry.h"
 #include "neural/blas/blas_forward_pipe.h"
 #include "neural/loader.h"
 #include "neural/network_basic.h"
@@ -143,6 +144,16 @@ long ref_time_forward(const float* planes, int n_pos, int board_size, int thread
     auto t1 = std::chrono::steady_clock::now();
     *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
     return total.load();
+}
+
+// Symmetry::TransformIndex (game/symmetry.h:35-37, tables built by symmetry.cc:97-123) for every cell of an N x N board:
+// the gather index of Encoder::SymmetryPlanes (encoder.cc:80-100) and the scatter index of Network::TransformResult
+// (network.cc:376-383).  Pins the oracle's index tables to the reference, bit-exactly.
+int ref_symmetry_table(int board_size, int symmetry, int* out) {
+    EnsureArgs();
+    if (board_size < 2 || board_size > 19 || symmetry < 0 || symmetry >= Symmetry::kNumSymmetris) return -1;
+    for (int i = 0; i < board_size * board_size; ++i) out[i] = Symmetry::Get().TransformIndex(board_size, symmetry, i);
+    return 0;
 }
 
 }  // extern "C"

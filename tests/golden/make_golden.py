@@ -73,6 +73,22 @@ def randomise_bn(net, seed):
                     mod.gamma.copy_(torch.rand(mod.gamma.shape, generator=g) * 0.8 + 0.6)
 
 
+def main_symmetry():
+    """Fourth fixture: Symmetry::TransformIndex of the compiled reference (game/symmetry.cc:97-123) for boards 2, 5, 9, 13,
+    19 and all 8 symmetries: the bit-exact pin of the gather / scatter index work (encoder.cc:80-100, network.cc:376-383)."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsayuri_ref_v3.so"))
+    lib.ref_symmetry_table.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    out = {}
+    for n in (2, 5, 9, 13, 19):
+        for sy in range(8):
+            t = np.zeros(n * n, dtype=np.int32)
+            assert lib.ref_symmetry_table(n, sy, t.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 0
+            out["sym_%d_%d" % (n, sy)] = t
+    np.savez_compressed(os.path.join(HERE, "golden_symmetry.npz"), **out)
+    print("wrote golden_symmetry.npz")
+
+
 def main_blocks():
     _fixture(CFG_BLOCKS, "btl_5bx32", 20260418, 9, 21)
     _fixture(CFG_MIXER, "mix_4bx32", 20260419, 10, 22)
@@ -204,7 +220,10 @@ def main():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "blocks":
-        main_blocks()      # only the second fixture (the first one stays byte-identical)
+        main_blocks()      # only the block-family fixtures (the first one stays byte-identical)
+    elif len(sys.argv) > 1 and sys.argv[1] == "symmetry":
+        main_symmetry()
     else:
         main()
         main_blocks()
+        main_symmetry()

@@ -135,6 +135,15 @@ def test_symmetry_tables_are_permutations_and_involutive_pairs(oracle_lib):
         assert np.array_equal(oracle_lib.Oracle.symmetry_table(n, 0), np.arange(n * n))
 
 
+def test_symmetry_tables_equal_the_reference_bit_exact(oracle_lib):
+    """tests/golden/golden_symmetry.npz = Symmetry::TransformIndex of the compiled reference for boards 2..19 x 8 symmetries."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_symmetry.npz"))
+    for n in (2, 5, 9, 13, 19):
+        for symm in range(8):
+            assert np.array_equal(oracle_lib.Oracle.symmetry_table(n, symm), g["sym_%d_%d" % (n, symm)]), (n, symm)
+
+
 def test_loader_rejects_out_of_scope_and_malformed(oracle_lib, tmp_path):
     from sayuri_b200 import synth
     info, layers = synth.synth_tensors(1, 16, 4, 4, seed=0, stack=["ResidualBlock"])
