@@ -232,6 +232,19 @@ int sb_time_forward(sb_engine* e, int gpu, int slot, int iters, int flush_l2, fl
                     float* conv_ms, int* conv_launches);
 long long sb_launch_count(const sb_engine* e);  /* kernels launched by this engine so far */
 
+/* ---- the weight-file reader on its own (host only, no CUDA): DNNLoader::FromFile + ProcessWeights -----------------
+ *      (src/neural/loader.cc:26-121,628-831).  Lets a host feed sb_create() from a file it parsed here, and lets the
+ *      CPU tests compare this reader with the oracle's, tensor by tensor, bit-exactly.                               */
+typedef struct sb_host_net sb_host_net;
+int sb_host_net_load(sb_host_net** out, const char* weights_path);          /* message: sb_last_error(NULL) */
+void sb_host_net_free(sb_host_net* h);
+/* Scalar description; the int arrays (NULL to skip) receive `blocks` entries each (capacity checked). */
+int sb_host_net_desc(const sb_host_net* h, sb_net_desc* desc, int* se_sizes, int* block_types, int* inner_channels,
+                     int* dw_kernels, int capacity);
+/* Tensor `idx` in the order of struct sb_weights, BN folded; returns its element count and sets *data (owned by `h`), or -1
+ * past the end. */
+long long sb_host_net_tensor(const sb_host_net* h, int idx, const float** data);
+
 /* ---- debugging / tests -------------------------------------------------------------------------- */
 /* Tower output of sample `sample` of the last batch on (gpu, slot) as fp32 NCHW [channels][n*n]. */
 int sb_debug_read_trunk(sb_engine* e, int gpu, int slot, int sample, float* out);

@@ -1646,6 +1646,85 @@ double sb_eval_throughput(sb_engine* e, const float* planes, int n_pos, int boar
     return (double)total.load() / el;
 }
 
+struct sb_host_net {
+    HostNet net;
+    std::vector<const std::vector<float>*> tensors;   // sb_weights order
+};
+
+int sb_host_net_load(sb_host_net** out, const char* weights_path) {
+    if (!out || !weights_path) return SB_ERR_INVALID;
+    *out = nullptr;
+    std::unique_ptr<sb_host_net> h(new sb_host_net);
+    std::string err;
+    if (!LoadWeightsFile(weights_path, h->net, err)) return Fail(nullptr, SB_ERR_IO, err);
+    auto conv = [&](const HostConv& c) {
+        h->tensors.push_back(&c.w);
+        h->tensors.push_back(&c.b);
+    };
+    auto fc = [&](const HostFC& f) {
+        h->tensors.push_back(&f.w);
+        h->tensors.push_back(&f.b);
+    };
+    const HostNet& n = h->net;
+    conv(n.input_conv);
+    for (const HostBlock& b : n.tower) {
+        for (const HostConv& c : b.convs) conv(c);
+        if (b.se_size > 0) {
+            fc(b.squeeze);
+            fc(b.excite);
+        }
+    }
+    conv(n.p_hd_conv);
+    if (n.replk) {
+        conv(n.p_dw_conv);
+        conv(n.p_pt_conv);
+    }
+    fc(n.p_inter_fc);
+    conv(n.prob_conv);
+    fc(n.pass_fc);
+    conv(n.v_hd_conv);
+    fc(n.v_inter_fc);
+    conv(n.v_ownership);
+    fc(n.v_misc);
+    *out = h.release();
+    return SB_OK;
+}
+
+void sb_host_net_free(sb_host_net* h) { delete h; }
+
+int sb_host_net_desc(const sb_host_net* h, sb_net_desc* d, int* se_sizes, int* block_types, int* inner_channels, int* dw_kernels,
+                     int capacity) {
+    if (!h || !d) return SB_ERR_INVALID;
+    const HostNet& n = h->net;
+    if ((se_sizes || block_types || inner_channels || dw_kernels) && capacity < n.blocks) return SB_ERR_INVALID;
+    d->version = n.version;
+    d->input_channels = n.input_channels;
+    d->blocks = n.blocks;
+    d->channels = n.channels;
+    d->policy_channels = n.P;
+    d->value_channels = n.V;
+    d->activation = n.act;
+    d->se_sizes = se_sizes;
+    d->block_types = block_types;
+    d->inner_channels = inner_channels;
+    d->dw_kernels = dw_kernels;
+    d->policy_head_type = n.replk ? SB_POLICY_HEAD_REPLK : SB_POLICY_HEAD_NORMAL;
+    d->policy_dw_kernel = n.replk ? n.p_dw_conv.k : 0;
+    for (int b = 0; b < n.blocks; ++b) {
+        if (se_sizes) se_sizes[b] = n.tower[b].se_size;
+        if (block_types) block_types[b] = n.tower[b].type;
+        if (inner_channels) inner_channels[b] = n.tower[b].inner;
+        if (dw_kernels) dw_kernels[b] = n.tower[b].dw_kernel();
+    }
+    return SB_OK;
+}
+
+long long sb_host_net_tensor(const sb_host_net* h, int idx, const float** data) {
+    if (!h || !data || idx < 0 || idx >= (int)h->tensors.size()) return -1;
+    *data = h->tensors[idx]->data();
+    return (long long)h->tensors[idx]->size();
+}
+
 void* sb_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {

@@ -85,7 +85,8 @@ ABI_SYMBOLS = [
     "sb_forward_batch", "sb_submit", "sb_wait", "sb_host_alloc", "sb_host_free", "sb_weights_blob",
     "sb_weights_export", "sb_weights_import",
     "sb_weights_checksum", "sb_time_forward", "sb_launch_count", "sb_debug_read_trunk", "sb_conv_stats", "sb_set_option",
-    "sb_get_block_desc", "sb_get_dw_desc", "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
+    "sb_get_block_desc", "sb_get_dw_desc", "sb_host_net_load", "sb_host_net_free", "sb_host_net_desc", "sb_host_net_tensor",
+    "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
 ]
 
 _lib = None
@@ -134,6 +135,12 @@ def load_library():
     lib.sb_debug_read_trunk.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F]
     lib.sb_conv_stats.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     lib.sb_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    lib.sb_host_net_load.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p]
+    lib.sb_host_net_free.argtypes = [vp]
+    lib.sb_host_net_free.restype = None
+    lib.sb_host_net_desc.argtypes = [vp, ctypes.POINTER(SbNetDesc), _I, _I, _I, _I, ctypes.c_int]
+    lib.sb_host_net_tensor.argtypes = [vp, ctypes.c_int, ctypes.POINTER(_F)]
+    lib.sb_host_net_tensor.restype = ctypes.c_longlong
     lib.sb_pack_position.argtypes = [_F, ctypes.c_int, ctypes.c_int, ctypes.POINTER(SbPackedPosition)]
     lib.sb_unpack_position.argtypes = [ctypes.POINTER(SbPackedPosition), _F]
     lib.sb_eval.argtypes = [vp, _F, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -143,6 +150,37 @@ def load_library():
     lib.sb_eval_throughput.restype = ctypes.c_double
     _lib = lib
     return lib
+
+
+def load_weights_file(path):
+    """sb_host_net_*: the engine's own weight-file reader (host only).  Returns (desc dict, [tensor, ...]) with the
+    tensors in sb_weights order, BN folded — directly usable with B200ForwardPipe.initialize_from_tensors."""
+    lib = load_library()
+    h = ctypes.c_void_p(None)
+    if lib.sb_host_net_load(ctypes.byref(h), str(path).encode()):
+        raise RuntimeError(lib.sb_last_error(None).decode())
+    try:
+        d = SbNetDesc()
+        se, ty, inner, dwk = ((ctypes.c_int * 1024)() for _ in range(4))
+        if lib.sb_host_net_desc(h, ctypes.byref(d), se, ty, inner, dwk, 1024):
+            raise RuntimeError("sb_host_net_desc failed")
+        nb = d.blocks
+        desc = dict(version=d.version, blocks=nb, channels=d.channels, P=d.policy_channels, V=d.value_channels,
+                    activation=d.activation, se_sizes=[se[i] for i in range(nb)], block_types=[ty[i] for i in range(nb)],
+                    inner_channels=[inner[i] for i in range(nb)], dw_kernels=[dwk[i] for i in range(nb)],
+                    policy_head_type=d.policy_head_type, policy_dw_kernel=d.policy_dw_kernel)
+        tensors = []
+        idx = 0
+        while True:
+            p = _F()
+            n = lib.sb_host_net_tensor(h, idx, ctypes.byref(p))
+            if n < 0:
+                break
+            tensors.append(np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, dtype=np.float32))
+            idx += 1
+        return desc, tensors
+    finally:
+        lib.sb_host_net_free(h)
 
 
 def pack_position(planes, board_size, offset=0):

@@ -84,3 +84,31 @@ def test_invalid_arguments_rejected(eng, golden_weights_bin):
     assert lib.sb_num_gpus(None) == 0
     assert lib.sb_submit(None, 0, 0, 1, None, 1, None, None) != 0
     assert lib.sb_wait(None, 0, 0, None) != 0
+
+
+@pytest.mark.parametrize("which", ["residual", "bottleneck", "mixer", "synthetic"])
+def test_engine_weight_reader_equals_oracle_reader_bit_exact(eng, oracle_lib, golden_weights_bin, golden_weights_txt, tmp_path, which):
+    """The product's own file reader + BN folding (host_net.cc) against the oracle's (oracle_forward.c), tensor by tensor,
+    bit for bit, for every block family / the RepLK head, text and binary formats (host only: runs without a GPU)."""
+    from sayuri_b200 import synth
+    golden_dir = os.path.dirname(golden_weights_bin)
+    if which == "residual":
+        paths = [golden_weights_bin, golden_weights_txt]
+    elif which == "bottleneck":
+        paths = [os.path.join(golden_dir, "ref_btl_5bx32.bin.txt")]
+    elif which == "mixer":
+        paths = [os.path.join(golden_dir, "ref_mix_4bx32.bin.txt")]
+    else:
+        p = str(tmp_path / "synth.txt")
+        synth.write_synth_net(p, (3, 48, 8, 24), seed=5, binary=False, stack=["MixerBlock-SE", "NestedBottleneckBlock", "BottleneckBlock-SE"],
+                              policy_head="RepLK", dw_kernel=5)
+        paths = [p]
+    for path in paths:
+        desc, tensors = eng.load_weights_file(path)
+        o = oracle_lib.Oracle(path)
+        ref = [t for pair in o.tensors() for t in pair]
+        assert len(tensors) == len(ref)
+        for i, (a, b) in enumerate(zip(tensors, ref)):
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (path, i)
+        assert (desc["blocks"], desc["channels"], desc["P"], desc["V"], desc["activation"]) == (o.blocks, o.channels, o.P, o.V, o.act)
+        assert sum(1 for s in desc["se_sizes"] if s > 0) == o.n_se

@@ -535,3 +535,26 @@ def test_batcher_stress_every_result_is_the_callers_own(eng, golden_weights_bin)
         assert st["positions"] == 64 * 64 and st["full"] > 0 and st["timer"] > 0
     finally:
         pipe.destroy()
+
+
+@pytest.mark.parametrize("fixture", ["ref_3bx32.bin.txt", "ref_btl_5bx32.bin.txt", "ref_mix_4bx32.bin.txt"])
+def test_create_from_tensors_equals_create_from_file(eng, golden_weights_bin, fixture):
+    """sb_create (net description + folded tensors in loader order: what the C++ shim passes from DNNWeights) builds the
+    same engine as sb_create_from_file, for every block family and both policy heads: bit-identical outputs and blob."""
+    from sayuri_b200 import synth
+    path = os.path.join(os.path.dirname(golden_weights_bin), fixture)
+    desc, tensors = eng.load_weights_file(path)
+    sizes = [19, 13, 9, 19]
+    planes = [synth.synth_positions(1, bs, seed=600 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    a = eng.B200ForwardPipe().initialize(path, 19, 4, gpus=[0])
+    b = eng.B200ForwardPipe().initialize_from_tensors(desc, tensors, 19, 4, gpus=[0])
+    try:
+        assert a.weights_checksum() == b.weights_checksum()
+        oa = a.batch_forward(0, planes, sizes, [0, 1, 2, 3])
+        ob = b.batch_forward(0, planes, sizes, [0, 1, 2, 3])
+        for f in FIELDS:
+            assert np.array_equal(oa[f], ob[f]), f
+        assert a.net_desc() == b.net_desc()
+    finally:
+        a.destroy()
+        b.destroy()
