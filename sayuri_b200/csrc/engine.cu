@@ -386,7 +386,7 @@ struct HostBatch {
     std::atomic<int> any_raw{0};
     int rc = 0;
     std::string err;
-    std::chrono::steady_clock::time_point first;
+    std::chrono::steady_clock::time_point first, last;   // arrival of the first / the latest position
 };
 
 struct Batcher {
@@ -399,8 +399,11 @@ struct Batcher {
     int fill = -1;
     int batch_size = 0;
     int wait_us = 200;                   // configured ceiling (reference default gpu_waittime = 2 ms, config.cc:59)
-    int cur_wait_us = 200;               // adaptive: 0 after a futile timer close, restored while idle (batch_forward_pipe.cc:120-147)
+    int cur_wait_us = 200;               // adaptive (cf. batch_forward_pipe.cc:120-147): halved when a timer close saw no
+                                         // arrival during the second half of the wait, doubled when batches fill up
     bool quit = false;
+    std::vector<int> in_flight;          // per replica: batches currently running on that GPU (under m)
+    std::vector<std::chrono::steady_clock::time_point> last_finish;   // per replica: when its latest batch was published
     std::vector<std::thread> workers;
     std::atomic<long long> n_batches{0}, n_positions{0}, n_full{0}, n_timer{0}, n_raw{0};
 };
@@ -1247,11 +1250,23 @@ static void BatchWorker(sb_engine* e, int gpu, int k) {
                 }
                 if (B.fill >= 0 && B.ring[B.fill]->count > 0) {
                     HostBatch& hb = *B.ring[B.fill];
-                    const auto deadline = hb.first + std::chrono::microseconds(B.cur_wait_us);
-                    if (std::chrono::steady_clock::now() >= deadline) {
-                        // closed by the timer: if nothing joined while we waited the traffic is low or the front-end is
-                        // CPU-bound, so stop waiting (batch_forward_pipe.cc:139-143)
-                        if (hb.count <= 1 && B.cur_wait_us > 0) B.cur_wait_us = 0;
+                    if (B.in_flight[gpu] > 0) {
+                        // this GPU is busy (forwards of its slots are chained, a second one could not start anyway): let
+                        // the partial batch grow until it is full or the running batch has finished — with few search
+                        // threads this is what keeps all of them in ONE batch instead of two half-size ones
+                        B.cv_work.wait(lk);
+                        continue;
+                    }
+                    // the timer runs from the batch's first position or, if later, from the moment this GPU published its
+                    // previous batch: the callers it just released need a few tens of microseconds to come back, and
+                    // closing before that splits a handful of search threads into two alternating half-size batches
+                    const auto deadline = std::max(hb.first, B.last_finish[gpu]) + std::chrono::microseconds(B.cur_wait_us);
+                    const auto now = std::chrono::steady_clock::now();
+                    if (now >= deadline) {
+                        // closed by the timer.  If nothing joined during the second half of the wait, every caller that was
+                        // going to come is already in (few search threads, or a CPU-bound front-end): waiting that long was
+                        // futile, halve it (the reference drops its wait to zero in this case, batch_forward_pipe.cc:139-143)
+                        if (now - hb.last > std::chrono::microseconds(B.cur_wait_us / 2)) B.cur_wait_us /= 2;
                         idx = CloseFill(B);
                         B.n_timer++;
                         break;
@@ -1263,6 +1278,7 @@ static void BatchWorker(sb_engine* e, int gpu, int k) {
                     B.cv_work.wait(lk);
                 }
             }
+            B.in_flight[gpu]++;
         }
         HostBatch& hb = *B.ring[idx];
         while (hb.ready.load(std::memory_order_acquire) < hb.count) std::this_thread::yield();   // packers still writing
@@ -1271,6 +1287,12 @@ static void BatchWorker(sb_engine* e, int gpu, int k) {
         B.n_positions += hb.count;
         hb.done_seq.fetch_add(1, std::memory_order_release);
         FutexWakeAll(&hb.done_seq);
+        {
+            std::lock_guard<std::mutex> lk(B.m);
+            B.in_flight[gpu]--;
+            B.last_finish[gpu] = std::chrono::steady_clock::now();
+        }
+        B.cv_work.notify_all();   // a partial batch that was growing behind this one may be closed now
     }
 }
 
@@ -1308,7 +1330,10 @@ static void StartBatcher(sb_engine* e) {
     B->batch_size = e->batcher_batch > 0 ? std::min(e->batcher_batch, e->max_batch) : e->max_batch;
     B->wait_us = B->cur_wait_us = e->batcher_wait_us;
     const int n_workers = (int)e->replicas.size() * kBatcherSlots;
-    const int n_ring = n_workers + 2;
+    // one batch per worker in flight, one filling, one spare — plus enough further entries that a few thousand blocked
+    // callers all find a slot: callers that find no FILLING batch sleep on one condition variable and are all woken
+    // when a batch is recycled (measured: 4096 callers on a 4 x 256 ring ran 10x slower than 256 callers)
+    const int n_ring = n_workers + 2 + std::min(14, std::max(0, 4096 / std::max(1, e->max_batch)));
     for (int i = 0; i < n_ring; ++i) {
         std::unique_ptr<HostBatch> hb(new HostBatch);
         SB_CUDA(cudaHostAlloc(&hb->rec, (size_t)e->max_batch * sizeof(sb_packed_position), cudaHostAllocPortable));
@@ -1317,6 +1342,8 @@ static void StartBatcher(sb_engine* e) {
         if (i > 0) B->free_list.push_back(i);
     }
     B->fill = 0;
+    B->in_flight.assign(e->replicas.size(), 0);
+    B->last_finish.assign(e->replicas.size(), std::chrono::steady_clock::now());
     for (Replica& r : e->replicas) AllocSlotVec(e, r, r.bslots, kBatcherSlots);
     e->batcher = std::move(B);
     for (int g2 = 0; g2 < (int)e->replicas.size(); ++g2)
@@ -1348,8 +1375,11 @@ static int EvalImpl(sb_engine* e, const float* planes, int board_size, int offse
         hb = B.ring[idx].get();
         i = hb->count++;
         seq0 = hb->done_seq.load(std::memory_order_relaxed);
-        if (i == 0) hb->first = std::chrono::steady_clock::now();
+        hb->last = std::chrono::steady_clock::now();
+        if (i == 0) hb->first = hb->last;
         if (hb->count >= B.batch_size) {
+            // filled before its timer: traffic is high, a longer wait costs nothing and keeps batches full
+            B.cur_wait_us = std::min(B.wait_us, B.cur_wait_us * 2 + 10);
             B.closed.push_back(CloseFill(B));
             B.n_full++;
             B.cv_work.notify_one();
