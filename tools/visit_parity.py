@@ -44,9 +44,14 @@ def main():
     ap.add_argument("--playouts", type=int, default=400)
     ap.add_argument("--moves", type=int, default=6)
     ap.add_argument("--seeds", default="1,2,3")
+    ap.add_argument("--weights", default=None, help="an existing weight file instead of a synthetic --net")
     a = ap.parse_args()
-    w = os.path.join(tempfile.gettempdir(), "vp_%s.bin" % a.net)
-    synth.write_synth_net(w, a.net, seed=11)
+    if a.weights:
+        w = a.weights
+        a.net = os.path.basename(w)
+    else:
+        w = os.path.join(tempfile.gettempdir(), "vp_%s.bin" % a.net)
+        synth.write_synth_net(w, a.net, seed=11)
     gtp = "boardsize %d\nclear_board\n" % a.board + "".join("genmove %s\n" % ("b" if i % 2 == 0 else "w") for i in range(a.moves)) + "quit\n"
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "sayuri_eigen_det")
     our_bin = os.path.join(ROOT, "oracle", "_ref", "sayuri_b200_det")
