@@ -25,4 +25,4 @@ print("$1 19x19 10bx128 -p 400: %d games in %.1f s -> %.1f games/hour, %.0f NN e
 PY
 }
 run "engine-batcher" "SAYURI_B200_REF_BATCHER=0" | tee gpurun_out/selfplay19.log
-run "reference-batcher" "SAYURI_B200_REF_BATCHER=1" | tee -a gpurun_out/selfplay19.log
+if [ "${2:-both}" = "both" ]; then run "reference-batcher" "SAYURI_B200_REF_BATCHER=1" | tee -a gpurun_out/selfplay19.log; fi
