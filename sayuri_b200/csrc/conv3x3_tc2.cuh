@@ -19,11 +19,14 @@
 
 namespace sb {
 
+// Split rung: 2 activation-slab buffers and a 12-stage weight ring measured best (profiles/r01s2_ring_depth.log: +2.4 % on
+// 10bx128, +3.5 % on 20bx256 over 3 slabs + 8 stages; 16 stages: +2 % / +3 %) — the weight stream is what the MMA
+// issuer waits for, a third slab buffer is not.  Overridable for experiments.
 #ifndef SB_TC2_NA
-#define SB_TC2_NA 3      // activation-slab buffers
+#define SB_TC2_NA 2      // activation-slab buffers (split rung)
 #endif
 #ifndef SB_TC2_NB
-#define SB_TC2_NB 8      // weight-stage ring depth (<= 16)
+#define SB_TC2_NB 12     // weight-stage ring depth (split rung, <= 18)
 #endif
 constexpr int kTileRows2 = 128;                              // rows per CTA per item
 constexpr int kSlabRows2 = kTileRows2 + 2 * kSlabMargin;     // 176
@@ -40,7 +43,7 @@ struct Conv2Cfg {
     static constexpr int kParts = SPLIT ? 2 : 1;
     static constexpr int kSlabPartBytes = kSlabRows2 * 128;          // [8 chunks][176 rows][16 B]
     static constexpr int kSlabBytes = kParts * kSlabPartBytes;
-    static constexpr int kNumSlabs = SB_TC2_NA;
+    static constexpr int kNumSlabs = SPLIT ? SB_TC2_NA : 3;
     static constexpr int kBStageBytes = 64 * 128;                    // this CTA's half: up to 64 rows x 64 fp16
     // fp16 rung: 18 stages x 8 KB hold ALL of this CTA's weights of a C <= 128 layer (9 taps x 2 k-halves): they are
     // then loaded once per launch and stay resident (ConvParams::resident), instead of being re-streamed for every
