@@ -245,7 +245,11 @@ def run_ours(args, rank, local_rank, world):
     # (sb_time_forward brackets the NON-convolution kernels of a forward with CUDA events on the engine's stream and
     #  subtracts them from the forward's duration, median of 5 forwards, L2 flushed: the conv launches keep their
     #  programmatic-dependent-launch overlap exactly as in the timed steps)
-    _, conv_ms, conv_n = pipe.time_forward(0, 0, 0, flush_l2=True, profile_conv=True)
+    prof_ms, conv_ms_prof, conv_n = pipe.time_forward(0, 0, 0, flush_l2=True, profile_conv=True)
+    # the profiling pass runs under event overhead and a different power state: take its SHARE of conv time and apply
+    # it to the timed steps' own duration
+    conv_share = conv_ms_prof / float(prof_ms[0]) if len(prof_ms) and prof_ms[0] > 0 else None
+    conv_ms = conv_share * float(ms.mean()) if conv_share else conv_ms_prof
     peaks = measured_peaks()
     conv_flops = conv3x3_flops_per_eval(blocks, C, P, V) * B
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
@@ -259,10 +263,10 @@ def run_ours(args, rank, local_rank, world):
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel": "conv3x3_tc2_kernel<%s, mish> (tcgen05 cta_group::2)" % ("split" if precision == engine.PRECISION_FP32_SPLIT else "fp16"),
                 "launches_per_step": conv_n, "kernel_ms_per_step": conv_ms,
-                "kernel_share_of_step": conv_ms / float(ms.mean()) if len(ms) else None,
+                "kernel_share_of_step": conv_share,
                 "algorithmic_flops_per_launch_avg": conv_flops / max(conv_n, 1),
                 "peak_source": peaks["source"] + ", dense bf16/fp16 sustained; kernel timed inside the step",
-                "how": "achieved = algorithmic flops of the %d conv launches of a step / (step time - time of the other kernels, CUDA events on the engine's stream, median of 5 L2-flushed forwards)" % conv_n,
+                "how": "achieved = algorithmic flops of the %d conv launches of a step / (kernel_share_of_step x ms_per_step); the share comes from extra L2-flushed forwards (median of 5) whose non-conv kernels are bracketed with CUDA events on the engine's stream, so the conv launches keep their dependent-launch overlap" % conv_n,
                 "tensor_flops_issued_per_algorithmic": 3 * (400.0 / 361.0) if precision == engine.PRECISION_FP32_SPLIT else (400.0 / 361.0),
                 "note": "fp32-faithful rung issues 3 fp16 MMAs per algorithmic MAC (hi*hi + lo*hi + hi*lo) on a 400-row/361-cell canvas"}
 

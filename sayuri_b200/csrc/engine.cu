@@ -1837,7 +1837,7 @@ int sb_time_forward(sb_engine* e, int gpu, int slot, int iters, int flush_l2, fl
         }
         if (conv_ms || conv_launches) {
             // conv kernel time = forward time - time of the bracketed non-convolution kernel groups, median of 5 passes
-            std::vector<float> samples;
+            std::vector<float> samples, totals;
             int launches = 0;
             for (int pass = 0; pass < 5; ++pass) {
                 ConvTimer tm;
@@ -1858,9 +1858,17 @@ int sb_time_forward(sb_engine* e, int gpu, int slot, int iters, int flush_l2, fl
                 }
                 if (verbose) std::fprintf(stderr, "sb_time_forward: forward %.1f us, other kernels %.1f us\n", total * 1e3f, others * 1e3f);
                 samples.push_back(total - others);
+                totals.push_back(total);
                 launches = tm.conv_launches;
                 for (cudaEvent_t ev : tm.ev) cudaEventDestroy(ev);
             }
+            // report the pass with the median conv time, and (iters == 0) that pass's whole-forward time in ms_each[0] so
+            // that the caller can apply the conv SHARE of this pass to its own timed steps
+            std::vector<size_t> order(samples.size());
+            for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return samples[a] < samples[b]; });
+            const size_t mid = order[order.size() / 2];
+            if (iters == 0 && ms_each) ms_each[0] = totals[mid];
             std::sort(samples.begin(), samples.end());
             if (conv_ms) *conv_ms = samples[samples.size() / 2];
             if (conv_launches) *conv_launches = launches;

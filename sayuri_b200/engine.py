@@ -428,7 +428,8 @@ class B200ForwardPipe:
         self._check(self._lib.sb_time_forward(self._h, gpu, slot, iters, int(flush_l2), ms.ctypes.data_as(_F),
                                               ctypes.byref(conv_ms) if profile_conv else None,
                                               ctypes.byref(conv_n) if profile_conv else None))
-        return ms[:iters], conv_ms.value, conv_n.value
+        # with iters == 0 and profile_conv, ms[0] holds the whole-forward time of the profiling pass conv_ms comes from
+        return (ms[:iters] if iters > 0 or not profile_conv else ms[:1]), conv_ms.value, conv_n.value
 
     def launch_count(self):
         return int(self._lib.sb_launch_count(self._h))
