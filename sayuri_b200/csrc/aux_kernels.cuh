@@ -45,6 +45,8 @@ __global__ void unpack_planes_kernel(const float* __restrict__ planes, size_t sa
                                      const int* __restrict__ board_sizes, Geom g, int n, int n_rows, int R,
                                      __half* __restrict__ hi, __half* __restrict__ lo, bool split,
                                      uint8_t* __restrict__ mask) {
+    pdl_launch_dependents();
+    pdl_wait();   // the canvas may still be read by the previous forward's input convolution
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = idx / n_rows, r = idx - cg * n_rows;   // rows fastest: coalesced 16-byte pieces
     if (cg >= 8) return;
@@ -72,6 +74,8 @@ __global__ void unpack_packed_kernel(const sb_packed_position* __restrict__ rec,
                                      size_t sample_stride, Geom g, int n, int n_rows, int R, int max_batch,
                                      __half* __restrict__ hi, __half* __restrict__ lo, bool split,
                                      uint8_t* __restrict__ mask, int* __restrict__ meta) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n) {
         meta[idx] = rec[idx].board_size;
@@ -227,6 +231,8 @@ se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_
     __shared__ float s_part[128];
     __shared__ float s_sum[64], s_max[64];
     __shared__ int s_flag;
+    pdl_launch_dependents();
+    pdl_wait();   // u is the previous convolution's output
     const int b = blockIdx.y;
     const int chunk0 = blockIdx.x * 8;          // 8 chunks = 64 channels per CTA: 2 CTAs per sample at C = 128, so that
     const int ncl = min(8, (C >> 3) - chunk0);  // the whole grid is resident at once (48 registers: 5 CTAs per SM)
@@ -267,6 +273,8 @@ __global__ void se_apply_kernel(__half* __restrict__ u_hi, __half* __restrict__ 
                                 const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, bool split,
                                 const uint8_t* __restrict__ mask, const float* __restrict__ gb, Geom g, int C,
                                 int R, int n_rows) {
+    pdl_launch_dependents();
+    pdl_wait();   // gb comes from se_pool_fc
     const int groups = C >> 3;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = (int)(idx / n_rows), r = (int)(idx - (size_t)cg * n_rows);   // rows fastest
@@ -414,6 +422,8 @@ head_fused_kernel(const __half* __restrict__ pv_hi, const __half* __restrict__ p
     __shared__ float s_sum[64], s_max[64];
     __shared__ float s_pass[5], s_misc[15];
     __shared__ int s_flag;
+    pdl_launch_dependents();
+    pdl_wait();   // pv is the head-entry convolution's output
     const int PV = P + V;
     const int b = blockIdx.y, bs = board_sizes[b];
     const int chunk0 = blockIdx.x * 4;

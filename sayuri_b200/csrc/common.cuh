@@ -47,6 +47,14 @@ struct Geom {
     __host__ __device__ int rows_alloc(int max_batch) const { return kGuardRows + n_super(max_batch) * kSuperRows + 64; }
 };
 
+// ---- Programmatic dependent launch ------------------------------------------------------------------------------
+// Every kernel of a forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the CTAs of kernel
+// k+1 become resident as soon as SMs free up, run whatever does not depend on kernel k (for the convolution: barrier
+// init, TMEM alloc, bias, first WEIGHT stages — constants) and block in griddepcontrol.wait only before touching
+// activations written (or still read) by kernel k; the launch latency and the prologue disappear behind kernel k's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- Activations: same ints and formulas as /root/reference/src/neural/activation.h:8-17,43-59 --
 enum Act : int { kIdentity = 0, kReLU = 1, kELU = 2, kSELU = 3, kGELU = 4, kMISH = 5, kSwish = 6, kHardSwish = 7 };
 

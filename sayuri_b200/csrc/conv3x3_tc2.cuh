@@ -31,13 +31,6 @@ namespace sb {
 constexpr int kTileRows2 = 128;                              // rows per CTA per item
 constexpr int kSlabRows2 = kTileRows2 + 2 * kSlabMargin;     // 176
 
-// Programmatic dependent launch: consecutive convolutions of a forward are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of layer L+1 become resident as soon as the CTAs of
-// layer L leave their SM, run their prologue (barrier init, TMEM alloc, bias, first WEIGHT stages: constants) and
-// block in griddepcontrol.wait only before touching activations written (or still read) by layer L.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 template <bool SPLIT>
 struct Conv2Cfg {
     static constexpr int kParts = SPLIT ? 2 : 1;

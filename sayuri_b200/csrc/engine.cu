@@ -436,6 +436,8 @@ struct sb_engine {
     int chain_forwards = 1;      // forwards of different slots of a replica run back to back, never interleaved
     int small_batch_split = 1;   // narrower N tiles when a batch does not fill one wave of CTA pairs
     int use_pdl = 1;     // programmatic dependent launch between consecutive conv3x3_tc2 launches
+    int pdl_aux = 1;     // ... and for the unpack / SE / head kernels between them: 0 off, 1 for batches <= 64 (measured:
+                         // -2.0..-2.5 % per forward at batch 32, +-1 % noise at batch 256; profiles/r01s2_pdl_aux_ab.md), 2 always
     int tail_split = 1;  // split the items of a partial last wave into N-halves (conv3x3_tc2)
     int pack_inputs = 1; // pageable inputs travel as compact exact records (host_pack.cc); 0 = always fp32 staging
     int pack_threads = 4;
@@ -784,6 +786,23 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
     e->launches++;
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait() in common.cuh).
+template <typename... KArgs, typename... Args>
+static void LaunchPdl(sb_engine* e, int n, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                      Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (e->use_pdl && (e->pdl_aux == 2 || (e->pdl_aux == 1 && n <= 64))) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SB_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+
 static void LaunchDw(sb_engine* e, Slot& s, const DwLayout& d, const uint8_t* blob, const ActBuf& in, ActBuf& out, int act,
                      bool add_input, int n, int n_rows) {
     const dim3 grid((n_rows + 127) / 128, d.ch / 8);
@@ -815,12 +834,11 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     {   // input planes -> canvas
         const int threads = n_rows * 8;
         if (s.packed) {
-            unpack_packed_kernel<<<(threads + 255) / 256, 256, 0, s.stream>>>(s.d_packed, s.d_in, (size_t)SB_PLANE_FLOATS, g, n,
-                                                                              n_rows, s.in.rows, e->max_batch, s.in.hi, s.in.lo,
-                                                                              split, s.mask, s.d_meta);
+            LaunchPdl(e, n, unpack_packed_kernel, dim3((threads + 255) / 256), dim3(256), 0, s.stream, s.d_packed, s.d_in,
+                      (size_t)SB_PLANE_FLOATS, g, n, n_rows, s.in.rows, e->max_batch, s.in.hi, s.in.lo, split, s.mask, s.d_meta);
         } else {
-            unpack_planes_kernel<<<(threads + 255) / 256, 256, 0, s.stream>>>(s.d_in, (size_t)SB_PLANE_FLOATS, d_sizes, g, n,
-                                                                              n_rows, s.in.rows, s.in.hi, s.in.lo, split, s.mask);
+            LaunchPdl(e, n, unpack_planes_kernel, dim3((threads + 255) / 256), dim3(256), 0, s.stream, s.d_in,
+                      (size_t)SB_PLANE_FLOATS, d_sizes, g, n, n_rows, s.in.rows, s.in.hi, s.in.lo, split, s.mask);
         }
         SB_CUDA(cudaGetLastError());
         e->launches++;
@@ -868,14 +886,15 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         if (se > 0) {
             mark();
             const size_t smem = ((size_t)3 * C + se) * sizeof(float);
-            SB_DISPATCH_ACT(act, ACT, (se_pool_fc_kernel<ACT><<<dim3((C + 63) / 64, n), 256, smem, s.stream>>>(
-                                          u->hi, u->lo, split, s.mask, d_sizes, g, C, u->rows, se, F(L.squeeze[b].w),
-                                          F(L.squeeze[b].b), F(L.excite[b].w), F(L.excite[b].b), s.pooled, s.counters, s.gb,
-                                          e->conv_dbg)));
+            SB_DISPATCH_ACT(act, ACT, LaunchPdl(e, n, se_pool_fc_kernel<ACT>, dim3((C + 63) / 64, n), dim3(256), smem, s.stream,
+                                                (const __half*)u->hi, (const __half*)u->lo, split, (const uint8_t*)s.mask, d_sizes, g, C,
+                                                u->rows, se, F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
+                                                F(L.excite[b].b), s.pooled, s.counters, s.gb, e->conv_dbg));
             SB_CUDA(cudaGetLastError());
             const size_t total = (size_t)n_rows * (C / 8);
-            SB_DISPATCH_ACT(act, ACT, (se_apply_kernel<ACT><<<(unsigned)((total + 255) / 256), 256, 0, s.stream>>>(
-                                          u->hi, u->lo, se_skip->hi, se_skip->lo, split, s.mask, s.gb, g, C, u->rows, n_rows)));
+            SB_DISPATCH_ACT(act, ACT, LaunchPdl(e, n, se_apply_kernel<ACT>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s.stream,
+                                                u->hi, u->lo, (const __half*)se_skip->hi, (const __half*)se_skip->lo, split,
+                                                (const uint8_t*)s.mask, (const float*)s.gb, g, C, u->rows, n_rows));
             SB_CUDA(cudaGetLastError());
             e->launches += 2;
             mark();
@@ -910,8 +929,9 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     {
         const int PV = P + V;
         const size_t smem = ((size_t)3 * P + 3 * V + P + 3 * V) * sizeof(float);
-        head_fused_kernel<<<dim3((PV + 31) / 32, n), 256, smem, s.stream>>>(s.pv.hi, s.pv.lo, split, s.pv.rows, s.mask, d_sizes, d_offsets, g,
-                                                                            P, V, hw, act, s.pooled, s.counters, s.d_out);
+        LaunchPdl(e, n, head_fused_kernel, dim3((PV + 31) / 32, n), dim3(256), smem, s.stream, (const __half*)s.pv.hi,
+                  (const __half*)s.pv.lo, split, s.pv.rows, (const uint8_t*)s.mask, d_sizes, d_offsets, g, P, V, hw, act, s.pooled,
+                  s.counters, s.d_out);
         SB_CUDA(cudaGetLastError());
     }
     e->launches += 1;
@@ -1964,6 +1984,10 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     }
     if (!std::strcmp(key, "pdl")) {
         e->use_pdl = value ? 1 : 0;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "pdl_aux")) {
+        e->pdl_aux = value < 0 ? 0 : value > 2 ? 2 : value;
         return SB_OK;
     }
     if (!std::strcmp(key, "tail_split")) {

@@ -398,12 +398,13 @@ def test_scheduling_knobs_do_not_change_a_single_bit(eng):
             try:
                 base = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
                 assert np.isfinite(base["probabilities"]).all()
-                for knob in ("resident_weights", "pdl", "small_batch_split", "chain_forwards"):
-                    pipe.set_option(knob, 0)
-                    other = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
-                    pipe.set_option(knob, 1)
-                    for f in FIELDS:
-                        assert np.array_equal(base[f], other[f]), (prec, n, knob, f)
+                for knob in ("resident_weights", "pdl", "pdl_aux", "small_batch_split", "chain_forwards"):
+                    for value in ((0, 2) if knob == "pdl_aux" else (0,)):   # pdl_aux: 0 off, 1 small batches only, 2 always
+                        pipe.set_option(knob, value)
+                        other = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
+                        pipe.set_option(knob, 1)
+                        for f in FIELDS:
+                            assert np.array_equal(base[f], other[f]), (prec, n, knob, value, f)
             finally:
                 pipe.destroy()
 
