@@ -1,0 +1,229 @@
+// TEST INFRASTRUCTURE.  Links the UNMODIFIED reference objects (oracle/_ref/obj_v3) and compares, in one process,
+//   Board::ComputePassAliveArea   /root/reference/src/game/board.cc:1720-1901   (private: reached with the usual
+//                                                                                 `#define private public` test trick)
+// with sb_go::PassAliveArea (sayuri_b200/csrc/host_go/pass_alive.h) on every position of seeded random games.
+//   pass_alive_harness check <games> <seed>          all board sizes 2..19, both colours, the four flag combinations
+//   pass_alive_harness time  <games> <seed> <size>   ns per call of each, (true, true) as all callers use
+//   pass_alive_harness digest <games> <seed>         FNV-1a over Board::ComputeSafeArea and Board::ComputeScoreArea (public
+//                                                    callers) on every position, each asked twice as the encoder does:
+//                                                    the build with the link-time override (pass_alive_harness_fast,
+//                                                    oracle/Makefile) must print the same digest as the plain one
+//   pass_alive_harness dump  <games> <seed> <file>   fixture file for tests/test_pass_alive.py (positions + the
+//                                                    REFERENCE's answers), format in tests/test_pass_alive.py
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <array>
+#include <functional>
+#include <memory>
+#include <sstream>
+#include <iostream>
+
+#define private public
+#include "game/board.h"
+#undef private
+#include "config.h"
+
+#include "../sayuri_b200/csrc/host_go/pass_alive.h"
+
+namespace {
+
+std::uint64_t SplitMix(std::uint64_t& s) {
+    std::uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// One random game; `visit` sees the board after every move.  Mostly eye-respecting play (so that living groups and
+// dead stones appear), sometimes not (so that eyes get filled and big captures happen).
+template <typename F> void PlayGame(int size, std::uint64_t& rng, F&& visit) {
+    Board board;
+    board.Reset(size);
+    int color = kBlack, passes = 0;
+    const int max_moves = size * size * 3;
+    const bool respect_eyes = SplitMix(rng) % 8 != 0;
+    visit(board);
+    for (int move = 0; move < max_moves && passes < 2; ++move) {
+        std::vector<int> cand;
+        for (int i = 0; i < board.GetEmptyCount(); ++i) {
+            const int vtx = board.GetEmpty(i);
+            if (!board.IsLegalMove(vtx, color)) continue;
+            if (respect_eyes && board.IsRealEye(vtx, color)) continue;
+            cand.push_back(vtx);
+        }
+        if (cand.empty() || SplitMix(rng) % 97 == 0) {
+            board.PlayMoveAssumeLegal(kPass, color);
+            ++passes;
+        } else {
+            board.PlayMoveAssumeLegal(cand[SplitMix(rng) % cand.size()], color);
+            passes = 0;
+        }
+        color = !color;
+        visit(board);
+    }
+}
+
+sb_go::BoardView View(const Board& b) {
+    return sb_go::BoardView{reinterpret_cast<const std::uint8_t*>(b.state_.data()), b.GetBoardSize(), b.GetLetterBoxSize()};
+}
+
+int SizeOfGame(int g) {   // small boards settle life and death quickly; big ones are what self-play runs
+    static const int sizes[] = {2, 3, 4, 5, 5, 6, 7, 7, 8, 9, 9, 9, 10, 11, 12, 13, 13, 15, 17, 19, 19};
+    return sizes[g % (int)(sizeof(sizes) / sizeof(sizes[0]))];
+}
+
+int Check(int games, std::uint64_t seed) {
+    std::uint64_t rng = seed;
+    long positions = 0, calls = 0, mismatches = 0, marked = 0, with_dead = 0;
+    for (int g = 0; g < games; ++g) {
+        PlayGame(SizeOfGame(g), rng, [&](const Board& b) {
+            ++positions;
+            const int n = b.GetNumIntersections();
+            for (int color = 0; color < 2; ++color) {
+                for (int flags = 0; flags < 4; ++flags) {
+                    const bool vit = flags & 1, dead = flags & 2;
+                    std::vector<bool> ref(n, false);
+                    b.ComputePassAliveArea(ref, color, vit, dead);
+                    std::uint8_t ours[kNumIntersections] = {0};
+                    sb_go::PassAliveArea(View(b), color, vit, dead, ours);
+                    ++calls;
+                    bool bad = false;
+                    for (int i = 0; i < n; ++i) {
+                        bad |= (bool)ours[i] != (bool)ref[i];
+                        marked += ref[i];
+                    }
+                    if (flags == 3) {
+                        std::vector<bool> alive_only(n, false);
+                        b.ComputePassAliveArea(alive_only, color, true, false);
+                        with_dead += alive_only != ref;
+                    }
+                    if (bad && mismatches++ < 3) {
+                        std::fprintf(stderr, "MISMATCH size %d color %d vitals %d dead %d\n%s", b.GetBoardSize(), color, (int)vit, (int)dead,
+                                     b.GetBoardString(kNullVertex, true).c_str());
+                        for (int y = b.GetBoardSize() - 1; y >= 0; --y) {
+                            for (int x = 0; x < b.GetBoardSize(); ++x) std::fprintf(stderr, "%c", "._"[0] + 0 * x + (ref[y * b.GetBoardSize() + x] ? 'R' - '.' : 0));
+                            std::fprintf(stderr, "   ");
+                            for (int x = 0; x < b.GetBoardSize(); ++x) std::fprintf(stderr, "%c", ours[y * b.GetBoardSize() + x] ? 'O' : '.');
+                            std::fprintf(stderr, "\n");
+                        }
+                    }
+                }
+            }
+        });
+    }
+    std::printf("{\"games\": %d, \"positions\": %ld, \"calls\": %ld, \"marked_points\": %ld, \"calls_with_pass_dead_points\": %ld, \"mismatches\": %ld}\n",
+                games, positions, calls, marked, with_dead, mismatches);
+    return mismatches ? 1 : 0;
+}
+
+int Digest(int games, std::uint64_t seed) {
+    std::uint64_t rng = seed, h = 0xcbf29ce484222325ull;
+    auto mix = [&](std::uint64_t v) {
+        h ^= v;
+        h *= 0x100000001b3ull;
+    };
+    Board previous;
+    previous.Reset(9);
+    for (int g = 0; g < games; ++g) {
+        PlayGame(SizeOfGame(g), rng, [&](const Board& b) {
+            const int n = b.GetNumIntersections();
+            std::vector<int> helper(n, kEmpty), score(n, kInvalid);
+            std::vector<bool> safe(n, false);
+            b.ComputeScoreArea(score, kArea, helper);
+            b.ComputeSafeArea(safe, false);
+            for (int i = 0; i < n; ++i) mix((std::uint64_t)score[i] * 2 + safe[i]);
+            // interleave another board (the per-thread reuse must notice), then ask again
+            std::vector<bool> other(previous.GetNumIntersections(), false);
+            previous.ComputeSafeArea(other, false);
+            for (size_t i = 0; i < other.size(); ++i) mix(other[i]);
+            std::vector<bool> again(n, false);
+            b.ComputeSafeArea(again, true);
+            for (int i = 0; i < n; ++i) mix(again[i]);
+            if (SplitMix(rng) % 3 == 0) previous = b;
+        });
+    }
+    std::printf("%016llx\n", (unsigned long long)h);
+    return 0;
+}
+
+int Time(int games, std::uint64_t seed, int size) {
+    std::uint64_t rng = seed;
+    std::vector<Board> boards;
+    for (int g = 0; g < games; ++g) PlayGame(size, rng, [&](const Board& b) { boards.push_back(b); });
+    using clk = std::chrono::steady_clock;
+    long sink = 0;
+    const auto t0 = clk::now();
+    for (const Board& b : boards) {
+        for (int color = 0; color < 2; ++color) {
+            std::vector<bool> ref(b.GetNumIntersections(), false);
+            b.ComputePassAliveArea(ref, color, true, true);
+            sink += ref[0];
+        }
+    }
+    const auto t1 = clk::now();
+    for (const Board& b : boards) {
+        for (int color = 0; color < 2; ++color) {
+            std::uint8_t ours[kNumIntersections] = {0};
+            sb_go::PassAliveArea(View(b), color, true, true, ours);
+            sink += ours[0];
+        }
+    }
+    const auto t2 = clk::now();
+    const double n = 2.0 * boards.size();
+    std::printf("{\"board_size\": %d, \"positions\": %zu, \"reference_ns_per_call\": %.0f, \"ours_ns_per_call\": %.0f, \"sink\": %ld}\n", size,
+                boards.size(), std::chrono::duration<double, std::nano>(t1 - t0).count() / n,
+                std::chrono::duration<double, std::nano>(t2 - t1).count() / n, sink);
+    return 0;
+}
+
+int Dump(int games, std::uint64_t seed, const char* path) {
+    std::uint64_t rng = seed;
+    std::FILE* f = std::fopen(path, "wb");
+    if (!f) return 2;
+    long records = 0;
+    for (int g = 0; g < games; ++g) {
+        int k = 0;
+        PlayGame(SizeOfGame(g), rng, [&](const Board& b) {
+            // every 5th position plus the late ones (where life and death is settled)
+            if (k++ % 5 && SplitMix(rng) % 4) return;
+            const int n = b.GetBoardSize(), cells = n * n;
+            std::uint8_t header[2] = {(std::uint8_t)n, 0};
+            std::fwrite(header, 1, 2, f);
+            std::vector<std::uint8_t> stones(cells);
+            for (int i = 0; i < cells; ++i) stones[i] = (std::uint8_t)b.GetState(b.IndexToVertex(i));
+            std::fwrite(stones.data(), 1, cells, f);
+            for (int color = 0; color < 2; ++color) {
+                for (int flags = 0; flags < 4; ++flags) {
+                    std::vector<bool> ref(cells, false);
+                    b.ComputePassAliveArea(ref, color, flags & 1, flags & 2);
+                    std::vector<std::uint8_t> bytes(cells);
+                    for (int i = 0; i < cells; ++i) bytes[i] = ref[i];
+                    std::fwrite(bytes.data(), 1, cells, f);
+                }
+            }
+            ++records;
+        });
+    }
+    std::fclose(f);
+    std::printf("%ld records\n", records);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    static char a0[] = "pass_alive_harness", a1[] = "--quiet";
+    char* args[] = {a0, a1};
+    ArgsParser(2, args);   // Zobrist tables etc. (config.cc:336-381)
+    if (argc >= 4 && !std::strcmp(argv[1], "check")) return Check(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10));
+    if (argc >= 4 && !std::strcmp(argv[1], "digest")) return Digest(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10));
+    if (argc >= 5 && !std::strcmp(argv[1], "time")) return Time(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), std::atoi(argv[4]));
+    if (argc >= 5 && !std::strcmp(argv[1], "dump")) return Dump(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argv[4]);
+    std::fprintf(stderr, "usage: pass_alive_harness check <games> <seed> | time <games> <seed> <size> | dump <games> <seed> <file>\n");
+    return 2;
+}

@@ -45,6 +45,9 @@ def main():
     ap.add_argument("--moves", type=int, default=6)
     ap.add_argument("--seeds", default="1,2,3")
     ap.add_argument("--weights", default=None, help="an existing weight file instead of a synthetic --net")
+    ap.add_argument("--host-override", action="store_true",
+                    help="compare sayuri_eigen_det with sayuri_eigen_det_fast (same Eigen pipe, link-time "
+                         "Board::ComputePassAliveArea override) instead of our pipe: runs without a GPU")
     a = ap.parse_args()
     if a.weights:
         w = a.weights
@@ -54,13 +57,13 @@ def main():
         synth.write_synth_net(w, a.net, seed=11)
     gtp = "boardsize %d\nclear_board\n" % a.board + "".join("genmove %s\n" % ("b" if i % 2 == 0 else "w") for i in range(a.moves)) + "quit\n"
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "sayuri_eigen_det")
-    our_bin = os.path.join(ROOT, "oracle", "_ref", "sayuri_b200_det")
+    our_bin = os.path.join(ROOT, "oracle", "_ref", "sayuri_eigen_det_fast" if a.host_override else "sayuri_b200_det")
     total = same = 0
     first_div = []
     l1 = []
     for seed in [int(s) for s in a.seeds.split(",")]:
         rs, rm, _ = run(ref_bin, w, gtp, a.playouts, seed, [])
-        os_, om, oout = run(our_bin, w, gtp, a.playouts, seed, ["--no-fp16", "-g", "0"])
+        os_, om, oout = run(our_bin, w, gtp, a.playouts, seed, [] if a.host_override else ["--no-fp16", "-g", "0"])
         if not os_:
             print(oout[-2000:])
             raise SystemExit("our front-end produced no search output")
