@@ -1,7 +1,8 @@
 // TEST INFRASTRUCTURE.  Links the UNMODIFIED reference objects (oracle/_ref/obj_v3) and compares, in one process,
 //   Board::ComputePassAliveArea   /root/reference/src/game/board.cc:1720-1901   (private: reached with the usual
 //                                                                                 `#define private public` test trick)
-// with sb_go::PassAliveArea (sayuri_b200/csrc/host_go/pass_alive.h) on every position of seeded random games.
+// with sb_go::PassAliveArea (sayuri_b200/csrc/host_go/pass_alive.h), and Board::ComputeReachArea (board.cc:1547-1579)
+// with sb_go::ReachArea, on every position of seeded random games.
 //   pass_alive_harness check <games> <seed>          all board sizes 2..19, both colours, the four flag combinations
 //   pass_alive_harness time  <games> <seed> <size>   ns per call of each, (true, true) as all callers use
 //   pass_alive_harness digest <games> <seed>         FNV-1a over Board::ComputeSafeArea and Board::ComputeScoreArea (public
@@ -84,6 +85,16 @@ int Check(int games, std::uint64_t seed) {
         PlayGame(SizeOfGame(g), rng, [&](const Board& b) {
             ++positions;
             const int n = b.GetNumIntersections();
+            {
+                std::vector<int> ref_reach(n, -1);
+                int our_reach[kNumIntersections];
+                b.ComputeReachArea(ref_reach);
+                sb_go::ReachArea(View(b), our_reach);
+                bool bad = false;
+                for (int i = 0; i < n; ++i) bad |= ref_reach[i] != our_reach[i];
+                if (bad && mismatches++ < 3) std::fprintf(stderr, "REACH MISMATCH size %d\n%s", b.GetBoardSize(), b.GetBoardString(kNullVertex, true).c_str());
+                ++calls;
+            }
             for (int color = 0; color < 2; ++color) {
                 for (int flags = 0; flags < 4; ++flags) {
                     const bool vit = flags & 1, dead = flags & 2;
@@ -174,10 +185,25 @@ int Time(int games, std::uint64_t seed, int size) {
         }
     }
     const auto t2 = clk::now();
+    for (const Board& b : boards) {
+        std::vector<int> reach(b.GetNumIntersections(), -1);
+        b.ComputeReachArea(reach);
+        sink += reach[0];
+    }
+    const auto t3 = clk::now();
+    for (const Board& b : boards) {
+        int reach[kNumIntersections];
+        sb_go::ReachArea(View(b), reach);
+        sink += reach[0];
+    }
+    const auto t4 = clk::now();
     const double n = 2.0 * boards.size();
-    std::printf("{\"board_size\": %d, \"positions\": %zu, \"reference_ns_per_call\": %.0f, \"ours_ns_per_call\": %.0f, \"sink\": %ld}\n", size,
+    std::printf("{\"board_size\": %d, \"positions\": %zu, \"reference_ns_per_call\": %.0f, \"ours_ns_per_call\": %.0f, "
+                "\"reach_reference_ns_per_call\": %.0f, \"reach_ours_ns_per_call\": %.0f, \"sink\": %ld}\n", size,
                 boards.size(), std::chrono::duration<double, std::nano>(t1 - t0).count() / n,
-                std::chrono::duration<double, std::nano>(t2 - t1).count() / n, sink);
+                std::chrono::duration<double, std::nano>(t2 - t1).count() / n,
+                std::chrono::duration<double, std::nano>(t3 - t2).count() / boards.size(),
+                std::chrono::duration<double, std::nano>(t4 - t3).count() / boards.size(), sink);
     return 0;
 }
 
@@ -206,6 +232,11 @@ int Dump(int games, std::uint64_t seed, const char* path) {
                     std::fwrite(bytes.data(), 1, cells, f);
                 }
             }
+            std::vector<int> reach(cells, -1);
+            b.ComputeReachArea(reach);
+            std::vector<std::uint8_t> reach_bytes(cells);
+            for (int i = 0; i < cells; ++i) reach_bytes[i] = (std::uint8_t)reach[i];
+            std::fwrite(reach_bytes.data(), 1, cells, f);
             ++records;
         });
     }

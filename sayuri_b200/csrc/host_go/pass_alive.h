@@ -266,4 +266,44 @@ inline void PassAliveArea(const BoardView& b, int color, bool mark_vitals, bool 
     }
 }
 
+// Board::ComputeReachArea (/root/reference/src/game/board.cc:1547-1579, flood fills :309-349): out[y * board_size + x]
+// = kBlack / kWhite when the point is a stone of that colour or is reached from such stones through empty points and
+// is NOT reached that way by the other colour; kEmpty otherwise (reached by both or by none).  Second half of
+// Board::ComputeScoreArea, which the encoder asks for at every leaf.
+inline void ReachArea(const BoardView& b, int* out) {
+    const int n = b.board_size, S = b.stride;
+    const int d4[4] = {-S, -1, +1, +S};
+    const std::uint8_t* st = b.state;
+    std::uint8_t reached[kMaxVertices];          // bit 0: from black, bit 1: from white
+    std::int16_t queue[kMaxVertices];
+    std::memset(reached, 0, (size_t)S * S);
+    for (int color = 0; color < 2; ++color) {
+        const std::uint8_t bit = (std::uint8_t)(1 << color);
+        int head = 0, tail = 0;
+        for (int y = 0; y < n; ++y)
+            for (int x = 0; x < n; ++x) {
+                const int v = (y + 1) * S + x + 1;
+                if (st[v] == color) {
+                    reached[v] |= bit;
+                    queue[tail++] = (std::int16_t)v;
+                }
+            }
+        while (head < tail) {
+            const int v = queue[head++];
+            for (int k = 0; k < 4; ++k) {
+                const int a = v + d4[k];
+                if (st[a] == kEmpty && !(reached[a] & bit)) {
+                    reached[a] |= bit;
+                    queue[tail++] = (std::int16_t)a;
+                }
+            }
+        }
+    }
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) {
+            const std::uint8_t r = reached[(y + 1) * S + x + 1];
+            out[y * n + x] = r == 1 ? kBlack : r == 2 ? kWhite : kEmpty;
+        }
+}
+
 }  // namespace sb_go

@@ -1,5 +1,6 @@
-// Link-time replacement of ONE member function of the unmodified reference:
+// Link-time replacement of TWO member functions of the unmodified reference:
 //   void Board::ComputePassAliveArea(std::vector<bool>&, int, bool, bool) const   (/root/reference/src/game/board.cc:1720)
+//   void Board::ComputeReachArea(std::vector<int>&) const                         (/root/reference/src/game/board.cc:1547)
 // The front-end build (oracle/Makefile, targets sayuri_b200_frontend / sayuri_b200_det) weakens that symbol in its
 // copy of board.o (objcopy --weaken-symbol) and links this file, so every caller — Board::ComputeSafeArea,
 // Board::ComputeScoreArea and through them Encoder::FillArea and GameState::GetStrictSafeArea — gets the flat-array
@@ -46,4 +47,10 @@ void Board::ComputePassAliveArea(std::vector<bool>& result, const int color, boo
     }
     for (int i = 0; i < num_intersections_; ++i)
         if (last.out[i]) result[i] = true;
+}
+
+void Board::ComputeReachArea(std::vector<int>& result) const {
+    if (result.size() != (size_t)num_intersections_) result.resize(num_intersections_);
+    const sb_go::BoardView view{reinterpret_cast<const std::uint8_t*>(state_.data()), board_size_, letter_box_size_};
+    sb_go::ReachArea(view, result.data());
 }

@@ -3,7 +3,7 @@ the REFERENCE's Board::ComputePassAliveArea (/root/reference/src/game/board.cc:1
 (mark_vitals, mark_pass_dead) combinations, written by oracle/_ref/pass_alive_harness (oracle/pass_alive_harness.cc,
 linked against the unmodified reference objects).  Run in the container that has /root/reference.
 Record: u8 board_size, u8 0, n*n stone bytes (0 black, 1 white, 2 empty), then 8 answers of n*n bytes
-(colour-major, flags = vitals | dead << 1)."""
+(colour-major, flags = vitals | dead << 1), then the answer of Board::ComputeReachArea (board.cc:1547), n*n bytes."""
 import gzip
 import os
 import subprocess

@@ -1,5 +1,5 @@
 // Replays tests/golden/pass_alive_cases.bin (the REFERENCE's answers, see tests/golden/make_pass_alive_golden.py) through
-// sb_go::PassAliveArea.  No reference code is needed to build or run this.
+// sb_go::PassAliveArea and sb_go::ReachArea.  No reference code is needed to build or run this.
 #include <cstdint>
 #include <cstdio>
 #include <vector>
@@ -10,7 +10,7 @@ int main(int argc, char** argv) {
     if (argc < 2) return 2;
     std::FILE* f = std::fopen(argv[1], "rb");
     if (!f) return 2;
-    long records = 0, answers = 0, mismatches = 0, marked = 0;
+    long records = 0, answers = 0, mismatches = 0, marked = 0, reach_answers = 0;
     std::uint8_t header[2];
     while (std::fread(header, 1, 2, f) == 2) {
         const int n = header[0], cells = n * n, stride = n + 2;
@@ -32,9 +32,17 @@ int main(int argc, char** argv) {
                 mismatches += bad;
             }
         }
+        if ((int)std::fread(want.data(), 1, cells, f) != cells) return 3;
+        std::vector<int> reach(cells, -1);
+        sb_go::ReachArea(sb_go::BoardView{state.data(), n, stride}, reach.data());
+        bool bad_reach = false;
+        for (int i = 0; i < cells; ++i) bad_reach |= reach[i] != (int)want[i];
+        mismatches += bad_reach;
+        ++reach_answers;
         ++records;
     }
     std::fclose(f);
-    std::printf("{\"records\": %ld, \"answers\": %ld, \"marked_points\": %ld, \"mismatches\": %ld}\n", records, answers, marked, mismatches);
+    std::printf("{\"records\": %ld, \"answers\": %ld, \"reach_answers\": %ld, \"marked_points\": %ld, \"mismatches\": %ld}\n", records, answers,
+                reach_answers, marked, mismatches);
     return mismatches ? 1 : 0;
 }

@@ -22,6 +22,7 @@ def test_pass_alive_replays_reference_fixtures(tmp_path):
     stats = json.loads(r.stdout)
     assert r.returncode == 0 and stats["mismatches"] == 0, stats
     assert stats["records"] > 2000 and stats["answers"] == 8 * stats["records"] and stats["marked_points"] > 100000
+    assert stats["reach_answers"] == stats["records"]
 
 
 def test_pass_alive_matches_reference_function_live_when_present():
