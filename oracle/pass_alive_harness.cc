@@ -9,6 +9,11 @@
 //                                                    callers) on every position, each asked twice as the encoder does:
 //                                                    the build with the link-time override (pass_alive_harness_fast,
 //                                                    oracle/Makefile) must print the same digest as the plain one
+//   pass_alive_harness encoder <games> <seed> [size] FNV-1a over the float bits of Encoder::GetPlanes (encoder.cc:31-50) for all
+//                                                    eight symmetries on positions of random games played through
+//                                                    GameState: every link-time override sits under that call, so
+//                                                    plain and override builds must print the same digest; also
+//                                                    prints the time per encoded position
 //   pass_alive_harness dump  <games> <seed> <file>   fixture file for tests/test_pass_alive.py (positions + the
 //                                                    REFERENCE's answers), format in tests/test_pass_alive.py
 #include <chrono>
@@ -26,8 +31,10 @@
 
 #define private public
 #include "game/board.h"
+#include "game/game_state.h"
 #undef private
 #include "config.h"
+#include "neural/encoder.h"
 
 #include "../sayuri_b200/csrc/host_go/pass_alive.h"
 
@@ -162,6 +169,48 @@ int Digest(int games, std::uint64_t seed) {
     return 0;
 }
 
+int EncoderDigest(int games, std::uint64_t seed, int only_size) {
+    std::uint64_t rng = seed, h = 0xcbf29ce484222325ull;
+    long encoded = 0;
+    double seconds = 0;
+    for (int g = 0; g < games; ++g) {
+        const int size = only_size ? only_size : SizeOfGame(g);
+        GameState state;
+        state.Reset(size, 7.5f - (g % 3), kArea);
+        int passes = 0;
+        for (int move = 0; move < size * size * 2 && passes < 2; ++move) {
+            const int color = state.GetToMove();
+            int vtx = kPass;
+            for (int attempt = 0; attempt < 30; ++attempt) {
+                const int x = SplitMix(rng) % size, y = SplitMix(rng) % size;
+                const int v = state.GetVertex(x, y);
+                if (state.IsLegalMove(v, color) && !state.board_.IsRealEye(v, color)) {
+                    vtx = v;
+                    break;
+                }
+            }
+            state.PlayMove(vtx, color);
+            passes = vtx == kPass ? passes + 1 : 0;
+            if (move % 3) continue;
+            for (int symm = 0; symm < 8; ++symm) {
+                const auto t0 = std::chrono::steady_clock::now();
+                const std::vector<float> planes = Encoder::Get().GetPlanes(state, symm, 5);
+                seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                for (float f : planes) {
+                    std::uint32_t bits;
+                    std::memcpy(&bits, &f, 4);
+                    h ^= bits;
+                    h *= 0x100000001b3ull;
+                }
+                ++encoded;
+            }
+        }
+    }
+    std::printf("{\"digest\": \"%016llx\", \"encoded_positions\": %ld, \"us_per_position\": %.1f}\n", (unsigned long long)h, encoded,
+                seconds * 1e6 / (encoded ? encoded : 1));
+    return 0;
+}
+
 int Time(int games, std::uint64_t seed, int size) {
     std::uint64_t rng = seed;
     std::vector<Board> boards;
@@ -252,6 +301,7 @@ int main(int argc, char** argv) {
     char* args[] = {a0, a1};
     ArgsParser(2, args);   // Zobrist tables etc. (config.cc:336-381)
     if (argc >= 4 && !std::strcmp(argv[1], "check")) return Check(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10));
+    if (argc >= 4 && !std::strcmp(argv[1], "encoder")) return EncoderDigest(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argc >= 5 ? std::atoi(argv[4]) : 0);
     if (argc >= 4 && !std::strcmp(argv[1], "digest")) return Digest(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10));
     if (argc >= 5 && !std::strcmp(argv[1], "time")) return Time(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), std::atoi(argv[4]));
     if (argc >= 5 && !std::strcmp(argv[1], "dump")) return Dump(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argv[4]);

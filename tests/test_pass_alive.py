@@ -46,3 +46,14 @@ def test_link_time_override_gives_the_same_safe_and_score_areas_when_present():
     t = json.loads(subprocess.run([fast, "time", "4", "3", "19"], check=True, capture_output=True, text=True).stdout)
     # in the override build "the reference's" member function IS ours: both columns time the same code
     assert t["reference_ns_per_call"] < 4 * t["ours_ns_per_call"]
+
+
+def test_whole_encoder_is_bit_identical_under_the_link_time_overrides_when_present():
+    """Encoder::GetPlanes (encoder.cc:31-50), all eight symmetries, on positions of random games: the build with every
+    override linked (pass-alive, reach area, symmetry gather, stone and last-move planes) hashes the same float bits."""
+    plain, fast = os.path.join(REF, "pass_alive_harness"), os.path.join(REF, "pass_alive_harness_fast")
+    if not (os.path.exists(plain) and os.path.exists(fast)):
+        pytest.skip("oracle/_ref not built")
+    a = json.loads(subprocess.run([plain, "encoder", "21", "4"], check=True, capture_output=True, text=True).stdout)
+    b = json.loads(subprocess.run([fast, "encoder", "21", "4"], check=True, capture_output=True, text=True).stdout)
+    assert a["encoded_positions"] == b["encoded_positions"] > 3000 and a["digest"] == b["digest"]
