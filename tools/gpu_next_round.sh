@@ -3,8 +3,8 @@
 #   1. parity gate + the bench line (both rungs)
 #   2. 19x19, 10bx128, 400 visits self-play through the unmodified loop with ALL host-side replacements of DESIGN.md 5b,
 #      at 64 / 128 / 256 parallel games (the 64-game run of round 1 was cut at 185 s: 31.4 k NN evals/s, no games/h)
-#   3. the same at 128 parallel games with the reference cache (A/B arm; the reference pass-alive arm is
-#      profiles/r01s2_selfplay19_sharded_cache.log: 633 games/h)
+#   3. the same at 128 parallel games with sayuri_b200_frontend_refcache = our pipe under the reference's host code
+#      with NO host-side replacement (A/B arm; at 64 parallel games that arm gave 618 games/h in round 1)
 mkdir -p gpurun_out
 echo "== pytest -m gpu"; timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -2 | tee gpurun_out/next_pytest_gpu.log
 echo "== bench (fp32-split, fp16)"
