@@ -25,6 +25,63 @@ def test_pass_alive_replays_reference_fixtures(tmp_path):
     assert stats["reach_answers"] == stats["records"]
 
 
+def _record(rows, answers, reach):
+    """One fixture record (format of tests/golden/make_pass_alive_golden.py) from ASCII rows: X black, O white, . empty."""
+    n = len(rows)
+    code = {"X": 0, "O": 1, ".": 2}
+    rec = bytes([n, 0]) + bytes(code[c] for row in rows for c in row)
+    for a in answers:
+        rec += bytes(1 if c == "#" else 0 for row in a for c in row)
+    return rec + bytes(code[c] for row in reach for c in row)
+
+
+def test_pass_alive_hand_worked_position(tmp_path):
+    """A position small enough to work by hand.  Black: one string with three one-point eyes on the edge => alive
+    (two healthy vital regions suffice); the open area below is nobody's.  White has no stones."""
+    rows = [".X.X.",
+            "XXXXX",
+            ".....",
+            ".....",
+            "....."]
+    stones = ["-#-#-", "#####", "-----", "-----", "-----"]
+    with_eyes = ["#####", "#####", "-----", "-----", "-----"]
+    nothing = ["-----"] * 5
+    # colour-major, flags = vitals | dead << 1.  Black: 0 = living stones; 1 = + their vital eyes; 2 = the eyes are
+    # reported as pass-dead regions of the opponent (no eye of his fits there); 3 = both.  White: nothing at all.
+    answers = [stones, with_eyes, with_eyes, with_eyes, nothing, nothing, nothing, nothing]
+    reach = ["XXXXX"] * 5          # only black stones on the board: every point is reached by black alone
+    exe, raw = str(tmp_path / "replay"), str(tmp_path / "one.bin")
+    subprocess.run(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "pass_alive_replay.cc"), "-o", exe], check=True)
+    with open(raw, "wb") as f:
+        f.write(_record(rows, answers, reach))
+    r = subprocess.run([exe, raw], capture_output=True, text=True)
+    assert r.returncode == 0 and json.loads(r.stdout)["mismatches"] == 0, r.stdout
+
+
+def test_pass_alive_hand_worked_dead_group(tmp_path):
+    """Black lives with two edge eyes and walls in a white group that has a single eye: the white group and its eye are
+    black's pass-dead region; white itself has only one vital region, so nothing of white is alive; the open right side
+    is left alone (room for three and more white eyes)."""
+    rows = [".X.X..",
+            "XXXX..",
+            "OOOX..",
+            ".OOX..",
+            "OOOX..",
+            "XXXX.."]
+    stones = ["-#-#--", "####--", "---#--", "---#--", "---#--", "####--"]
+    alive = ["####--", "####--", "---#--", "---#--", "---#--", "####--"]
+    with_dead = ["####--", "####--", "####--", "####--", "####--", "####--"]
+    nothing = ["------"] * 6
+    answers = [stones, alive, with_dead, with_dead, nothing, nothing, nothing, nothing]
+    reach = ["XXXXXX", "XXXXXX", "OOOXXX", "OOOXXX", "OOOXXX", "XXXXXX"]
+    exe, raw = str(tmp_path / "replay"), str(tmp_path / "one.bin")
+    subprocess.run(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "pass_alive_replay.cc"), "-o", exe], check=True)
+    with open(raw, "wb") as f:
+        f.write(_record(rows, answers, reach))
+    r = subprocess.run([exe, raw], capture_output=True, text=True)
+    assert r.returncode == 0 and json.loads(r.stdout)["mismatches"] == 0, r.stdout
+
+
 def test_pass_alive_matches_reference_function_live_when_present():
     exe = os.path.join(REF, "pass_alive_harness")
     if not os.path.exists(exe):
