@@ -1,7 +1,8 @@
 """BASELINE config 1 as plumbing: the reference's own `--mode selfplay` loop finishes 9x9 games and
 writes the SGF record, the training-data chunks and the NN-query log — with the unmodified reference
-(sayuri_eigen_v3) and with the link-time host-side replacements of DESIGN.md §5b (sayuri_eigen_fast: pass-alive and
-reach area, encoder planes, data-writer thread), over the reference's Eigen CPU pipe so that it runs without a GPU.
+(sayuri_eigen_v3) and with all host-side replacements of DESIGN.md §5b (sayuri_eigen_fast: sharded NN cache,
+pass-alive and reach area, encoder planes, data-writer thread), over the reference's Eigen CPU pipe so that it runs
+without a GPU.
 The same loop over our pipe is what tools/selfplay_host.sh times on the B200."""
 import glob
 import os
