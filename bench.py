@@ -193,6 +193,9 @@ def run_ours(args, rank, local_rank, world):
         desc = dict(version=5, blocks=blocks, channels=C, P=P, V=V, activation=5,
                     se_sizes=[C // 4 if s.endswith("-SE") else 0 for s in stack])
         pipe.initialize_from_tensors(desc, None, 19, B, gpus=[local_rank], precision=precision)
+    for kv in args.option:
+        k, v = kv.split("=")
+        pipe.set_option(k, int(v))
     if world > 1:
         from sayuri_b200.dist import replicate_weights
         replicate_weights(pipe, dist, rank, torch.device("cuda", local_rank))   # the path's only collective
@@ -319,7 +322,8 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": "19x19 board, %s net (P=%d,V=%d, SE every 3rd block, mish), batch-%d NN forward per GPU" % (args.net, P, V, B),
                        "net": args.net, "board": 19, "batch_per_gpu": B, "precision": args.precision,
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                       "parallelism": "replica per GPU, weights NCCL-broadcast from rank 0"},
+                       "parallelism": "replica per GPU, weights NCCL-broadcast from rank 0",
+                       **({"options": args.option} if args.option else {})},
             "clocks": clocks, "e2e": e2e, "e2e_eval": e2e_eval, "gpu_launches": int(launches), "roofline": roofline,
             "algorithmic_gflop_per_eval": algorithmic_flops_per_eval(blocks, C, P, V, n_se) / 1e9}
 
@@ -371,6 +375,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-threads", type=int, default=512, help="host threads of the sb_eval leg (0 = skip)")
     ap.add_argument("--eval-seconds", type=float, default=2.0)
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
+                    help="engine knob for A/B runs (sb_set_option), e.g. --option chunk_taps=3; recorded in config")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

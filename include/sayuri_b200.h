@@ -184,7 +184,9 @@ int sb_wait(sb_engine* e, int gpu, int slot, sb_output* out);
  *      and the per-call host copies of NNGraph::BatchForward (cuda_forward_pipe.cc:694-701).  The calling thread
  *      packs its position straight into a pinned batch record (sb_pack_position), one worker thread per
  *      (GPU, stream) closes a batch when it is full or `wait_us` after its first position arrived (and no earlier
- *      than a stream is free: batches grow while the GPU is busy), runs it and wakes the callers.             */
+ *      than a stream is free: batches grow while the GPU is busy), runs it and wakes the callers.  Every GPU has
+ *      its own lane (ring of batches, mutex, workers); a calling thread is bound to one lane for its lifetime
+ *      (thread -> GPU affinity), so nothing on the per-evaluation path is shared between GPUs.                */
 
 /* Exact packing of one position; returns 1 and fills *out, or returns 0 (out->flags = SB_PACKED_RAW) when some
  * plane holds two different non-zero values or a NaN.  Pure host function, thread-safe. */
@@ -194,6 +196,26 @@ int sb_unpack_position(const sb_packed_position* rec, float* planes);   /* inver
 /* Blocking, thread-safe evaluation of ONE position (planes: 43 * bs * bs floats at the native board size).
  * The first call starts the worker threads (2 per GPU, each with its own device slot and stream). */
 int sb_eval(sb_engine* e, const float* planes, int board_size, int policy_offset, sb_output* out);
+
+/* The same evaluation split in two for feeders that are NOT one OS thread per leaf: sb_eval_submit claims an entry of
+ * the forming batch and packs the position (returns at once), sb_eval_poll returns 1 while the batch has not run and 0
+ * once *out is filled (negative sb_status on failure), sb_eval_wait blocks.  A ticket must be collected exactly once (poll
+ * until it stops returning 1, or wait); sb_eval == submit + wait.  Precondition shared with sb_eval: sb_destroy must not
+ * be called while calls are in flight; sb_reconfigure / sb_reload_weights FAIL the positions that were claimed but not yet
+ * evaluated (their callers return SB_ERR_STATE) instead of stranding them. */
+typedef struct sb_eval_ticket {
+    void* owner;            /* opaque */
+    void* batch;            /* opaque */
+    uint32_t seq;
+    int32_t index;
+    int32_t lane;
+    int32_t flags;
+    int32_t board_size;
+    int32_t offset;
+} sb_eval_ticket;
+int sb_eval_submit(sb_engine* e, const float* planes, int board_size, int policy_offset, sb_eval_ticket* ticket);
+int sb_eval_poll(sb_engine* e, sb_eval_ticket* ticket, sb_output* out);
+int sb_eval_wait(sb_engine* e, sb_eval_ticket* ticket, sb_output* out);
 
 /* BatchForwardPipe::SetForwardingSize (batch_size <= max_batch; <= 0 keeps) and the --gpu-waittime analogue in
  * microseconds (< 0 keeps; default 200). */
@@ -206,6 +228,9 @@ int sb_batcher_stats(sb_engine* e, long long* out6);
  * `seconds` over n_pos positions (planes: n_pos records SB_PLANE_FLOATS apart, native packing, pageable memory).
  * Returns evaluations per second (wall clock), or a negative sb_status. */
 double sb_eval_throughput(sb_engine* e, const float* planes, int n_pos, int board_size, int threads, double seconds);
+/* Same through sb_eval_submit / sb_eval_wait: `threads` feeder threads, each with `depth` positions in flight. */
+double sb_eval_throughput_async(sb_engine* e, const float* planes, int n_pos, int board_size, int threads, int depth,
+                                double seconds);
 
 /* Pinned host memory (the reference's host_input_planes_ / host_output_* buffers, cuda_forward_pipe.cc:560-577). */
 void* sb_host_alloc(size_t bytes);
@@ -220,6 +245,17 @@ int sb_weights_blob(sb_engine* e, int gpu, void** device_ptr, size_t* bytes);
 int sb_weights_export(sb_engine* e, int gpu, void* device_dst, size_t bytes);
 int sb_weights_import(sb_engine* e, int gpu, const void* device_src, size_t bytes);
 uint64_t sb_weights_checksum(sb_engine* e, int gpu);   /* FNV-1a of the blob, to verify replicas agree */
+/* Several replicas in ONE process (gpu_ids with more than one entry): sb_create* / sb_reload_weights* upload the blob
+ * from host memory ONCE (into replica 0) and broadcast it device-to-device over NVLink: ncclBroadcast on an in-process
+ * communicator (libnccl.so.2, opened at run time), cudaMemcpyPeerAsync where NCCL cannot serve the device list; a
+ * device-side checksum of every replica is compared afterwards (mismatch = SB_ERR_CUDA).  This replaces the reference's
+ * per-GPU host uploads of every tensor (cuda_forward_pipe.cc:85-116,440-552; cuda_common.cc:228-243).
+ * sb_weights_broadcast repeats the broadcast + verification from replica 0 (after an sb_weights_import into it).
+ * out6 = {host->device blob uploads so far, replicas filled device-to-device so far, method of the last broadcast
+ * (0 = single replica, 1 = ncclBroadcast, 2 = peer copy), NCCL version code, replicas verified equal (1/0),
+ * duration of the last broadcast in microseconds}. */
+int sb_weights_broadcast(sb_engine* e);
+int sb_weights_stats(sb_engine* e, long long* out6);
 
 /* ---- measurement (bench.py; device timing on the engine's own stream with CUDA events) ------------- */
 

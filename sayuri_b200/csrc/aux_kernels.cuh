@@ -266,6 +266,45 @@ se_pool_fc_kernel(const __half* __restrict__ u_hi, const __half* __restrict__ u_
     });
 }
 
+// se_fc: the SE unit behind a convolution that already left pooling partials (conv3x3_tc2, POOL): part[group][2][C] holds
+// the sum and the maximum of every channel over the board cells of each aligned group of canvas rows; a sample owns
+// `gps` consecutive groups.  One CTA per sample adds its groups in a FIXED order (batch-invariant), then runs the squeeze
+// and excite FCs exactly like se_pool_fc.  Replaces the pooling pass over the whole tensor (52 MB at batch 256, C = 128)
+// by a 6.5 MB read.  (GlobalPooling + the two FCs of SEUnit::Forward, se_unit.cc:9-37,70-90.)
+template <int ACT>
+__global__ void __launch_bounds__(256)
+se_fc_kernel(const float* __restrict__ part, int gps, const int* __restrict__ board_sizes, int C, int se,
+             const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+             const float* __restrict__ b2, float* __restrict__ gb) {
+    extern __shared__ float sm[];
+    pdl_launch_dependents();
+    pdl_wait();   // the partials are the previous convolution's output
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int bs = board_sizes[b];
+    float* pool = sm;               // [3C]
+    float* hid = pool + 3 * C;      // [se]
+    const float b_coeff = ((float)bs - 14.0f) / 10.f;   // se_unit.h:17-20
+    const float* base = part + (size_t)b * gps * 2 * C;
+    for (int c = tid; c < C; c += 256) {
+        float s = 0.f, m = -5000.f;
+        for (int g = 0; g < gps; ++g) {      // fixed order over the row groups of the sample
+            s += base[(size_t)g * 2 * C + c];
+            m = fmaxf(m, base[(size_t)g * 2 * C + C + c]);
+        }
+        const float mean = s / (float)(bs * bs);
+        pool[c] = mean;
+        pool[C + c] = mean * b_coeff;
+        pool[2 * C + c] = m;
+    }
+    __syncthreads();
+    fc_tail_8lanes(w1, pool, 3 * C, se, [&](int o, float v) { hid[o] = activate_t<ACT>(v + b1[o]); });   // squeeze, activation
+    __syncthreads();
+    fc_tail_8lanes(w2, hid, se, 2 * C, [&](int o, float v) {                                             // excite, identity
+        v += b2[o];
+        gb[(size_t)b * 2 * C + o] = o < C ? 1.0f / (1.0f + expf(-v)) : v;   // gamma = sigmoid, se_unit.cc:103
+    });
+}
+
 // se_apply: x' = act(sigmoid(gamma) * u + beta + skip) on board cells, 0 elsewhere
 // (SEUnit::SEProcess, se_unit.cc:92-128; GPU twin se_scale_kernel cuda_kernels.cu:391-440).  In place on u.
 template <int ACT>

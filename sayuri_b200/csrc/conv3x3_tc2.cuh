@@ -1,23 +1,75 @@
-// conv3x3_tc2 — the CTA-pair (tcgen05 cta_group::2) form of conv3x3_tc: same math, same canvas / C8 layout, same
-// epilogue semantics, but two SMs of a TPC cooperate on one 256-row work item:
-//   * UMMA M = 256 (128 rows from each CTA), N = BN; each CTA stages only ITS HALF of every weight block
-//     ([BN/2][64], 8 KB): L2 -> SM weight traffic and the B-operand shared-memory reads per SM are halved (the
-//     single-CTA kernel was L2-bandwidth bound on weight streaming: ~25 B/clk/SM of a ~24 B/clk/SM budget);
-//   * each CTA owns ONE 128-row tile, so its 512 TMEM columns hold main + lo accumulators DOUBLE-buffered:
-//     the drain of item j overlaps the MMAs of item j+1 also on the split-precision rung, and the epilogue per
-//     item is half as long (4 warps x 128 rows), which shrinks the exposed tail;
-//   * 256 threads per CTA: every epilogue thread can hold its 128-column accumulator row without setmaxnreg.
+// conv3x3_tc2 — 3x3 same-pad convolution (+bias, +residual, *mask, activation) as an implicit GEMM on the 5th-gen tensor
+// cores, CTA-pair (tcgen05 cta_group::2) form: TMA-staged channel-blocked NHWC tiles in shared memory -> tcgen05.mma
+// (UMMA M = 256 = 128 rows from each CTA of the pair, N = BN, K = 16 per instruction, fp16 operands, fp32 accumulation in
+// TMEM) -> tcgen05.ld epilogue.
+//
+// Replaces, for the tower and input convolutions, the reference's
+//   Convolution<3>::Forward + Im2col          /root/reference/src/neural/blas/convolution.h:41-125
+//   (or WinogradConvolution3::Forward         /root/reference/src/neural/blas/winograd_convolution3.cc:280-291)
+//   followed by AddSpatialBiases::Forward     /root/reference/src/neural/blas/biases.cc:14-45
+// and on the reference GPU path im2col/Winograd kernels + cuBLAS/cuDNN + add_spatial
+//   (/root/reference/src/neural/cuda/cuda_kernels.cu:37-79,182-239,522-667); with POOL also the pooling pass of the SE unit
+//   (GlobalPooling, /root/reference/src/neural/blas/se_unit.cc:9-37; GPU twin cuda_kernels.cu:241-321).
+//
+// GEMM view: M = canvas rows (pixels of all samples, halo cells included), N = Cout, K = taps * Cin.  Because of the
+// canvas layout (common.cuh) the A operand of tap (ky,kx) is the SAME row-major tile shifted by (ky-1)*P + (kx-1) rows,
+// so one "slab" of 128 + 2*24 rows x 64 channels per CTA is loaded once per work item and k-half and re-used by all 9
+// taps through row-shifted UMMA descriptors (9x less activation traffic than per-tap loads).
+//   * each CTA stages only ITS HALF of every weight block ([BN/2][64], 8 KB): L2 -> SM weight traffic and the B-operand
+//     shared-memory reads per SM are halved against a single-CTA kernel;
+//   * 128 + kEpiParts*128 threads per CTA: every epilogue thread holds its part of an accumulator row in registers.
 // Protocol (leader = cluster rank 0 issues every MMA): `full` barriers live in the leader and receive the TMA
-// transaction bytes of BOTH CTAs (the peer's loads signal the leader's barrier through its shared::cluster
-// address); `empty` / `tmem_full` barriers are local to each CTA and are signalled by multicast tcgen05.commit;
-// `tmem_empty` lives in the leader and collects the epilogue warps of both CTAs (remote mbarrier.arrive).
-// Reference lines replaced: see conv3x3_tc.cuh.
+// transaction bytes of BOTH CTAs (the peer's loads signal the leader's barrier through its shared::cluster address);
+// `empty` / `tmem_full` / `lo_full` barriers are local to each CTA and are signalled by multicast tcgen05.commit;
+// `tmem_empty` / `lo_empty` live in the leader and collect the epilogue warps of both CTAs (remote mbarrier.arrive).
+//
+// Precision.  SPLIT = true evaluates x*w as hi*hi + lo*hi + hi*lo with x = x_hi + x_lo, w = w_hi + w_lo (fp16 pairs, ~22
+// significant bits): the fp32-faithful rung.  The tensor core adds into its fp32 accumulator with TRUNCATION: every MMA
+// into a large accumulator loses a fraction of an ulp TOWARDS ZERO, a systematic shrink of ~1e-8 per MMA that adds up
+// coherently over K (144 main MMAs at C = 256) and over the layers of a deep tower (measured, profiles/r02_precision_probe*:
+// 20bx256 trunk 5.7e-5 relative = 1.2e-3 absolute, 12x the fp32 noise floor).  Therefore:
+//   * the low-order products (lo*hi, hi*lo) have their own accumulator (small values: their truncation is harmless);
+//   * the MAIN product is accumulated in CHUNKS of `chunk_steps` (k-half, tap) steps (36 or 12 MMAs); each chunk starts
+//     from zero in one of two TMEM stages and is drained by the epilogue and added in fp32 round-to-nearest in registers
+//     (optionally scaled by 1 + the expected truncation loss of a chunk), while the next chunk runs in the other stage.
+// SPLIT = false uses the hi parts only, one chunk per item (the reference's own --fp16 trade).
+//
+// Warp roles:  warp 0 : TMA producer for weight stages      warp 1 : tcgen05.mma issuer (leader CTA; converged, elected lane)
+//              warp 2 : TMEM allocator                       warp 3 : TMA producer for activation slabs
+//              warps 4.. : epilogue (warp%4 = TMEM lane quadrant, (warp-4)/4 = column part of the accumulator row)
 #pragma once
 #include "common.cuh"
-#include "conv3x3_tc.cuh"
 #include "ptx.cuh"
 
 namespace sb {
+
+struct ConvParams {
+    __half* out_hi;
+    __half* out_lo;          // unused when !SPLIT
+    const __half* res_hi;    // optional residual (same layout as out), nullptr if none
+    const __half* res_lo;
+    const float* bias;       // [cout]
+    const uint8_t* mask;     // [rows]: 1 = real board cell of its sample, 0 = halo / off-board / padding
+    int cout;                // real output channels (bias length)
+    int rows;                // R: rows per channel chunk of the C8 activation tensors (out/res)
+    int kh;                  // number of 64-channel K blocks per tap = padded Cin / 64
+    int bn;                  // UMMA N = output channels per work item (multiple of 16)
+    int n_super;             // number of 256-row work items along M
+    int n_ntiles;            // cout / bn
+    int resident;            // fp16 rung: this CTA's weights fit the stage ring and are loaded once per launch
+    int n_full, n_units;     // whole items, and whole items + half units of the tail wave
+    int pitch;               // P = N + 1
+    int ntaps;               // 9 = 3x3 convolution, 1 = 1x1 convolution (centre tap only)
+    int dbg;                 // ablation bits for profiling only: 1 skip stores, 2 skip activation+split math, 8 no tap shifts, 16 no weight stream, 64 no slab stream
+    int chunk_steps;         // SPLIT: (k-half, tap) steps per main-accumulator chunk; kh * ntaps = one chunk per item
+    float chunk_scale;       // SPLIT: a drained chunk is multiplied by this (1 + expected truncation loss of a chunk)
+    float* pool_part;        // POOL: [group][2][pool_c] sums and maxima of the output over groups of 2^pool_log2 canvas rows
+    int pool_log2;           // 2..4; groups never straddle samples (the engine checks kGuardRows and SS are multiples)
+    int pool_groups;         // groups covered by the batch; groups beyond are not written
+    int pool_c;              // channel stride of pool_part
+    int* err;                // device int, receives a site code if a barrier wait times out
+    long long* stats;        // optional [grid][8] cycle counters (see sb_conv_stats), nullptr = off
+};
 
 // Split rung: 2 activation-slab buffers and a 12-stage weight ring measured best (profiles/r01s2_ring_depth.log: +2.4 % on
 // 10bx128, +3.5 % on 20bx256 over 3 slabs + 8 stages; 16 stages: +2 % / +3 %) — the weight stream is what the MMA
@@ -148,7 +200,40 @@ __device__ __forceinline__ ConvUnit conv_unit(int u, const ConvParams& p) {
     return w;
 }
 
-template <bool SPLIT, int ACT>
+// Reduce-scatter of 16 per-row values over the 2^L lanes of an aligned lane group (recursive halving): step `bit` pairs
+// lane and lane ^ bit, each keeps one half of its current index range and receives the partner's values of that half.
+// The summation tree of every channel depends only on the lane bits: results do not depend on where in the batch the
+// rows lie.  Afterwards lane l holds 16 >> L consecutive channels starting at pool_first(l); v[0 .. 16>>L) are valid.
+template <int L>
+__device__ __forceinline__ void pool_reduce16(float (&s)[16], float (&m)[16], int lane) {
+    int n = 16;
+#pragma unroll
+    for (int step = 0; step < L; ++step) {
+        const int bit = 1 << (L - 1 - step);
+        const int half = n >> 1;
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < half) {
+                const float send_s = upper ? s[i] : s[i + half], keep_s = upper ? s[i + half] : s[i];
+                const float send_m = upper ? m[i] : m[i + half], keep_m = upper ? m[i + half] : m[i];
+                s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                m[i] = fmaxf(keep_m, __shfl_xor_sync(0xffffffffu, send_m, bit));
+            }
+        }
+        n = half;
+    }
+}
+__device__ __forceinline__ int pool_first(int lane, int L) {   // first channel (of 16) a lane holds after pool_reduce16<L>
+    int first = 0, n = 16;
+    for (int step = 0; step < L; ++step) {
+        n >>= 1;
+        if (lane & (1 << (L - 1 - step))) first += n;
+    }
+    return first;
+}
+
+template <bool SPLIT, int ACT, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<SPLIT>::kThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -163,8 +248,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t slab_addr = smem_base;
     const uint32_t bst_addr = smem_base + Cfg::kOffB;
     const uint32_t bar_addr = smem_base + Cfg::kOffBar;
-    const uint32_t a_full = bar_addr + 0, a_empty = bar_addr + 32;                // [3] each
-    const uint32_t tmem_full = bar_addr + 64, tmem_empty = bar_addr + 80;         // [2] each
+    const uint32_t a_full = bar_addr + 0, a_empty = bar_addr + 32;                // [<= 4] each
+    const uint32_t tmem_full = bar_addr + 64, tmem_empty = bar_addr + 80;         // [2] each: main accumulator stages (chunks)
+    const uint32_t lo_full = bar_addr + 96, lo_empty = bar_addr + 112;            // [2] each: low-order accumulators (items)
     const uint32_t b_full = bar_addr + 128, b_empty = bar_addr + 288;             // [<= 18] each
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 448);
     float* sbias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
@@ -176,6 +262,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t stage_stride = BN > 128 ? 2u * Cfg::kBStageBytes : (uint32_t)Cfg::kBStageBytes;
     const uint32_t kNB = resident ? (uint32_t)(p.kh * p.ntaps * Cfg::kParts)
                                   : (uint32_t)(Cfg::kNumBStages * Cfg::kBStageBytes) / stage_stride;
+    // main-accumulator chunks: the (k-half, tap) steps t = h * ntaps + tap of an item are cut every chunk_steps steps
+    const int T = KH * p.ntaps;
+    const int chunk_steps = SPLIT ? p.chunk_steps : T;
+    const int n_chunks = (T + chunk_steps - 1) / chunk_steps;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -194,6 +284,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int i = 0; i < 2; ++i) {
             mbar_init(tmem_full + 8 * i, 1);
             mbar_init(tmem_empty + 8 * i, 2 * 4 * Cfg::kEpiParts);  // every epilogue warp of both CTAs
+            mbar_init(lo_full + 8 * i, 1);
+            mbar_init(lo_empty + 8 * i, 2 * 4 * Cfg::kEpiParts);
         }
         for (int i = 0; i < Cfg::kNumBStages; ++i) {
             mbar_init(b_full + 8 * i, 1);
@@ -277,23 +369,26 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     } else if (warp == 1) {
         if (leader) {
             // ===================== MMA issuer (leader CTA only) =====================
-            // TMEM columns per CTA: stage as -> main at as*2*BN, lo at as*2*BN + BN (fp16 rung: main at as*BN).
+            // TMEM columns per CTA: main stage s at s * BN (s = chunk counter & 1); split rung: low-order accumulator of
+            // item j at (2 + (j & 1)) * BN.
             const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);
             constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
             const bool stats = p.stats != nullptr;
-            uint32_t a_it = 0, j = 0;
+            uint32_t a_it = 0, j = 0, cc = 0;
             uint32_t bs = 0, bph = 0;   // weight ring position and phase (incremental: kNB is a run-time value)
             long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0, t0 = 0;
             const long long t_begin = stats ? clock64() : 0;
             for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
-                const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+                const uint32_t ls = j & 1u, lph = (j >> 1) & 1u;
                 const uint32_t idesc = item < p.n_full ? idesc_whole : idesc_half;
-                if (stats) t0 = clock64();
-                mbar_wait(tmem_empty + 8 * as, aph ^ 1u, p.err, 3);
-                if (stats) t_wait_tmem += clock64() - t0;
-                tc_fence_after();
-                const uint32_t d_main = tmem_base + (SPLIT ? as * 2 * BN : as * BN);
-                const uint32_t d_lo = d_main + BN;
+                const uint32_t d_lo = tmem_base + (2u + ls) * BN;
+                if (SPLIT) {
+                    if (stats) t0 = clock64();
+                    mbar_wait(lo_empty + 8 * ls, lph ^ 1u, p.err, 8);
+                    if (stats) t_wait_tmem += clock64() - t0;
+                }
+                uint32_t d_main = 0;
+                int in_chunk = 0;        // steps issued into the current chunk
                 for (int h = 0; h < KH; ++h, ++a_it) {
                     const uint32_t s = a_it % kNA, sph = (a_it / kNA) & 1u;
                     if (stats) t0 = clock64();
@@ -302,8 +397,17 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     tc_fence_after();
                     const uint32_t a_hi = slab_addr + s * Cfg::kSlabBytes;
                     for (int tap = 0; tap < p.ntaps; ++tap) {
+                        if (in_chunk == 0) {   // a new chunk: its accumulator stage must have been drained
+                            const uint32_t cs = cc & 1u, cph = (cc >> 1) & 1u;
+                            if (stats) t0 = clock64();
+                            mbar_wait(tmem_empty + 8 * cs, cph ^ 1u, p.err, 3);
+                            if (stats) t_wait_tmem += clock64() - t0;
+                            tc_fence_after();
+                            d_main = tmem_base + cs * BN;
+                        }
                         const int shift = (p.ntaps == 1 || (p.dbg & 8)) ? 0 : (tap / 3 - 1) * p.pitch + (tap % 3 - 1);   // 1 tap = 1x1 convolution
-                        const uint32_t first = (h | tap) == 0 ? 0u : 1u;
+                        const uint32_t first_main = in_chunk == 0 ? 0u : 1u;
+                        const uint32_t first_lo = (h | tap) == 0 ? 0u : 1u;
                         const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
                         {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
                             if (stats) t0 = clock64();
@@ -314,10 +418,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    umma2_f16(d_main, ad0 + kAStep * k, bd0 + 2 * k, idesc, (k == 0) ? first : 1u);
+                                    umma2_f16(d_main, ad0 + kAStep * k, bd0 + 2 * k, idesc, (k == 0) ? first_main : 1u);
                                     if (SPLIT)
                                         umma2_f16(d_lo, ad0 + (Cfg::kSlabPartBytes >> 4) + kAStep * k, bd0 + 2 * k, idesc,
-                                                  (k == 0) ? first : 1u);
+                                                  (k == 0) ? first_lo : 1u);
                                 }
                                 if (!resident) umma2_commit_mc(b_empty + 8 * bs, 3);   // resident stages are never recycled
                             }
@@ -344,12 +448,20 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                 if (!resident) bph ^= 1u;
                             }
                         }
+                        const bool last_step = h == KH - 1 && tap == p.ntaps - 1;
+                        if (++in_chunk == chunk_steps || last_step) {   // chunk complete: hand its stage to the epilogue
+                            if (elect_one()) {
+                                if (SPLIT && last_step) umma2_commit_mc(lo_full + 8 * ls, 3);
+                                umma2_commit_mc(tmem_full + 8 * (cc & 1u), 3);
+                            }
+                            __syncwarp();
+                            in_chunk = 0;
+                            ++cc;
+                        }
                     }
                     if (elect_one()) umma2_commit_mc(a_empty + 8 * s, 3);
                     __syncwarp();
                 }
-                if (elect_one()) umma2_commit_mc(tmem_full + 8 * as, 3);
-                __syncwarp();
             }
             if (stats && lane == 0) {
                 long long* st = p.stats + (size_t)cluster_id * 8;
@@ -367,10 +479,12 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const int q = warp & 3;
         const int part = (warp - 4) >> 2;                      // which column part of the accumulator row
         const bool stats = p.stats != nullptr;
-        uint32_t j = 0;
+        uint32_t j = 0, cc = 0;
         long long t_wait_full = 0, t_drain = 0;
         const long long t_begin = stats ? clock64() : 0;
         const uint32_t empty0 = mapa_u32(tmem_empty, 0);   // leader's tmem_empty[0]; [1] is +8
+        const uint32_t lo_empty0 = mapa_u32(lo_empty, 0);
+        const float chunk_scale = p.chunk_scale;
         pdl_wait();   // residual reads, and our stores may overwrite a buffer the previous layer still reads
         for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
             const ConvUnit w = conv_unit(item, p);
@@ -380,8 +494,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const int c_run = ((w.bn + Cfg::kEpiParts - 1) / Cfg::kEpiParts + 15) & ~15;
             const int cbase = min(part * c_run, w.bn);
             const int HC = min(c_run, w.bn - cbase);
-            const int n_pass = max(1, (HC + 63) >> 6);
-            const uint32_t as = j & 1u, aph = (j >> 1) & 1u;
+            const int n_pass = max(1, (HC + 63) >> 6);     // 1 on the split rung (BN <= 128)
+            const uint32_t ls = j & 1u, lph = (j >> 1) & 1u;
 
             const int row = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 + q * 32 + lane;
             const bool live = p.mask[row] != 0;
@@ -407,40 +521,84 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         rl[0][1] = *reinterpret_cast<const uint4*>(p.res_lo + off + chunk_stride);
                     }
                 }
-                if (pass == 0) {
-                    const long long t0 = stats ? clock64() : 0;
-                    mbar_wait(tmem_full + 8 * as, aph, p.err, 7);
-                    if (stats) t_wait_full += clock64() - t0;
-                    tc_fence_after();
-                }
-                const uint32_t t_main = lane_base + (SPLIT ? as * 2 * BN : as * BN) + pbase;
-                const uint32_t t_lo = t_main + BN;
                 float acc[Cfg::kMaxGroups * 16];
-                const long long t_d0 = stats ? clock64() : 0;
+                if (SPLIT) {
+                    // ---- split rung: drain every main chunk as it completes and add it in fp32 round-to-nearest ----
+                    for (int ch = 0; ch < n_chunks; ++ch, ++cc) {
+                        const uint32_t cs = cc & 1u, cph = (cc >> 1) & 1u;
+                        const long long t0 = stats ? clock64() : 0;
+                        mbar_wait(tmem_full + 8 * cs, cph, p.err, 7);
+                        if (stats) t_wait_full += clock64() - t0;
+                        tc_fence_after();
+                        const long long t_d0 = stats ? clock64() : 0;
+                        const uint32_t t_main = lane_base + cs * BN + pbase;
 #pragma unroll
-                for (int g = 0; g < Cfg::kMaxGroups; ++g) {
-                    if (g * 16 < PC) {
-                        uint32_t r[16];
-                        tmem_ld16(t_main + g * 16, r);
-                        if (SPLIT) {
-                            uint32_t r2[16];
-                            tmem_ld16(t_lo + g * 16, r2);
-                            tmem_ld_wait();
+                        for (int g = 0; g < Cfg::kMaxGroups; ++g) {
+                            if (g * 16 < PC) {
+                                uint32_t r[16];
+                                tmem_ld16(t_main + g * 16, r);
+                                tmem_ld_wait();
+                                if (ch == 0) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
-                        } else {
+                                    for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]) * chunk_scale;
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) acc[g * 16 + i] = fmaf(__uint_as_float(r[i]), chunk_scale, acc[g * 16 + i]);
+                                }
+                            }
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(empty0 + 8 * cs);   // main stage is free for the chunk after next
+                        if (stats) t_drain += clock64() - t_d0;
+                    }
+                    {   // the low-order accumulator of this item (committed together with the last chunk)
+                        mbar_wait(lo_full + 8 * ls, lph, p.err, 9);
+                        tc_fence_after();
+                        const uint32_t t_lo = lane_base + (2u + ls) * BN + pbase;
+#pragma unroll
+                        for (int g = 0; g < Cfg::kMaxGroups; ++g) {
+                            if (g * 16 < PC) {
+                                uint32_t r2[16];
+                                tmem_ld16(t_lo + g * 16, r2);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) acc[g * 16 + i] += __uint_as_float(r2[i]);
+                            }
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(lo_empty0 + 8 * ls);
+                    }
+                } else {
+                    // ---- fp16 rung: one chunk per item ----
+                    const uint32_t cs = cc & 1u, cph = (cc >> 1) & 1u;
+                    if (pass == 0) {
+                        const long long t0 = stats ? clock64() : 0;
+                        mbar_wait(tmem_full + 8 * cs, cph, p.err, 7);
+                        if (stats) t_wait_full += clock64() - t0;
+                        tc_fence_after();
+                    }
+                    const uint32_t t_main = lane_base + cs * BN + pbase;
+                    const long long t_d0 = stats ? clock64() : 0;
+#pragma unroll
+                    for (int g = 0; g < Cfg::kMaxGroups; ++g) {
+                        if (g * 16 < PC) {
+                            uint32_t r[16];
+                            tmem_ld16(t_main + g * 16, r);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 16; ++i) acc[g * 16 + i] = __uint_as_float(r[i]);
                         }
                     }
+                    if (pass == n_pass - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(empty0 + 8 * cs);   // accumulator stage is free again
+                        ++cc;
+                    }
+                    if (stats) t_drain += clock64() - t_d0;
                 }
-                if (pass == n_pass - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(empty0 + 8 * as);   // accumulator stage is free again
-                }
-                if (stats) t_drain += clock64() - t_d0;
 
 #pragma unroll
                 for (int g = 0; g < Cfg::kMaxGroups; ++g) {
@@ -495,6 +653,32 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         if (ch0 + 8 < p.cout) {
                             *reinterpret_cast<uint4*>(p.out_hi + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
                             if (SPLIT) *reinterpret_cast<uint4*>(p.out_lo + o1) = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+                        }
+                        if (POOL) {
+                            // SE pooling partials of the (pre-rounding) outputs: sum and max over the board cells of every
+                            // aligned group of 2^pool_log2 rows, per channel; off-board rows count 0 / -5000 (se_unit.cc:22)
+                            float ps[16], pm[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                ps[i] = v[i];                       // already 0 on dead rows
+                                pm[i] = live ? v[i] : -5000.f;
+                            }
+                            const int L = p.pool_log2;
+                            if (L == 4) pool_reduce16<4>(ps, pm, lane);
+                            else if (L == 3) pool_reduce16<3>(ps, pm, lane);
+                            else pool_reduce16<2>(ps, pm, lane);
+                            const int gi = (row - kGuardRows) >> L;
+                            const int cnt = 16 >> L, first = pool_first(lane, L);
+                            if (gi < p.pool_groups && ch0 + first < p.cout) {
+                                float* dst = p.pool_part + (size_t)gi * 2 * p.pool_c + ch0 + first;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    if (i < cnt) {
+                                        dst[i] = ps[i];
+                                        dst[p.pool_c + i] = pm[i];
+                                    }
+                                }
+                            }
                         }
                     }
                 }

@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
 #include <linux/futex.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -30,7 +31,6 @@
 #include "../../include/sayuri_b200.h"
 #include "aux_kernels.cuh"
 #include "common.cuh"
-#include "conv3x3_tc.cuh"
 #include "conv3x3_tc2.cuh"
 #include "host_net.h"
 
@@ -85,24 +85,8 @@ static CUtensorMap MakeMap2D(const void* base, int rows, int cols, int box_rows)
     return m;
 }
 
-// C8 activation tensor [chunks][R rows][8 ch] viewed as 4-D {8, R, 2, chunks} with an overlapping row split
-// (stride of dim 2 = 152 rows) so that ONE box {8, 152, 2, 8} covers 304 consecutive rows of 8 chunks and
-// lands in shared memory as [chunk][304 rows][16 B] (box dimensions are limited to 256).
-static CUtensorMap MakeActMap(const void* base, int R, int chunks) {
-    CUtensorMap m;
-    const int half = kSlabRows / 2;
-    cuuint64_t dims[4] = {8u, (cuuint64_t)(R - half), 2u, (cuuint64_t)chunks};
-    cuuint64_t strides[3] = {16u, (cuuint64_t)half * 16u, (cuuint64_t)R * 16u};
-    cuuint32_t box[4] = {8u, (cuuint32_t)half, 2u, 8u};
-    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    CUresult r = GetEncodeTiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box,
-                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled (activation) failed with code " + std::to_string((int)r)};
-    return m;
-}
-
-// Same tensor as a plain 3-D {8, R, chunks} view with a 176-row box: the per-CTA slab of the CTA-pair kernel.
+// C8 activation tensor [chunks][R rows][8 ch] as a 3-D {8, R, chunks} view with a 176-row box: one box {8, 176, 8} lands in
+// shared memory as [chunk][176 rows][16 B], the per-CTA slab of the conv kernel.
 static CUtensorMap MakeActMap3(const void* base, int R, int chunks) {
     CUtensorMap m;
     cuuint64_t dims[3] = {8u, (cuuint64_t)R, (cuuint64_t)chunks};
@@ -305,8 +289,7 @@ struct ActBuf {
     __half* lo = nullptr;
     int channels = 0;   // padded to a multiple of 64
     int rows = 0;       // R
-    CUtensorMap tm_hi, tm_lo;       // 304-row slabs (single-CTA kernel)
-    CUtensorMap tm3_hi, tm3_lo;     // 176-row slabs (CTA-pair kernel)
+    CUtensorMap tm3_hi, tm3_lo;     // 176-row slabs
 };
 
 struct Slot {
@@ -328,6 +311,7 @@ struct Slot {
     ActBuf* trunk = nullptr;   // which buffer holds the tower output after the last forward
     uint8_t* mask = nullptr;
     float* gb = nullptr;       // [max_batch][2C]
+    float* pool_part = nullptr;   // [row groups][2][C]: SE pooling partials written by the conv epilogue (PoolLog2)
     float* pooled = nullptr;   // [max_batch][2 * max(C, 64)]: per-channel sums and maxima between the pooling CTAs and the FC tail
     int* counters = nullptr;   // [max_batch]: pooling CTAs of a sample that have published (self-resetting)
     ActBuf pv;                 // head-entry conv output: P policy + V value channels (padded to 64)
@@ -338,14 +322,14 @@ struct Slot {
     int* h_err = nullptr;      // mapped pinned: barrier-timeout site code survives a trapped context
     int* d_err = nullptr;
     int n = 0;                 // samples of the batch in flight / last uploaded
+    int conv_counter = 0;      // conv launches of the forward being enqueued on this slot (option "stats_launch")
     bool busy = false;
     std::vector<int> sizes, offsets;
 };
 
 struct DevConv {
     ConvLayout L;
-    CUtensorMap tm_hi, tm_lo;     // box [bn][64]
-    // CTA-pair kernel: box [(bn >> level) / 2][64] = one CTA's half of an N tile of width bn >> level.  Level 0 is the
+    // box [(bn >> level) / 2][64] = one CTA's half of an N tile of width bn >> level.  Level 0 is the
     // throughput shape; levels 1-2 spread small batches over more CTA pairs and serve the tail-wave half units.
     CUtensorMap tm2_hi[4], tm2_lo[4];
     int levels = 1;               // usable N widths: bn0 >> 0 .. bn0 >> (levels - 1), each a multiple of 16
@@ -372,14 +356,17 @@ struct Replica {
 
 
 // ---- batcher (sb_eval): host-side data structures ------------------------------------------------------------
-// A ring of host batches in pinned memory.  Calling threads claim an index in the FILLING batch under the
-// batcher mutex, pack their position into it outside the lock and sleep on the batch's futex word; worker threads
-// (one per (GPU, batcher slot)) close a batch when it is full or its timer expired, run it and wake the sleepers.
+// One LANE per replica (GPU): its own ring of host batches in pinned memory, its own mutex and condition variables, its
+// own two worker threads (one per device slot / stream).  A calling thread is bound to a lane by a per-thread ticket
+// (thread -> GPU affinity, SURVEY.md §8(e) "static game -> GPU affinity"), claims an index in the lane's FILLING batch
+// under the lane's short mutex hold, packs its position into the batch record outside the lock and sleeps on the batch's
+// futex word (or keeps the ticket and polls: sb_eval_submit / sb_eval_poll).  With N GPUs there are N independent
+// mutexes, rings and wake-up domains: nothing on the per-evaluation path is shared between GPUs.
 struct HostBatch {
     sb_packed_position* rec = nullptr;   // pinned [max_batch]
-    float* raw = nullptr;                // pinned [max_batch][SB_PLANE_FLOATS], allocated on first unpackable position
+    std::atomic<float*> raw{nullptr};    // pinned [max_batch][SB_PLANE_FLOATS], allocated on first unpackable position
     float* out = nullptr;                // pinned [max_batch][kOutFloats]
-    int count = 0;                       // claimed entries (under Batcher::m)
+    int count = 0;                       // claimed entries (under Lane::m)
     std::atomic<int> ready{0};           // entries whose record is complete
     std::atomic<int> readers{0};         // callers that still have to copy their result out
     std::atomic<uint32_t> done_seq{0};   // futex word: bumped when the results (or the error) are published
@@ -389,7 +376,8 @@ struct HostBatch {
     std::chrono::steady_clock::time_point first, last;   // arrival of the first / the latest position
 };
 
-struct Batcher {
+struct Lane {
+    int gpu = 0;
     std::mutex m;
     std::condition_variable cv_work;     // workers: a batch was closed / the first position of a batch arrived
     std::condition_variable cv_space;    // callers: a batch became free
@@ -397,15 +385,35 @@ struct Batcher {
     std::vector<int> free_list;
     std::deque<int> closed;
     int fill = -1;
-    int batch_size = 0;
-    int wait_us = 200;                   // configured ceiling (reference default gpu_waittime = 2 ms, config.cc:59)
     int cur_wait_us = 200;               // adaptive (cf. batch_forward_pipe.cc:120-147): halved when a timer close saw no
                                          // arrival during the second half of the wait, doubled when batches fill up
-    bool quit = false;
-    std::vector<int> in_flight;          // per replica: batches currently running on that GPU (under m)
-    std::vector<std::chrono::steady_clock::time_point> last_finish;   // per replica: when its latest batch was published
+    int in_flight = 0;                   // batches currently running on this GPU (under m)
+    std::chrono::steady_clock::time_point last_finish;   // when the latest batch of this GPU was published
+};
+
+struct Batcher {
+    std::vector<std::unique_ptr<Lane>> lanes;
+    std::atomic<int> batch_size{0};
+    std::atomic<int> wait_us{200};       // configured ceiling (reference default gpu_waittime = 2 ms, config.cc:59)
+    std::atomic<bool> quit{false};
+    std::atomic<int> outstanding{0};     // calls between claim and result copy (blocking callers and open tickets)
     std::vector<std::thread> workers;
     std::atomic<long long> n_batches{0}, n_positions{0}, n_full{0}, n_timer{0}, n_raw{0};
+    int max_batch = 0;
+    bool buffers_freed = false;
+    void FreeBuffers() {
+        if (buffers_freed) return;
+        for (auto& ln : lanes)
+            for (auto& hb : ln->ring) {
+                cudaFreeHost(hb->rec);
+                cudaFreeHost(hb->raw.load());
+                cudaFreeHost(hb->out);
+                hb->rec = nullptr;
+                hb->raw.store(nullptr);
+                hb->out = nullptr;
+            }
+        buffers_freed = true;
+    }
 };
 
 }  // namespace sb
@@ -427,10 +435,12 @@ struct sb_engine {
     int precision = SB_PRECISION_FP32_SPLIT;
     int collect_stats = 0;
     int stats_launch = -1;   // conv launch index within a forward whose counters are kept (-1: every launch, last wins)
-    int conv_counter = 0;
-    int desc_swap = 0;
     int conv_dbg = 0;
-    int conv_impl = 2;   // 1 = single-CTA conv3x3_tc, 2 = CTA-pair conv3x3_tc2 (default)
+    int chunk_taps = 9;          // split rung: taps per main-accumulator chunk of a 3x3 conv (9 = one chunk per k-half, 3, 1)
+    int acc_comp_ppb = 12;       // split rung: a drained chunk is scaled by 1 + ppb * 1e-9 * (main MMAs of the chunk): the expected
+                                 // loss of the tensor core's truncating fp32 accumulation (measured: the TC - SIMT slope crosses
+                                 // zero at 9-13 ppb on 1..41-layer towers, profiles/r02_precision_probe.log)
+    int fuse_se_pool = 1;        // SE pooling partials come from the conv epilogue (0 = separate pooling pass over the tensor)
     int wide_n = 1;              // fp16 rung: N = 256 tiles for 256-wide layers (read at engine creation / reload)
     int resident_weights = 1;    // fp16 rung: keep a C <= 128 layer's weights in shared memory for the whole launch
     int chain_forwards = 1;      // forwards of different slots of a replica run back to back, never interleaved
@@ -443,13 +453,23 @@ struct sb_engine {
     int pack_threads = 4;
     int batcher_batch = 0;      // 0 = max_batch
     int batcher_wait_us = 200;
-    std::unique_ptr<sb::Batcher> batcher;   // sb_eval
+    std::atomic<sb::Batcher*> batcher{nullptr};             // sb_eval; owned by `batchers`
+    std::vector<std::unique_ptr<sb::Batcher>> batchers;     // the live batcher and the retired ones (freed at sb_destroy: a
+                                                            // caller that raced with a stop may still hold a pointer)
     std::mutex batcher_start_mutex;
-    std::atomic<bool> batcher_on{false};
     std::mutex error_mutex;
     int n_slots = 2;
     bool weights_ready = false;
     std::atomic<long long> launches{0};
+    // weight distribution (DistributeBlob): ONE host->device upload per (re)load, then a device-side broadcast
+    std::vector<void*> nccl_comms;     // ncclComm_t per replica (in-process communicator, created on first use)
+    long long stat_h2d_uploads = 0;    // blob uploads from host memory since creation
+    long long stat_d2d_fills = 0;      // replicas filled device-to-device since creation
+    int bcast_method = 0;              // 0 none (single replica), 1 ncclBroadcast, 2 cudaMemcpyPeerAsync
+    int nccl_version = 0;
+    int verify_ok = 1;                 // device checksums of all replicas agreed after the last (re)load
+    double bcast_ms = 0.0;
+    int use_nccl = 1;                  // option "nccl": 0 forces the peer-copy broadcast
     std::string last_error;
     std::vector<float> host_wT_scratch;
 };
@@ -481,6 +501,7 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.mask);
     cudaFree(s.gb);
     cudaFree(s.pooled);
+    cudaFree(s.pool_part);
     cudaFree(s.counters);
     cudaFree(s.pint);
     cudaFree(s.pass5);
@@ -490,23 +511,29 @@ static void FreeSlot(Slot& s) {
     s = Slot{};
 }
 
+// SE pooling partials from the conv epilogue need row groups (2^L rows) that never straddle two samples: the first sample
+// starts at kGuardRows and every sample covers SS rows.  Returns L in {4, 3, 2}, or 0 when the canvas does not allow it
+// (even board sizes: SS is odd) and the separate pooling kernel has to run.
+static int PoolLog2(const Geom& g) {
+    for (int L = 4; L >= 2; --L)
+        if (g.SS % (1 << L) == 0 && kGuardRows % (1 << L) == 0) return L;
+    return 0;
+}
+
 static void AllocAct(ActBuf& a, int rows, int channels, bool split) {
     a.channels = channels;
     a.rows = rows;
     const size_t bytes = (size_t)rows * channels * sizeof(__half);
     SB_CUDA(cudaMalloc(&a.hi, bytes));
     SB_CUDA(cudaMemset(a.hi, 0, bytes));
-    a.tm_hi = MakeActMap(a.hi, rows, channels / 8);
     a.tm3_hi = MakeActMap3(a.hi, rows, channels / 8);
     a.tm3_lo = a.tm3_hi;
     if (split) {
         SB_CUDA(cudaMalloc(&a.lo, bytes));
         SB_CUDA(cudaMemset(a.lo, 0, bytes));
-        a.tm_lo = MakeActMap(a.lo, rows, channels / 8);
         a.tm3_lo = MakeActMap3(a.lo, rows, channels / 8);
     } else {
         a.lo = a.hi;
-        a.tm_lo = a.tm_hi;
     }
 }
 
@@ -549,6 +576,8 @@ static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int
         SB_CUDA(cudaMemset(s.mask, 0, (size_t)rows));
         SB_CUDA(cudaMalloc(&s.gb, (size_t)e->max_batch * 2 * C * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.pooled, (size_t)e->max_batch * 2 * std::max(C, 64) * sizeof(float)));
+        if (PoolLog2(e->geom) > 0)
+            SB_CUDA(cudaMalloc(&s.pool_part, ((size_t)rows >> PoolLog2(e->geom)) * 2 * C * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.counters, (size_t)e->max_batch * sizeof(int)));
         SB_CUDA(cudaMemset(s.counters, 0, (size_t)e->max_batch * sizeof(int)));
         AllocAct(s.pv, rows, 64, split);
@@ -569,8 +598,6 @@ static void AllocSlots(sb_engine* e, Replica& r) { AllocSlotVec(e, r, r.slots, e
 
 static void MakeConvMaps(const Replica& r, DevConv& c, bool wide_n) {
     const int K = c.L.taps * c.L.cinp;
-    c.tm_hi = MakeMap2D(r.blob + c.L.w_hi, c.L.coutp, K, c.L.bn);
-    c.tm_lo = MakeMap2D(r.blob + c.L.w_lo, c.L.coutp, K, c.L.bn);
     // CTA-pair kernel, fp16 rung: a layer wider than 128 (up to 256) runs as ONE N tile (the accumulators of the fp16
     // rung leave room in TMEM: 2 stages x N <= 512 columns): the activation slab is loaded, and read from shared memory
     // by the tensor core, once instead of once per narrow tile (20bx256: 43 k -> 60 k evals/s)
@@ -612,8 +639,7 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
                         std::to_string(prop.major) + std::to_string(prop.minor)};
     }
     r.sm_count = prop.multiProcessorCount;
-    if (!r.blob) SB_CUDA(cudaMalloc(&r.blob, e->layout.bytes));
-    if (blob) SB_CUDA(cudaMemcpy(r.blob, blob->data(), e->layout.bytes, cudaMemcpyHostToDevice));
+    if (!r.blob) SB_CUDA(cudaMalloc(&r.blob, e->layout.bytes));   // filled by DistributeBlob (one upload + broadcast)
     const int blocks = e->net_shape.blocks;
     r.input.L = e->layout.input;
     const bool wide_n = !Split(e) && e->wide_n;
@@ -644,10 +670,176 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     // widths can coexist in one process
     for (int act = 0; act < 8; ++act) {
         SB_DISPATCH_ACT(act, ACT,
-            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
-            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes));
-            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<true>::kSmemBytes));
-            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<false>::kSmemBytes)));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes)));
+    }
+    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, kIdentity, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
+    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, kIdentity, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes));
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Weight distribution at (re)load.  The reference uploads every tensor to every GPU from host memory
+// (CudaForwardPipe::Construct -> NNGraph::ConstructGraph per device, /root/reference/src/neural/cuda/cuda_forward_pipe.cc:85-116,
+// 440-552 via MallocAndCopy, cuda_common.cc:228-243).  Here the packed blob crosses PCIe ONCE, into replica 0, and is
+// then broadcast device-to-device over NVLink / NVSwitch: ncclBroadcast on an in-process communicator (libnccl.so.2 is
+// opened at run time, so the library still loads on a box without it), or cudaMemcpyPeerAsync when NCCL cannot serve
+// the device list (e.g. two replicas on one device).  A device-side checksum of every replica is compared afterwards.
+typedef int (*NcclCommInitAllFn)(void**, int, const int*);
+typedef int (*NcclCommDestroyFn)(void*);
+typedef int (*NcclGroupFn)();
+typedef int (*NcclBroadcastFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*NcclGetVersionFn)(int*);
+typedef const char* (*NcclGetErrorStringFn)(int);
+struct NcclApi {
+    void* lib = nullptr;
+    NcclCommInitAllFn CommInitAll = nullptr;
+    NcclCommDestroyFn CommDestroy = nullptr;
+    NcclGroupFn GroupStart = nullptr, GroupEnd = nullptr;
+    NcclBroadcastFn Broadcast = nullptr;
+    NcclGetVersionFn GetVersion = nullptr;
+    NcclGetErrorStringFn GetErrorString = nullptr;
+    bool ok = false;
+};
+static NcclApi& Nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.CommInitAll = (NcclCommInitAllFn)dlsym(api.lib, "ncclCommInitAll");
+        api.CommDestroy = (NcclCommDestroyFn)dlsym(api.lib, "ncclCommDestroy");
+        api.GroupStart = (NcclGroupFn)dlsym(api.lib, "ncclGroupStart");
+        api.GroupEnd = (NcclGroupFn)dlsym(api.lib, "ncclGroupEnd");
+        api.Broadcast = (NcclBroadcastFn)dlsym(api.lib, "ncclBroadcast");
+        api.GetVersion = (NcclGetVersionFn)dlsym(api.lib, "ncclGetVersion");
+        api.GetErrorString = (NcclGetErrorStringFn)dlsym(api.lib, "ncclGetErrorString");
+        api.ok = api.CommInitAll && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast;
+    });
+    return api;
+}
+constexpr int kNcclUint8 = 1;   // ncclDataType_t::ncclUint8 (nccl.h)
+
+__global__ void blob_checksum_kernel(const uint64_t* __restrict__ w, size_t n, unsigned long long* out) {
+    uint64_t h = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t z = w[i] + (i + 1) * 0x9e3779b97f4a7c15ull;     // position-dependent splitmix64 finaliser, summed
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        h += z ^ (z >> 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)h);
+}
+
+static uint64_t DeviceChecksum(sb_engine* e, Replica& r) {
+    SB_CUDA(cudaSetDevice(r.device));
+    unsigned long long* d = nullptr;
+    SB_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    SB_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
+    blob_checksum_kernel<<<r.sm_count * 4, 256>>>(reinterpret_cast<const uint64_t*>(r.blob), e->layout.bytes / 8, d);
+    unsigned long long h = 0;
+    cudaError_t err = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    SB_CUDA(err);
+    e->launches++;
+    return h;
+}
+
+static void DestroyComms(sb_engine* e) {
+    if (!e->nccl_comms.empty() && Nccl().ok)
+        for (void* c : e->nccl_comms)
+            if (c) Nccl().CommDestroy(c);
+    e->nccl_comms.clear();
+}
+
+// `host_blob` == nullptr: replica 0 already holds the blob (sb_weights_import), broadcast only.
+static void DistributeBlob(sb_engine* e, const std::vector<uint8_t>* host_blob) {
+    const size_t bytes = e->layout.bytes;
+    const int n = (int)e->replicas.size();
+    Replica& r0 = e->replicas[0];
+    SB_CUDA(cudaSetDevice(r0.device));
+    if (host_blob) {
+        SB_CUDA(cudaMemcpy(r0.blob, host_blob->data(), bytes, cudaMemcpyHostToDevice));   // the ONLY PCIe crossing of the weights
+        e->stat_h2d_uploads++;
+    }
+    e->bcast_method = 0;
+    e->bcast_ms = 0.0;
+    if (n > 1) {
+        const auto t0 = std::chrono::steady_clock::now();
+        bool done = false;
+        std::vector<int> devs;
+        for (Replica& r : e->replicas) devs.push_back(r.device);
+        std::vector<int> uniq = devs;
+        std::sort(uniq.begin(), uniq.end());
+        const bool distinct = std::adjacent_find(uniq.begin(), uniq.end()) == uniq.end();
+        if (e->use_nccl && distinct && Nccl().ok) {
+            NcclApi& nc = Nccl();
+            if (e->nccl_comms.empty()) {
+                e->nccl_comms.assign(n, nullptr);
+                if (nc.CommInitAll(e->nccl_comms.data(), n, devs.data()) != 0) e->nccl_comms.clear();
+                if (nc.GetVersion) nc.GetVersion(&e->nccl_version);
+            }
+            if (!e->nccl_comms.empty()) {
+                std::vector<cudaStream_t> st(n, nullptr);
+                for (int i = 0; i < n; ++i) {
+                    SB_CUDA(cudaSetDevice(devs[i]));
+                    SB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+                }
+                int rc = nc.GroupStart();
+                for (int i = 0; i < n && rc == 0; ++i) {
+                    SB_CUDA(cudaSetDevice(devs[i]));
+                    rc = nc.Broadcast(e->replicas[i].blob, e->replicas[i].blob, bytes, kNcclUint8, 0, e->nccl_comms[i], st[i]);
+                }
+                const int rc_end = nc.GroupEnd();
+                if (rc == 0) rc = rc_end;
+                for (int i = 0; i < n; ++i) {
+                    SB_CUDA(cudaSetDevice(devs[i]));
+                    cudaError_t se = cudaStreamSynchronize(st[i]);
+                    cudaStreamDestroy(st[i]);
+                    SB_CUDA(se);
+                }
+                if (rc != 0)
+                    throw CudaError{std::string("ncclBroadcast of the weight blob failed: ") +
+                                    (nc.GetErrorString ? nc.GetErrorString(rc) : "unknown NCCL error")};
+                e->bcast_method = 1;
+                done = true;
+            }
+        }
+        if (!done) {   // peer copies replica 0 -> replica i (NVLink P2P when the devices differ; plain D2D on one device)
+            SB_CUDA(cudaSetDevice(r0.device));
+            for (int i = 1; i < n; ++i) {
+                if (devs[i] != r0.device) {
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, r0.device, devs[i]);
+                    if (can) {
+                        cudaError_t pe = cudaDeviceEnablePeerAccess(devs[i], 0);
+                        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) SB_CUDA(pe);
+                        cudaGetLastError();
+                    }
+                }
+                SB_CUDA(cudaMemcpyPeerAsync(e->replicas[i].blob, devs[i], r0.blob, r0.device, bytes, 0));
+            }
+            SB_CUDA(cudaDeviceSynchronize());
+            e->bcast_method = 2;
+        }
+        e->stat_d2d_fills += n - 1;
+        e->bcast_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    // every replica must hold the same bytes
+    e->verify_ok = 1;
+    if (n > 1) {
+        const uint64_t h0 = DeviceChecksum(e, r0);
+        for (int i = 1; i < n; ++i) {
+            if (DeviceChecksum(e, e->replicas[i]) != h0) {
+                e->verify_ok = 0;
+                throw CudaError{"weight broadcast verification failed: replica " + std::to_string(i) + " differs from replica 0"};
+            }
+        }
     }
 }
 
@@ -691,7 +883,7 @@ struct ConvTimer {
 };
 
 static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, const ActBuf& in, ActBuf& out,
-                       const ActBuf* res, int act, int n, ConvTimer* tm) {
+                       const ActBuf* res, int act, int n, ConvTimer* tm, bool pool = false) {
     const int n_super = e->geom.n_super(n);
     if (tm && tm->on) tm->conv_launches++;
     if (e->precision == SB_PRECISION_SIMT_DEBUG) {
@@ -712,74 +904,74 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.cout = c.L.cout;
         p.rows = out.rows;
         p.kh = c.L.kh;
-        p.bn = c.L.bn;
         p.n_super = n_super;
-        p.n_ntiles = c.L.ntiles;
-        p.n_full = n_super * c.L.ntiles;
-        p.n_units = p.n_full;
-        p.resident = 0;
         p.pitch = e->geom.P;
         p.ntaps = c.L.taps;
         p.dbg = e->conv_dbg;
-        p.a_lbo = e->desc_swap ? 128 : kSlabRows * 16;
-        p.a_sbo = e->desc_swap ? kSlabRows * 16 : 128;
+        // split rung: the main accumulator is drained and re-accumulated in fp32 RN every `chunk_steps` (k-half, tap) steps
+        // (conv3x3_tc2.cuh, "Precision"); a 1x1 convolution (<= 24 main MMAs) is one chunk
+        p.chunk_steps = (c.L.taps == 9 && e->chunk_taps > 0) ? e->chunk_taps : c.L.kh * c.L.taps;   // chunk_taps 0: one chunk per item
+        p.chunk_scale = 1.0f + 1e-9f * (float)e->acc_comp_ppb * (float)(4 * std::min(p.chunk_steps, c.L.kh * c.L.taps));
+        p.pool_part = pool ? s.pool_part : nullptr;
+        p.pool_log2 = PoolLog2(e->geom);
+        p.pool_groups = (n * e->geom.SS) >> std::max(p.pool_log2, 1);
+        p.pool_c = e->net_shape.channels;
         p.err = s.d_err;
-        p.stats = (e->collect_stats && (e->stats_launch < 0 || e->stats_launch == e->conv_counter)) ? s.d_stats : nullptr;
-        e->conv_counter++;
-        const int items = n_super * c.L.ntiles;
-        const int grid = std::min(items, r.sm_count);
-        if (e->conv_impl == 2) {
-            // Small batches: narrow the N tile (bn >> level) while all items still fit in one wave, so that a handful of
-            // positions is spread over up to 4x more CTA pairs (latency of the single-position / GTP case).
-            int level = 0;
-            const int max_pairs = r.sm_count / 2;
-            while (e->small_batch_split && level + 1 < c.levels && level < 2 &&
-                   n_super * (c.L.coutp / (c.bn0 >> (level + 1))) <= max_pairs)
-                ++level;
-            p.bn = c.bn0 >> level;
-            p.n_ntiles = c.L.coutp / p.bn;
-            const int items2 = n_super * p.n_ntiles;
-            // fp16 rung, one N tile, <= 18 weight stages per item: weights stay resident in shared memory
-            p.resident = (e->resident_weights && !Split(e) && p.n_ntiles == 1 && c.L.kh * c.L.taps <= Conv2Cfg<false>::kNumBStages &&
-                          items2 > max_pairs) ? 1 : 0;
-            // persistent CTA pairs; the items of a partial last wave are split into N-halves when that makes the
-            // wave half as long (conv_unit in conv3x3_tc2.cuh)
-            const int pairs = std::min(items2, max_pairs);
-            const int grid2 = 2 * pairs;
-            const int rem = items2 % pairs;
-            int n_tail = 0;
-            if (e->tail_split && !p.resident && items2 > pairs && rem > 0 && 2 * rem <= pairs && level + 1 < c.levels) n_tail = rem;
-            p.n_full = items2 - n_tail;
-            p.n_units = items2 + n_tail;
-            const CUtensorMap& w_hi = c.tm2_hi[level];
-            const CUtensorMap& w_lo = c.tm2_lo[level];
-            const CUtensorMap& wq_hi = c.tm2_hi[level + 1];
-            const CUtensorMap& wq_lo = c.tm2_lo[level + 1];
-            // launched with the programmatic-stream-serialization attribute: see pdl_wait() in conv3x3_tc2.cuh
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid2);
-            cfg.blockDim = dim3(Split(e) ? Conv2Cfg<true>::kThreads : Conv2Cfg<false>::kThreads);
-            cfg.stream = s.stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
+        p.stats = (e->collect_stats && (e->stats_launch < 0 || e->stats_launch == s.conv_counter)) ? s.d_stats : nullptr;
+        s.conv_counter++;
+        // Small batches: narrow the N tile (bn >> level) while all items still fit in one wave, so that a handful of
+        // positions is spread over up to 4x more CTA pairs (latency of the single-position / GTP case).
+        int level = 0;
+        const int max_pairs = r.sm_count / 2;
+        while (e->small_batch_split && level + 1 < c.levels && level < 2 &&
+               n_super * (c.L.coutp / (c.bn0 >> (level + 1))) <= max_pairs)
+            ++level;
+        p.bn = c.bn0 >> level;
+        p.n_ntiles = c.L.coutp / p.bn;
+        const int items2 = n_super * p.n_ntiles;
+        // fp16 rung, one N tile, <= 18 weight stages per item: weights stay resident in shared memory
+        p.resident = (e->resident_weights && !Split(e) && p.n_ntiles == 1 && c.L.kh * c.L.taps <= Conv2Cfg<false>::kNumBStages &&
+                      items2 > max_pairs) ? 1 : 0;
+        // persistent CTA pairs; the items of a partial last wave are split into N-halves when that makes the
+        // wave half as long (conv_unit in conv3x3_tc2.cuh)
+        const int pairs = std::min(items2, max_pairs);
+        const int grid2 = 2 * pairs;
+        const int rem = items2 % pairs;
+        int n_tail = 0;
+        if (e->tail_split && !p.resident && items2 > pairs && rem > 0 && 2 * rem <= pairs && level + 1 < c.levels) n_tail = rem;
+        p.n_full = items2 - n_tail;
+        p.n_units = items2 + n_tail;
+        const CUtensorMap& w_hi = c.tm2_hi[level];
+        const CUtensorMap& w_lo = c.tm2_lo[level];
+        const CUtensorMap& wq_hi = c.tm2_hi[level + 1];
+        const CUtensorMap& wq_lo = c.tm2_lo[level + 1];
+        // launched with the programmatic-stream-serialization attribute: see pdl_wait() in conv3x3_tc2.cuh
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid2);
+        cfg.blockDim = dim3(Split(e) ? Conv2Cfg<true>::kThreads : Conv2Cfg<false>::kThreads);
+        cfg.stream = s.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (pool) {   // the last convolution of an SE block: identity activation, pooling partials from the epilogue
+            if (act != kIdentity) throw CudaError{"internal error: pooled convolution with an activation"};
             if (Split(e)) {
                 cfg.dynamicSmemBytes = Conv2Cfg<true>::kSmemBytes;
-                SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, ACT>, in.tm3_hi, in.tm3_lo, w_hi,
-                                                                      w_lo, wq_hi, wq_lo, p)));
+                SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, kIdentity, true>, in.tm3_hi, in.tm3_lo, w_hi, w_lo, wq_hi, wq_lo, p));
             } else {
                 cfg.dynamicSmemBytes = Conv2Cfg<false>::kSmemBytes;
-                SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT>, in.tm3_hi, in.tm3_hi, w_hi,
-                                                                      w_hi, wq_hi, wq_hi, p)));
+                SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, kIdentity, true>, in.tm3_hi, in.tm3_hi, w_hi, w_hi, wq_hi, wq_hi, p));
             }
         } else if (Split(e)) {
-            SB_DISPATCH_ACT(act, ACT, (conv3x3_tc_kernel<true, ACT><<<grid, 384, ConvCfg<true>::kSmemBytes, s.stream>>>(
-                                          in.tm_hi, in.tm_lo, c.tm_hi, c.tm_lo, p)));
+            cfg.dynamicSmemBytes = Conv2Cfg<true>::kSmemBytes;
+            SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, ACT, false>, in.tm3_hi, in.tm3_lo, w_hi,
+                                                                  w_lo, wq_hi, wq_lo, p)));
         } else {
-            SB_DISPATCH_ACT(act, ACT, (conv3x3_tc_kernel<false, ACT><<<grid, 384, ConvCfg<false>::kSmemBytes, s.stream>>>(
-                                          in.tm_hi, in.tm_hi, c.tm_hi, c.tm_hi, p)));
+            cfg.dynamicSmemBytes = Conv2Cfg<false>::kSmemBytes;
+            SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT, false>, in.tm3_hi, in.tm3_hi, w_hi,
+                                                                  w_hi, wq_hi, wq_hi, p)));
         }
     }
     SB_CUDA(cudaGetLastError());
@@ -828,7 +1020,9 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     const BlobLayout& L = e->layout;
     auto F = [&](size_t off) { return reinterpret_cast<const float*>(r.blob + off); };
 
-    e->conv_counter = 0;
+    s.conv_counter = 0;
+    const int pool_log2 = PoolLog2(g);
+    const bool pool_fused = e->fuse_se_pool && pool_log2 > 0 && e->precision != SB_PRECISION_SIMT_DEBUG;
     auto mark = [&]() { if (tm) tm->Mark(s.stream); };   // brackets groups of non-convolution kernels (profiling pass)
     mark();
     {   // input planes -> canvas
@@ -856,24 +1050,25 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
         const ActBuf* last_res = se > 0 ? nullptr : x;
         const int last_act = se > 0 ? kIdentity : act;
         const ActBuf* se_skip = x;
+        const bool pool = se > 0 && pool_fused;
         if (e->block_types[b] == SB_BLOCK_MIXER) {
             // MixerBlockForward, blas_forward_pipe.cc:265-312: y = act(dw(x) + b) + x ; out = ffn2(act(ffn1(y))) (+ y)
             mark();
             LaunchDw(e, s, L.bdw[b], r.blob, *x, *t, act, true, n, n_rows);
             mark();
             LaunchConv(e, r, s, cv[0], *t, s.ia, nullptr, act, n, tm);
-            LaunchConv(e, r, s, cv[1], s.ia, *u, se > 0 ? nullptr : t, last_act, n, tm);
+            LaunchConv(e, r, s, cv[1], s.ia, *u, se > 0 ? nullptr : t, last_act, n, tm, pool);
             se_skip = t;   // the skip of this block and of its SE unit is y
         } else if (e->block_types[b] == SB_BLOCK_RESIDUAL) {
             // ResidualBlockForward, blas_forward_pipe.cc:46-88
             LaunchConv(e, r, s, cv[0], *x, *t, nullptr, act, n, tm);
-            LaunchConv(e, r, s, cv[1], *t, *u, last_res, last_act, n, tm);
+            LaunchConv(e, r, s, cv[1], *t, *u, last_res, last_act, n, tm, pool);
         } else if (e->block_types[b] == SB_BLOCK_BOTTLENECK) {
             // BottleneckBlockForward, blas_forward_pipe.cc:90-162: 1x1 down, 3x3, 3x3, 1x1 up (+ skip)
             LaunchConv(e, r, s, cv[0], *x, s.ia, nullptr, act, n, tm);
             LaunchConv(e, r, s, cv[1], s.ia, s.ib, nullptr, act, n, tm);
             LaunchConv(e, r, s, cv[2], s.ib, s.ic, nullptr, act, n, tm);
-            LaunchConv(e, r, s, cv[3], s.ic, *u, last_res, last_act, n, tm);
+            LaunchConv(e, r, s, cv[3], s.ic, *u, last_res, last_act, n, tm, pool);
         } else {
             // NestedBottleneckBlockForward, blas_forward_pipe.cc:164-263: 1x1 down, two inner residual blocks, 1x1 up
             LaunchConv(e, r, s, cv[0], *x, s.ia, nullptr, act, n, tm);       // a
@@ -881,15 +1076,22 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
             LaunchConv(e, r, s, cv[2], s.ib, s.ic, &s.ia, act, n, tm);       // c = act(conv2(b) + a)
             LaunchConv(e, r, s, cv[3], s.ic, s.ib, nullptr, act, n, tm);     // d = act(conv3(c))
             LaunchConv(e, r, s, cv[4], s.ib, s.ia, &s.ic, act, n, tm);       // e = act(conv4(d) + c)
-            LaunchConv(e, r, s, cv[5], s.ia, *u, last_res, last_act, n, tm);
+            LaunchConv(e, r, s, cv[5], s.ia, *u, last_res, last_act, n, tm, pool);
         }
         if (se > 0) {
             mark();
             const size_t smem = ((size_t)3 * C + se) * sizeof(float);
-            SB_DISPATCH_ACT(act, ACT, LaunchPdl(e, n, se_pool_fc_kernel<ACT>, dim3((C + 63) / 64, n), dim3(256), smem, s.stream,
-                                                (const __half*)u->hi, (const __half*)u->lo, split, (const uint8_t*)s.mask, d_sizes, g, C,
-                                                u->rows, se, F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
-                                                F(L.excite[b].b), s.pooled, s.counters, s.gb, e->conv_dbg));
+            if (pool_fused) {
+                // the block's last convolution left per-(16-row group, channel) sums and maxima: fixed-order finalize + FCs
+                SB_DISPATCH_ACT(act, ACT, LaunchPdl(e, n, se_fc_kernel<ACT>, dim3(n), dim3(256), smem, s.stream,
+                                                    (const float*)s.pool_part, g.SS >> pool_log2, d_sizes, C, se, F(L.squeeze[b].w),
+                                                    F(L.squeeze[b].b), F(L.excite[b].w), F(L.excite[b].b), s.gb));
+            } else {
+                SB_DISPATCH_ACT(act, ACT, LaunchPdl(e, n, se_pool_fc_kernel<ACT>, dim3((C + 63) / 64, n), dim3(256), smem, s.stream,
+                                                    (const __half*)u->hi, (const __half*)u->lo, split, (const uint8_t*)s.mask, d_sizes, g, C,
+                                                    u->rows, se, F(L.squeeze[b].w), F(L.squeeze[b].b), F(L.excite[b].w),
+                                                    F(L.excite[b].b), s.pooled, s.counters, s.gb, e->conv_dbg));
+            }
             SB_CUDA(cudaGetLastError());
             const size_t total = (size_t)n_rows * (C / 8);
             SB_DISPATCH_ACT(act, ACT, LaunchPdl(e, n, se_apply_kernel<ACT>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s.stream,
@@ -1065,9 +1267,11 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
             e->replicas[i].device = gpus[i];
             BuildReplica(e.get(), e->replicas[i], net ? &blob : nullptr);
         }
+        if (net) DistributeBlob(e.get(), &blob);
         e->weights_ready = net != nullptr;
         Configure(e.get(), board, max_batch);
     } catch (const CudaError& ce) {
+        DestroyComms(e.get());
         for (Replica& r : e->replicas) DestroyReplica(r);
         return Fail(nullptr, SB_ERR_CUDA, ce.msg);
     }
@@ -1208,16 +1412,16 @@ static void FutexWakeAll(std::atomic<uint32_t>* a) {
 
 constexpr int kBatcherSlots = 2;   // worker threads (= device slots = streams) per GPU
 
-// caller holds B.m: the FILLING batch stops accepting positions; the next free batch (if any) takes over
-static int CloseFill(Batcher& B) {
-    const int idx = B.fill;
-    HostBatch& hb = *B.ring[idx];
+// caller holds L.m: the FILLING batch stops accepting positions; the next free batch (if any) takes over
+static int CloseFill(Lane& L) {
+    const int idx = L.fill;
+    HostBatch& hb = *L.ring[idx];
     hb.readers.store(hb.count, std::memory_order_relaxed);
-    if (B.free_list.empty()) {
-        B.fill = -1;
+    if (L.free_list.empty()) {
+        L.fill = -1;
     } else {
-        B.fill = B.free_list.back();
-        B.free_list.pop_back();
+        L.fill = L.free_list.back();
+        L.free_list.pop_back();
     }
     return idx;
 }
@@ -1228,10 +1432,11 @@ static void RunHostBatch(sb_engine* e, Replica& r, Slot& s, HostBatch& hb) {
         cudaGetLastError();
         SB_CUDA(cudaMemcpyAsync(s.d_packed, hb.rec, (size_t)n * sizeof(sb_packed_position), cudaMemcpyHostToDevice, s.stream));
         if (hb.any_raw.load(std::memory_order_relaxed)) {
+            const float* raw = hb.raw.load(std::memory_order_acquire);
             for (int i = 0; i < n; ++i) {
                 if (hb.rec[i].flags & SB_PACKED_RAW) {
                     const int bs = hb.rec[i].board_size;
-                    SB_CUDA(cudaMemcpyAsync(s.d_in + (size_t)i * SB_PLANE_FLOATS, hb.raw + (size_t)i * SB_PLANE_FLOATS,
+                    SB_CUDA(cudaMemcpyAsync(s.d_in + (size_t)i * SB_PLANE_FLOATS, raw + (size_t)i * SB_PLANE_FLOATS,
                                             (size_t)SB_INPUT_CHANNELS * bs * bs * sizeof(float), cudaMemcpyHostToDevice, s.stream));
                 }
             }
@@ -1252,216 +1457,325 @@ static void RunHostBatch(sb_engine* e, Replica& r, Slot& s, HostBatch& hb) {
     }
 }
 
-static void BatchWorker(sb_engine* e, int gpu, int k) {
-    Batcher& B = *e->batcher;
+static void PublishBatch(HostBatch& hb) {
+    hb.done_seq.fetch_add(1, std::memory_order_release);
+    FutexWakeAll(&hb.done_seq);
+}
+
+static void BatchWorker(sb_engine* e, Batcher* Bp, int gpu, int k) {
+    Batcher& B = *Bp;
+    Lane& L = *B.lanes[gpu];
     Replica& r = e->replicas[gpu];
     Slot& s = r.bslots[k];
     cudaSetDevice(r.device);
     for (;;) {
         int idx = -1;
         {
-            std::unique_lock<std::mutex> lk(B.m);
+            std::unique_lock<std::mutex> lk(L.m);
             for (;;) {
-                if (B.quit) return;
-                if (!B.closed.empty()) {
-                    idx = B.closed.front();
-                    B.closed.pop_front();
+                if (B.quit.load(std::memory_order_relaxed)) return;
+                if (!L.closed.empty()) {
+                    idx = L.closed.front();
+                    L.closed.pop_front();
                     break;
                 }
-                if (B.fill >= 0 && B.ring[B.fill]->count > 0) {
-                    HostBatch& hb = *B.ring[B.fill];
-                    if (B.in_flight[gpu] > 0) {
+                if (L.fill >= 0 && L.ring[L.fill]->count > 0) {
+                    HostBatch& hb = *L.ring[L.fill];
+                    if (L.in_flight > 0) {
                         // this GPU is busy (forwards of its slots are chained, a second one could not start anyway): let
                         // the partial batch grow until it is full or the running batch has finished — with few search
                         // threads this is what keeps all of them in ONE batch instead of two half-size ones
-                        B.cv_work.wait(lk);
+                        L.cv_work.wait(lk);
                         continue;
                     }
                     // the timer runs from the batch's first position or, if later, from the moment this GPU published its
                     // previous batch: the callers it just released need a few tens of microseconds to come back, and
                     // closing before that splits a handful of search threads into two alternating half-size batches
-                    const auto deadline = std::max(hb.first, B.last_finish[gpu]) + std::chrono::microseconds(B.cur_wait_us);
+                    const auto deadline = std::max(hb.first, L.last_finish) + std::chrono::microseconds(L.cur_wait_us);
                     const auto now = std::chrono::steady_clock::now();
                     if (now >= deadline) {
                         // closed by the timer.  If nothing joined during the second half of the wait, every caller that was
                         // going to come is already in (few search threads, or a CPU-bound front-end): waiting that long was
                         // futile, halve it (the reference drops its wait to zero in this case, batch_forward_pipe.cc:139-143)
-                        if (now - hb.last > std::chrono::microseconds(B.cur_wait_us / 2)) B.cur_wait_us /= 2;
-                        idx = CloseFill(B);
+                        if (now - hb.last > std::chrono::microseconds(L.cur_wait_us / 2)) L.cur_wait_us /= 2;
+                        idx = CloseFill(L);
                         B.n_timer++;
                         break;
                     }
-                    B.cv_work.wait_until(lk, deadline);
+                    L.cv_work.wait_until(lk, deadline);
                 } else {
                     // idle: restore the configured wait step by step (batch_forward_pipe.cc:132-138)
-                    B.cur_wait_us = std::min(B.wait_us, B.cur_wait_us + std::max(1, B.wait_us / 8));
-                    B.cv_work.wait(lk);
+                    const int w = B.wait_us.load(std::memory_order_relaxed);
+                    L.cur_wait_us = std::min(w, L.cur_wait_us + std::max(1, w / 8));
+                    L.cv_work.wait(lk);
                 }
             }
-            B.in_flight[gpu]++;
+            L.in_flight++;
         }
-        HostBatch& hb = *B.ring[idx];
+        HostBatch& hb = *L.ring[idx];
         while (hb.ready.load(std::memory_order_acquire) < hb.count) std::this_thread::yield();   // packers still writing
         RunHostBatch(e, r, s, hb);
         B.n_batches++;
         B.n_positions += hb.count;
-        hb.done_seq.fetch_add(1, std::memory_order_release);
-        FutexWakeAll(&hb.done_seq);
+        PublishBatch(hb);
         {
-            std::lock_guard<std::mutex> lk(B.m);
-            B.in_flight[gpu]--;
-            B.last_finish[gpu] = std::chrono::steady_clock::now();
+            std::lock_guard<std::mutex> lk(L.m);
+            L.in_flight--;
+            L.last_finish = std::chrono::steady_clock::now();
         }
-        B.cv_work.notify_all();   // a partial batch that was growing behind this one may be closed now
+        L.cv_work.notify_all();   // a partial batch that was growing behind this one may be closed now
     }
 }
 
+// Stops the workers and FAILS every position that was claimed but not yet evaluated (its caller returns SB_ERR_STATE):
+// nobody stays blocked on a batch that will never run.  The Batcher object itself is retired, not deleted: a caller that
+// loaded the pointer just before the stop finds `quit` set and leaves.  Its pinned buffers are released once no call
+// is in flight (immediately in the normal case).
 static void StopBatcher(sb_engine* e) {
     std::lock_guard<std::mutex> g(e->batcher_start_mutex);
-    if (!e->batcher) return;
-    Batcher& B = *e->batcher;
-    {
-        std::lock_guard<std::mutex> lk(B.m);
-        B.quit = true;
+    Batcher* Bp = e->batcher.load(std::memory_order_acquire);
+    if (!Bp) return;
+    Batcher& B = *Bp;
+    B.quit.store(true, std::memory_order_release);
+    for (auto& ln : B.lanes) {
+        { std::lock_guard<std::mutex> lk(ln->m); }   // callers / workers inside the lock have seen `quit` after this
+        ln->cv_work.notify_all();
+        ln->cv_space.notify_all();
     }
-    B.cv_work.notify_all();
-    B.cv_space.notify_all();
     for (auto& t : B.workers) t.join();
-    for (auto& hb : B.ring) {
-        cudaFreeHost(hb->rec);
-        cudaFreeHost(hb->raw);
-        cudaFreeHost(hb->out);
+    B.workers.clear();
+    for (auto& ln : B.lanes) {
+        std::vector<int> pending;
+        {
+            std::lock_guard<std::mutex> lk(ln->m);
+            for (int idx : ln->closed) pending.push_back(idx);
+            ln->closed.clear();
+            if (ln->fill >= 0 && ln->ring[ln->fill]->count > 0) {
+                ln->ring[ln->fill]->readers.store(ln->ring[ln->fill]->count, std::memory_order_relaxed);
+                pending.push_back(ln->fill);
+            }
+            ln->fill = -1;
+        }
+        for (int idx : pending) {
+            HostBatch& hb = *ln->ring[idx];
+            hb.rc = SB_ERR_STATE;
+            hb.err = "the batcher was stopped (sb_reconfigure / sb_reload_weights / sb_destroy) before this position was evaluated";
+            PublishBatch(hb);
+        }
     }
+    for (int spin = 0; spin < 2000 && B.outstanding.load(std::memory_order_acquire) > 0; ++spin)
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    if (B.outstanding.load(std::memory_order_acquire) == 0) B.FreeBuffers();   // else: kept until sb_destroy (open tickets)
     for (Replica& r : e->replicas) {
         if (r.device >= 0) cudaSetDevice(r.device);
         for (Slot& s : r.bslots) FreeSlot(s);
         r.bslots.clear();
         r.chain_tail = nullptr;
     }
-    e->batcher_on.store(false, std::memory_order_release);
-    e->batcher.reset();
+    e->batcher.store(nullptr, std::memory_order_release);
 }
 
 // Starts the worker threads on first use.  Throws CudaError.
-static void StartBatcher(sb_engine* e) {
+static Batcher* StartBatcher(sb_engine* e) {
     std::lock_guard<std::mutex> g(e->batcher_start_mutex);
-    if (e->batcher) return;
+    if (Batcher* live = e->batcher.load(std::memory_order_acquire)) return live;
     std::unique_ptr<Batcher> B(new Batcher);
+    B->max_batch = e->max_batch;
     B->batch_size = e->batcher_batch > 0 ? std::min(e->batcher_batch, e->max_batch) : e->max_batch;
-    B->wait_us = B->cur_wait_us = e->batcher_wait_us;
-    const int n_workers = (int)e->replicas.size() * kBatcherSlots;
-    // one batch per worker in flight, one filling, one spare — plus enough further entries that a few thousand blocked
-    // callers all find a slot: callers that find no FILLING batch sleep on one condition variable and are all woken
-    // when a batch is recycled (measured: 4096 callers on a 4 x 256 ring ran 10x slower than 256 callers)
-    const int n_ring = n_workers + 2 + std::min(14, std::max(0, 4096 / std::max(1, e->max_batch)));
-    for (int i = 0; i < n_ring; ++i) {
-        std::unique_ptr<HostBatch> hb(new HostBatch);
-        SB_CUDA(cudaHostAlloc(&hb->rec, (size_t)e->max_batch * sizeof(sb_packed_position), cudaHostAllocPortable));
-        SB_CUDA(cudaHostAlloc(&hb->out, (size_t)e->max_batch * kOutFloats * sizeof(float), cudaHostAllocPortable));
-        B->ring.push_back(std::move(hb));
-        if (i > 0) B->free_list.push_back(i);
+    B->wait_us = e->batcher_wait_us;
+    // per lane: one batch per worker in flight, one filling, one spare — plus enough further entries that a few thousand
+    // blocked callers all find a slot: callers that find no FILLING batch sleep on one condition variable and are all
+    // woken when a batch is recycled (measured: 4096 callers on a 4 x 256 ring ran 10x slower than 256 callers)
+    const int n_lanes = (int)e->replicas.size();
+    const int n_ring = kBatcherSlots + 2 + std::min(14, std::max(0, 4096 / std::max(1, e->max_batch * n_lanes)));
+    for (int g2 = 0; g2 < n_lanes; ++g2) {
+        std::unique_ptr<Lane> L(new Lane);
+        L->gpu = g2;
+        L->cur_wait_us = e->batcher_wait_us;
+        L->last_finish = std::chrono::steady_clock::now();
+        for (int i = 0; i < n_ring; ++i) {
+            std::unique_ptr<HostBatch> hb(new HostBatch);
+            SB_CUDA(cudaHostAlloc(&hb->rec, (size_t)e->max_batch * sizeof(sb_packed_position), cudaHostAllocPortable));
+            SB_CUDA(cudaHostAlloc(&hb->out, (size_t)e->max_batch * kOutFloats * sizeof(float), cudaHostAllocPortable));
+            L->ring.push_back(std::move(hb));
+            if (i > 0) L->free_list.push_back(i);
+        }
+        L->fill = 0;
+        B->lanes.push_back(std::move(L));
     }
-    B->fill = 0;
-    B->in_flight.assign(e->replicas.size(), 0);
-    B->last_finish.assign(e->replicas.size(), std::chrono::steady_clock::now());
     for (Replica& r : e->replicas) AllocSlotVec(e, r, r.bslots, kBatcherSlots);
-    e->batcher = std::move(B);
-    for (int g2 = 0; g2 < (int)e->replicas.size(); ++g2)
-        for (int k = 0; k < kBatcherSlots; ++k) e->batcher->workers.emplace_back(BatchWorker, e, g2, k);
-    e->batcher_on.store(true, std::memory_order_release);
+    Batcher* raw = B.get();
+    e->batchers.push_back(std::move(B));
+    for (int g2 = 0; g2 < n_lanes; ++g2)
+        for (int k = 0; k < kBatcherSlots; ++k) raw->workers.emplace_back(BatchWorker, e, raw, g2, k);
+    e->batcher.store(raw, std::memory_order_release);
+    return raw;
 }
 
-static int EvalImpl(sb_engine* e, const float* planes, int board_size, int offset, sb_output* out) {
-    if (!e || !planes || !out) return SB_ERR_INVALID;
+// thread -> lane affinity: every calling thread draws one ticket for its lifetime
+static std::atomic<unsigned> g_lane_ticket{0};
+static unsigned ThreadTicket() {
+    thread_local unsigned t = g_lane_ticket.fetch_add(1, std::memory_order_relaxed);
+    return t;
+}
+
+constexpr int kTicketFailed = 1;   // sb_eval_ticket::flags: the position could not be staged, the call returns an error
+
+// First half of an evaluation: claim an entry of the lane's FILLING batch, pack the position into it.
+static int EvalBegin(sb_engine* e, const float* planes, int board_size, int offset, sb_eval_ticket* t) {
+    if (!e || !planes || !t) return SB_ERR_INVALID;
     if (board_size < 2 || board_size > e->geom.N) return Fail(e, SB_ERR_INVALID, "board size of a sample exceeds the NN canvas");
     if (offset < 0 || offset > 4) return Fail(e, SB_ERR_INVALID, "policy offset must be in [0, 4]");
     if (!e->weights_ready) return Fail(e, SB_ERR_STATE, "weights have not been loaded");
-    if (!e->batcher_on.load(std::memory_order_acquire)) {
+    Batcher* Bp = e->batcher.load(std::memory_order_acquire);
+    if (!Bp) {
         try {
-            StartBatcher(e);
+            Bp = StartBatcher(e);
         } catch (const CudaError& ce) {
             return Fail(e, SB_ERR_CUDA, ce.msg);
         }
     }
-    Batcher& B = *e->batcher;
+    Batcher& B = *Bp;
+    B.outstanding.fetch_add(1, std::memory_order_acq_rel);
+    const int lane = (int)(ThreadTicket() % (unsigned)B.lanes.size());
+    Lane& L = *B.lanes[lane];
     HostBatch* hb = nullptr;
     int idx = -1, i = -1;
     uint32_t seq0 = 0;
     {
-        std::unique_lock<std::mutex> lk(B.m);
-        while (B.fill < 0 && !B.quit) B.cv_space.wait(lk);
-        if (B.quit) return Fail(e, SB_ERR_STATE, "the batcher is shutting down");
-        idx = B.fill;
-        hb = B.ring[idx].get();
+        std::unique_lock<std::mutex> lk(L.m);
+        while (L.fill < 0 && !B.quit.load(std::memory_order_relaxed)) L.cv_space.wait(lk);
+        if (B.quit.load(std::memory_order_relaxed)) {
+            lk.unlock();
+            B.outstanding.fetch_sub(1, std::memory_order_acq_rel);
+            std::lock_guard<std::mutex> el(e->error_mutex);
+            return Fail(e, SB_ERR_STATE, "the batcher is shutting down");
+        }
+        idx = L.fill;
+        hb = L.ring[idx].get();
         i = hb->count++;
         seq0 = hb->done_seq.load(std::memory_order_relaxed);
         hb->last = std::chrono::steady_clock::now();
         if (i == 0) hb->first = hb->last;
-        if (hb->count >= B.batch_size) {
+        if (hb->count >= B.batch_size.load(std::memory_order_relaxed)) {
             // filled before its timer: traffic is high, a longer wait costs nothing and keeps batches full
-            B.cur_wait_us = std::min(B.wait_us, B.cur_wait_us * 2 + 10);
-            B.closed.push_back(CloseFill(B));
+            L.cur_wait_us = std::min(B.wait_us.load(std::memory_order_relaxed), L.cur_wait_us * 2 + 10);
+            L.closed.push_back(CloseFill(L));
             B.n_full++;
-            B.cv_work.notify_one();
+            L.cv_work.notify_one();
         } else if (i == 0) {
-            B.cv_work.notify_one();   // somebody has to watch this batch's timer
+            L.cv_work.notify_one();   // somebody has to watch this batch's timer
         }
     }
     // pack outside the lock, straight into the pinned batch record
+    int flags = 0;
     if (!sb_pack_position(planes, board_size, offset, &hb->rec[i])) {
-        hb->rec[i].board_size = board_size;
-        hb->rec[i].offset = offset;
-        hb->rec[i].flags = SB_PACKED_RAW;
-        if (!hb->raw) {
-            std::lock_guard<std::mutex> lk(B.m);
-            if (!hb->raw && cudaHostAlloc(&hb->raw, (size_t)e->max_batch * SB_PLANE_FLOATS * sizeof(float), cudaHostAllocPortable) != cudaSuccess) {
-                cudaGetLastError();
-                hb->raw = nullptr;
+        float* raw = hb->raw.load(std::memory_order_acquire);
+        if (!raw) {
+            std::lock_guard<std::mutex> lk(L.m);
+            raw = hb->raw.load(std::memory_order_relaxed);
+            if (!raw) {
+                if (cudaHostAlloc(&raw, (size_t)B.max_batch * SB_PLANE_FLOATS * sizeof(float), cudaHostAllocPortable) == cudaSuccess) {
+                    hb->raw.store(raw, std::memory_order_release);
+                } else {
+                    cudaGetLastError();
+                    raw = nullptr;
+                }
             }
         }
-        if (hb->raw) {
-            std::memcpy(hb->raw + (size_t)i * SB_PLANE_FLOATS, planes, (size_t)SB_INPUT_CHANNELS * board_size * board_size * sizeof(float));
+        if (raw) {
+            hb->rec[i].board_size = board_size;
+            hb->rec[i].offset = offset;
+            hb->rec[i].flags = SB_PACKED_RAW;
+            std::memcpy(raw + (size_t)i * SB_PLANE_FLOATS, planes, (size_t)SB_INPUT_CHANNELS * board_size * board_size * sizeof(float));
             hb->any_raw.store(1, std::memory_order_relaxed);
+        } else {
+            // no staging memory for the fp32 planes: the entry runs as an empty position and this call FAILS
+            std::memset(&hb->rec[i], 0, sizeof(sb_packed_position));
+            hb->rec[i].board_size = board_size;
+            hb->rec[i].offset = offset;
+            flags |= kTicketFailed;
         }
         B.n_raw++;
     }
     hb->ready.fetch_add(1, std::memory_order_release);
+    t->owner = Bp;
+    t->batch = hb;
+    t->seq = seq0;
+    t->index = i;
+    t->lane = lane | (idx << 8);
+    t->flags = flags;
+    t->board_size = board_size;
+    t->offset = offset;
+    return SB_OK;
+}
+
+// Second half: wait for (or poll) the batch, copy the caller's result out, recycle the batch behind the last reader.
+// Returns 1 while the result is pending (block == false only).
+static int EvalFinish(sb_engine* e, sb_eval_ticket* t, sb_output* out, bool block) {
+    if (!e || !t || !t->owner || !t->batch) return SB_ERR_INVALID;
+    Batcher& B = *static_cast<Batcher*>(t->owner);
+    HostBatch* hb = static_cast<HostBatch*>(t->batch);
+    const uint32_t seq0 = t->seq;
+    if (!block && hb->done_seq.load(std::memory_order_acquire) == seq0) return 1;
     while (hb->done_seq.load(std::memory_order_acquire) == seq0) FutexWait(&hb->done_seq, seq0);
-    const int rc = hb->rc;
-    if (rc == SB_OK) {
-        const float* src = hb->out + (size_t)i * kOutFloats;
-        std::memcpy(out->probabilities, src, sizeof(float) * SB_MAX_INTERSECTIONS);
-        std::memcpy(out->ownership, src + SB_MAX_INTERSECTIONS, sizeof(float) * SB_MAX_INTERSECTIONS);
-        const float* m = src + 2 * SB_MAX_INTERSECTIONS;
-        out->pass_probability = m[0];
-        out->wdl[0] = m[1];
-        out->wdl[1] = m[2];
-        out->wdl[2] = m[3];
-        out->stm_winrate = m[4];
-        out->final_score = m[5];
-        out->q_error = m[6];
-        out->score_error = m[7];
-        out->board_size = board_size;
-        out->offset = offset;
-        out->fp16 = e->precision == SB_PRECISION_FP16 ? 1 : 0;
+    int rc = hb->rc;
+    const int i = t->index;
+    if (rc == SB_OK && (t->flags & kTicketFailed)) {
+        rc = SB_ERR_CUDA;
+        std::lock_guard<std::mutex> lk(e->error_mutex);
+        e->last_error = "no pinned staging memory for a position that cannot be packed (cudaHostAlloc failed)";
+    } else if (rc == SB_OK) {
+        if (out) {
+            const float* src = hb->out + (size_t)i * kOutFloats;
+            std::memcpy(out->probabilities, src, sizeof(float) * SB_MAX_INTERSECTIONS);
+            std::memcpy(out->ownership, src + SB_MAX_INTERSECTIONS, sizeof(float) * SB_MAX_INTERSECTIONS);
+            const float* m = src + 2 * SB_MAX_INTERSECTIONS;
+            out->pass_probability = m[0];
+            out->wdl[0] = m[1];
+            out->wdl[1] = m[2];
+            out->wdl[2] = m[3];
+            out->stm_winrate = m[4];
+            out->final_score = m[5];
+            out->q_error = m[6];
+            out->score_error = m[7];
+            out->board_size = t->board_size;
+            out->offset = t->offset;
+            out->fp16 = e->precision == SB_PRECISION_FP16 ? 1 : 0;
+        }
     } else {
         std::lock_guard<std::mutex> lk(e->error_mutex);
         e->last_error = hb->err;
     }
     if (hb->readers.fetch_sub(1, std::memory_order_acq_rel) == 1) {
         // last reader recycles the batch
+        Lane& L = *B.lanes[t->lane & 0xff];
+        const int idx = t->lane >> 8;
         hb->count = 0;
         hb->ready.store(0, std::memory_order_relaxed);
         hb->any_raw.store(0, std::memory_order_relaxed);
-        std::lock_guard<std::mutex> lk(B.m);
-        if (B.fill < 0) {
-            B.fill = idx;
-            B.cv_space.notify_all();
-        } else {
-            B.free_list.push_back(idx);
+        std::lock_guard<std::mutex> lk(L.m);
+        if (!B.quit.load(std::memory_order_relaxed)) {
+            if (L.fill < 0) {
+                L.fill = idx;
+                L.cv_space.notify_all();
+            } else {
+                L.free_list.push_back(idx);
+            }
         }
     }
+    t->owner = nullptr;
+    t->batch = nullptr;
+    B.outstanding.fetch_sub(1, std::memory_order_acq_rel);
     return rc;
+}
+
+static int EvalImpl(sb_engine* e, const float* planes, int board_size, int offset, sb_output* out) {
+    if (!out) return SB_ERR_INVALID;
+    sb_eval_ticket t;
+    const int rc = EvalBegin(e, planes, board_size, offset, &t);
+    if (rc) return rc;
+    return EvalFinish(e, &t, out, true);
 }
 
 }  // namespace sb
@@ -1529,6 +1843,7 @@ static int ReloadImpl(sb_engine* e, HostNet& net) {
             SB_CUDA(cudaDeviceSynchronize());
             BuildReplica(e, r, &blob);
         }
+        DistributeBlob(e, &blob);
         e->weights_ready = true;
     } catch (const CudaError& ce) {
         return Fail(e, SB_ERR_CUDA, ce.msg);
@@ -1562,6 +1877,8 @@ void sb_destroy(sb_engine* e) {
         }
         DestroyReplica(r);
     }
+    DestroyComms(e);
+    for (auto& b : e->batchers) b->FreeBuffers();
     delete e;
 }
 
@@ -1630,16 +1947,27 @@ int sb_eval(sb_engine* e, const float* planes, int board_size, int policy_offset
     return EvalImpl(e, planes, board_size, policy_offset, out);
 }
 
+int sb_eval_submit(sb_engine* e, const float* planes, int board_size, int policy_offset, sb_eval_ticket* ticket) {
+    return EvalBegin(e, planes, board_size, policy_offset, ticket);
+}
+int sb_eval_poll(sb_engine* e, sb_eval_ticket* ticket, sb_output* out) { return EvalFinish(e, ticket, out, false); }
+int sb_eval_wait(sb_engine* e, sb_eval_ticket* ticket, sb_output* out) { return EvalFinish(e, ticket, out, true); }
+
 int sb_batcher_config(sb_engine* e, int batch_size, int wait_us) {
     if (!e) return SB_ERR_INVALID;
     if (batch_size > e->max_batch) return Fail(e, SB_ERR_INVALID, "batch size exceeds max_batch");
     if (batch_size > 0) e->batcher_batch = batch_size;
     if (wait_us >= 0) e->batcher_wait_us = wait_us;
     std::lock_guard<std::mutex> g(e->batcher_start_mutex);
-    if (e->batcher) {
-        std::lock_guard<std::mutex> lk(e->batcher->m);
-        if (batch_size > 0) e->batcher->batch_size = batch_size;
-        if (wait_us >= 0) e->batcher->wait_us = e->batcher->cur_wait_us = wait_us;
+    if (Batcher* B = e->batcher.load(std::memory_order_acquire)) {
+        if (batch_size > 0) B->batch_size.store(batch_size, std::memory_order_relaxed);
+        if (wait_us >= 0) {
+            B->wait_us.store(wait_us, std::memory_order_relaxed);
+            for (auto& ln : B->lanes) {
+                std::lock_guard<std::mutex> lk(ln->m);
+                ln->cur_wait_us = wait_us;
+            }
+        }
         // a FILLING batch that is already over the new size is closed by the next arrival or its timer
     }
     return SB_OK;
@@ -1649,19 +1977,20 @@ int sb_batcher_stats(sb_engine* e, long long* out6) {
     if (!e || !out6) return SB_ERR_INVALID;
     std::lock_guard<std::mutex> g(e->batcher_start_mutex);
     for (int i = 0; i < 6; ++i) out6[i] = 0;
-    if (e->batcher) {
-        Batcher& B = *e->batcher;
-        out6[0] = B.n_batches;
-        out6[1] = B.n_positions;
-        out6[2] = B.n_full;
-        out6[3] = B.n_timer;
-        out6[4] = B.n_raw;
-        out6[5] = (long long)B.workers.size();
+    if (Batcher* B = e->batcher.load(std::memory_order_acquire)) {
+        out6[0] = B->n_batches;
+        out6[1] = B->n_positions;
+        out6[2] = B->n_full;
+        out6[3] = B->n_timer;
+        out6[4] = B->n_raw;
+        out6[5] = (long long)B->workers.size();
     }
     return SB_OK;
 }
 
-double sb_eval_throughput(sb_engine* e, const float* planes, int n_pos, int board_size, int threads, double seconds) {
+// depth <= 0: `threads` blocking callers (one position per thread in flight, the front-end's model);
+// depth  > 0: `threads` feeder threads, each keeping `depth` tickets in flight through sb_eval_submit / sb_eval_wait
+static double EvalThroughput(sb_engine* e, const float* planes, int n_pos, int board_size, int threads, int depth, double seconds) {
     if (!e || !planes || n_pos < 1 || threads < 1 || seconds <= 0) return (double)SB_ERR_INVALID;
     sb_output warm;
     int rc = EvalImpl(e, planes, board_size, 0, &warm);   // starts the workers, surfaces configuration errors
@@ -1677,13 +2006,38 @@ double sb_eval_throughput(sb_engine* e, const float* planes, int n_pos, int boar
             std::unique_ptr<sb_output> o(new sb_output);
             long long n = 0;
             int i = t % n_pos;
-            while (!stop.load(std::memory_order_relaxed)) {
-                if (EvalImpl(e, planes + (size_t)i * rec, board_size, i % 5, o.get())) {
-                    failed.store(1);
-                    break;
+            if (depth <= 0) {
+                while (!stop.load(std::memory_order_relaxed)) {
+                    if (EvalImpl(e, planes + (size_t)i * rec, board_size, i % 5, o.get())) {
+                        failed.store(1);
+                        break;
+                    }
+                    i = (i + 1) % n_pos;
+                    ++n;
                 }
-                i = (i + 1) % n_pos;
-                ++n;
+            } else {
+                std::vector<sb_eval_ticket> tk(depth);
+                int head = 0, live = 0;
+                while (!stop.load(std::memory_order_relaxed) && !failed.load(std::memory_order_relaxed)) {
+                    while (live < depth) {
+                        if (EvalBegin(e, planes + (size_t)i * rec, board_size, i % 5, &tk[(head + live) % depth])) {
+                            failed.store(1);
+                            break;
+                        }
+                        i = (i + 1) % n_pos;
+                        ++live;
+                    }
+                    if (failed.load()) break;
+                    if (EvalFinish(e, &tk[head], o.get(), true)) failed.store(1);
+                    head = (head + 1) % depth;
+                    --live;
+                    ++n;
+                }
+                while (live > 0) {   // drain
+                    EvalFinish(e, &tk[head], o.get(), true);
+                    head = (head + 1) % depth;
+                    --live;
+                }
             }
             total += n;
         });
@@ -1694,6 +2048,15 @@ double sb_eval_throughput(sb_engine* e, const float* planes, int n_pos, int boar
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (failed.load()) return (double)SB_ERR_CUDA;
     return (double)total.load() / el;
+}
+
+double sb_eval_throughput(sb_engine* e, const float* planes, int n_pos, int board_size, int threads, double seconds) {
+    return EvalThroughput(e, planes, n_pos, board_size, threads, 0, seconds);
+}
+double sb_eval_throughput_async(sb_engine* e, const float* planes, int n_pos, int board_size, int threads, int depth,
+                                double seconds) {
+    if (depth < 1) return (double)SB_ERR_INVALID;
+    return EvalThroughput(e, planes, n_pos, board_size, threads, depth, seconds);
 }
 
 struct sb_host_net {
@@ -1817,6 +2180,28 @@ int sb_weights_export(sb_engine* e, int gpu, void* device_dst, size_t bytes) {
 int sb_weights_import(sb_engine* e, int gpu, const void* device_src, size_t bytes) {
     if (!e || gpu < 0 || gpu >= (int)e->replicas.size()) return SB_ERR_INVALID;
     return BlobCopy(e, gpu, e->replicas[gpu].blob, device_src, bytes, true);
+}
+
+int sb_weights_broadcast(sb_engine* e) {
+    if (!e) return SB_ERR_INVALID;
+    try {
+        DistributeBlob(e, nullptr);
+        e->weights_ready = true;
+    } catch (const CudaError& ce) {
+        return Fail(e, SB_ERR_CUDA, ce.msg);
+    }
+    return SB_OK;
+}
+
+int sb_weights_stats(sb_engine* e, long long* out6) {
+    if (!e || !out6) return SB_ERR_INVALID;
+    out6[0] = e->stat_h2d_uploads;
+    out6[1] = e->stat_d2d_fills;
+    out6[2] = e->bcast_method;
+    out6[3] = e->nccl_version;
+    out6[4] = e->verify_ok;
+    out6[5] = (long long)(e->bcast_ms * 1000.0);
+    return SB_OK;
 }
 
 uint64_t sb_weights_checksum(sb_engine* e, int gpu) {
@@ -1945,13 +2330,17 @@ int sb_conv_stats(sb_engine* e, int gpu, int slot, long long* out, int capacity)
 
 int sb_set_option(sb_engine* e, const char* key, int value) {
     if (!e || !key) return SB_ERR_INVALID;
-    if (!std::strcmp(key, "desc_swap")) {
-        e->desc_swap = value ? 1 : 0;
+    if (!std::strcmp(key, "chunk_taps")) {   // split rung: 9 (one main-accumulator chunk per k-half), 3 or 1 taps per chunk
+        if (value != 1 && value != 3 && value != 9 && value != 0) return Fail(e, SB_ERR_INVALID, "chunk_taps must be 9, 3, 1 (or 0 = one chunk per item)");
+        e->chunk_taps = value;
         return SB_OK;
     }
-    if (!std::strcmp(key, "conv_impl")) {
-        if (value != 1 && value != 2) return Fail(e, SB_ERR_INVALID, "conv_impl must be 1 or 2");
-        e->conv_impl = value;
+    if (!std::strcmp(key, "acc_comp_ppb")) {
+        e->acc_comp_ppb = value;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "fuse_se_pool")) {
+        e->fuse_se_pool = value ? 1 : 0;
         return SB_OK;
     }
     if (!std::strcmp(key, "conv_dbg")) {
@@ -1992,6 +2381,10 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     }
     if (!std::strcmp(key, "tail_split")) {
         e->tail_split = value ? 1 : 0;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "nccl")) {   // weight broadcast at the next (re)load: 1 = ncclBroadcast (default), 0 = peer copies
+        e->use_nccl = value ? 1 : 0;
         return SB_OK;
     }
     if (!std::strcmp(key, "stats_launch")) {

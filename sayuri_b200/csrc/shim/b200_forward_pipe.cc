@@ -122,7 +122,7 @@ void CudaForwardPipe::Construct(ForwardPipeOption option, std::shared_ptr<DNNWei
         // Reconstruct (network.cc:494-498): keep the weights, re-allocate activations.
         Check(sb_reconfigure(engine_, board_size, batch_size), engine_);
         board_size_ = board_size;
-        max_batch_per_nn_ = std::max(batch_size, max_batch_per_nn_);
+        max_batch_per_nn_ = sb_max_batch(engine_);   // what the engine really allocated (a board change allocates exactly `batch`)
         BatchForwardPipe::SetBoardSize(board_size);
         ConfigureBatcher(batch_size);
         return;

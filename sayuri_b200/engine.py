@@ -72,6 +72,11 @@ class SbPackedPosition(ctypes.Structure):
                 ("reserved", ctypes.c_int32)]
 
 
+class SbEvalTicket(ctypes.Structure):
+    _fields_ = [("owner", ctypes.c_void_p), ("batch", ctypes.c_void_p), ("seq", ctypes.c_uint32), ("index", ctypes.c_int32),
+                ("lane", ctypes.c_int32), ("flags", ctypes.c_int32), ("board_size", ctypes.c_int32), ("offset", ctypes.c_int32)]
+
+
 OUTPUT_DTYPE = np.dtype([("probabilities", np.float32, MAX_INTERSECTIONS), ("ownership", np.float32, MAX_INTERSECTIONS),
                          ("pass_probability", np.float32), ("wdl", np.float32, 3), ("stm_winrate", np.float32),
                          ("final_score", np.float32), ("q_error", np.float32), ("score_error", np.float32),
@@ -87,6 +92,7 @@ ABI_SYMBOLS = [
     "sb_weights_checksum", "sb_time_forward", "sb_launch_count", "sb_debug_read_trunk", "sb_conv_stats", "sb_set_option",
     "sb_get_block_desc", "sb_get_dw_desc", "sb_host_net_load", "sb_host_net_free", "sb_host_net_desc", "sb_host_net_tensor",
     "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
+    "sb_eval_submit", "sb_eval_poll", "sb_eval_wait", "sb_eval_throughput_async", "sb_weights_broadcast", "sb_weights_stats",
 ]
 
 _lib = None
@@ -148,6 +154,13 @@ def load_library():
     lib.sb_batcher_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     lib.sb_eval_throughput.argtypes = [vp, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
     lib.sb_eval_throughput.restype = ctypes.c_double
+    lib.sb_eval_throughput_async.argtypes = [vp, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+    lib.sb_eval_throughput_async.restype = ctypes.c_double
+    lib.sb_eval_submit.argtypes = [vp, _F, ctypes.c_int, ctypes.c_int, ctypes.POINTER(SbEvalTicket)]
+    lib.sb_eval_poll.argtypes = [vp, ctypes.POINTER(SbEvalTicket), ctypes.c_void_p]
+    lib.sb_eval_wait.argtypes = [vp, ctypes.POINTER(SbEvalTicket), ctypes.c_void_p]
+    lib.sb_weights_broadcast.argtypes = [vp]
+    lib.sb_weights_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     _lib = lib
     return lib
 
@@ -375,6 +388,29 @@ class B200ForwardPipe:
         self._check(self._lib.sb_eval(self._h, a.ctypes.data_as(_F), board_size, offset, out.ctypes.data))
         return out[0]
 
+    def eval_submit(self, planes, board_size, offset=0):
+        """sb_eval_submit: claims a batch entry and packs the position; returns a ticket for eval_poll / eval_wait."""
+        a = np.ascontiguousarray(planes, dtype=np.float32).ravel()
+        if a.size < INPUT_CHANNELS * board_size * board_size:
+            raise ValueError("planes array smaller than 43*bs*bs")
+        t = SbEvalTicket()
+        self._check(self._lib.sb_eval_submit(self._h, a.ctypes.data_as(_F), board_size, offset, ctypes.byref(t)))
+        return t
+
+    def eval_poll(self, ticket):
+        """None while the batch has not run, else the OutputResult mirror."""
+        out = np.zeros(1, dtype=OUTPUT_DTYPE)
+        rc = self._lib.sb_eval_poll(self._h, ctypes.byref(ticket), out.ctypes.data)
+        if rc == 1:
+            return None
+        self._check(rc)
+        return out[0]
+
+    def eval_wait(self, ticket):
+        out = np.zeros(1, dtype=OUTPUT_DTYPE)
+        self._check(self._lib.sb_eval_wait(self._h, ctypes.byref(ticket), out.ctypes.data))
+        return out[0]
+
     def batcher_config(self, batch_size=0, wait_us=-1):
         self._check(self._lib.sb_batcher_config(self._h, batch_size, wait_us))
 
@@ -389,6 +425,14 @@ class B200ForwardPipe:
         if a.ndim != 2 or a.shape[1] != PLANE_FLOATS:
             raise ValueError("positions must be [n_pos, 43*361]")
         v = self._lib.sb_eval_throughput(self._h, a.ctypes.data_as(_F), a.shape[0], board_size, threads, seconds)
+        if v < 0:
+            self._check(int(v))
+        return float(v)
+
+    def eval_throughput_async(self, positions, board_size, threads, depth, seconds):
+        """Feeder threads with `depth` tickets in flight each (sb_eval_submit / sb_eval_wait)."""
+        a = np.ascontiguousarray(positions, dtype=np.float32)
+        v = self._lib.sb_eval_throughput_async(self._h, a.ctypes.data_as(_F), a.shape[0], board_size, threads, depth, seconds)
         if v < 0:
             self._check(int(v))
         return float(v)
@@ -420,6 +464,17 @@ class B200ForwardPipe:
 
     def weights_checksum(self, gpu=0):
         return int(self._lib.sb_weights_checksum(self._h, gpu))
+
+    def weights_broadcast(self):
+        """Replica 0 -> all other replicas of this process, device to device (ncclBroadcast / peer copy) + verification."""
+        self._check(self._lib.sb_weights_broadcast(self._h))
+
+    def weights_stats(self):
+        buf = (ctypes.c_longlong * 6)()
+        self._check(self._lib.sb_weights_stats(self._h, buf))
+        d = dict(zip(("h2d_uploads", "d2d_fills", "method", "nccl_version", "verified", "broadcast_us"), [int(v) for v in buf]))
+        d["method"] = {0: "single", 1: "nccl", 2: "peer"}[d["method"]]
+        return d
 
     def time_forward(self, gpu, slot, iters, flush_l2=True, profile_conv=False):
         ms = np.zeros(max(iters, 1), dtype=np.float32)

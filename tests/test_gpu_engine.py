@@ -1,0 +1,160 @@
+"""Engine-level behaviour through the C ABI that is not numerics: weight distribution inside the engine (one host upload +
+device-side broadcast), the ticket form of the batcher (sb_eval_submit / sb_eval_poll / sb_eval_wait),
+lane affinity of the multi-replica batcher, and what happens to callers when the batcher is stopped under them."""
+import ctypes
+import os
+import subprocess
+import tempfile
+import threading
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("probabilities", "ownership", "pass_probability", "wdl", "stm_winrate", "final_score", "q_error", "score_error")
+
+
+def _n_gpus():
+    try:
+        return len([l for l in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.splitlines() if l.startswith("GPU")])
+    except OSError:
+        return 0
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from sayuri_b200 import engine
+    engine.load_library()
+    return engine
+
+
+def test_weights_cross_pcie_once_and_replicas_are_verified_equal(eng):
+    """Two replicas in one process: ONE host->device upload of the blob, the second replica is filled device to device,
+    the engine's own verification passed, FNV checksums agree, and both replicas compute bit-identical outputs.
+    (On one GPU both replicas sit on device 0 and the copy is a plain D2D; with two GPUs it is ncclBroadcast over NVLink.)"""
+    from sayuri_b200 import synth
+    two = _n_gpus() >= 2
+    gpus = [0, 1] if two else [0, 0]
+    stack = ["ResidualBlock", "ResidualBlock", "ResidualBlock-SE"]
+    first = os.path.join(tempfile.gettempdir(), "sb_bcast_first.bin")
+    synth.write_synth_net(first, (3, 32, 8, 8), seed=98, stack=stack)
+    pipe = eng.B200ForwardPipe().initialize(first, 19, 8, gpus=gpus)
+    try:
+        st = pipe.weights_stats()
+        assert st["h2d_uploads"] == 1 and st["d2d_fills"] == 1 and st["verified"] == 1, st
+        assert st["method"] == ("nccl" if two else "peer"), st
+        assert pipe.weights_checksum(0) == pipe.weights_checksum(1) != 0
+        x = [synth.synth_positions(1, bs, seed=31 + bs)[0].ravel() for bs in (19, 13, 9)]
+        a = pipe.batch_forward(0, x, [19, 13, 9], [0, 1, 2])
+        b = pipe.batch_forward(1, x, [19, 13, 9], [0, 1, 2])
+        for f in FIELDS:
+            assert np.array_equal(a[f], b[f]), f
+        # hot swap: again one upload, one device-side fill
+        other = os.path.join(tempfile.gettempdir(), "sb_bcast_other.bin")
+        synth.write_synth_net(other, (3, 32, 8, 8), seed=99, stack=stack)
+        before = pipe.weights_checksum(0)
+        pipe.reload(other)
+        st = pipe.weights_stats()
+        assert st["h2d_uploads"] == 2 and st["d2d_fills"] == 2 and st["verified"] == 1, st
+        assert pipe.weights_checksum(0) == pipe.weights_checksum(1) != before
+        # the peer-copy form of the broadcast gives the same bytes
+        pipe.set_option("nccl", 0)
+        pipe.weights_broadcast()
+        assert pipe.weights_stats()["method"] == "peer" and pipe.weights_checksum(0) == pipe.weights_checksum(1)
+        with open(os.path.join(tempfile.gettempdir(), "sb_weights_broadcast.log"), "a") as f:
+            f.write("replicas on devices %r: %r\n" % (gpus, st))
+    finally:
+        pipe.destroy()
+
+
+def test_ticket_calls_equal_the_blocking_call_bit_exact(eng, golden_weights_bin):
+    """sb_eval_submit / sb_eval_poll / sb_eval_wait: one feeder thread with many positions in flight gets, for every
+    ticket, exactly what sb_forward_batch returns for that position."""
+    from sayuri_b200 import synth
+    sizes = [19, 9, 13] * 7
+    planes = [synth.synth_positions(1, bs, seed=1200 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    offs = [i % 5 for i in range(len(sizes))]
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 16, gpus=[0])
+    try:
+        want = pipe.batch_forward(0, planes[:16], sizes[:16], offs[:16])
+        want2 = pipe.batch_forward(0, planes[16:], sizes[16:], offs[16:])
+        pipe.batcher_config(16, 300)
+        tickets = [pipe.eval_submit(p, bs, o) for p, bs, o in zip(planes, sizes, offs)]   # 21 in flight from ONE thread
+        got = [None] * len(tickets)
+        deadline = time.time() + 20
+        polled_pending = 0
+        while any(g is None for g in got) and time.time() < deadline:
+            for i, t in enumerate(tickets):
+                if got[i] is None:
+                    r = pipe.eval_poll(t)
+                    if r is None:
+                        polled_pending += 1
+                    else:
+                        got[i] = r
+        assert all(g is not None for g in got)
+        for i, g in enumerate(got):
+            w = want[i] if i < 16 else want2[i - 16]
+            for f in FIELDS:
+                assert np.array_equal(g[f], w[f]), (i, f)
+            assert g["board_size"] == sizes[i] and g["offset"] == offs[i]
+        # the blocking form of the second half
+        t = pipe.eval_submit(planes[3], sizes[3], offs[3])
+        r = pipe.eval_wait(t)
+        assert np.array_equal(r["probabilities"], want[3]["probabilities"])
+        st = pipe.batcher_stats()
+        assert st["positions"] == len(tickets) + 1
+    finally:
+        pipe.destroy()
+
+
+def test_stopping_the_batcher_fails_pending_callers_instead_of_stranding_them(eng, golden_weights_bin):
+    """A position that was claimed but not evaluated when sb_reconfigure stops the batcher returns SB_ERR_STATE."""
+    from sayuri_b200 import synth
+    x = synth.synth_positions(1, 19, seed=5)[0].ravel()
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 8, gpus=[0])
+    try:
+        pipe.eval(x, 19)                        # starts the workers
+        pipe.batcher_config(8, 5_000_000)       # a partial batch now waits 5 s for company
+        results = []
+
+        def call():
+            try:
+                pipe.eval(x, 19)
+                results.append("ok")
+            except RuntimeError as ex:
+                results.append(str(ex))
+
+        th = threading.Thread(target=call)
+        th.start()
+        time.sleep(0.3)                         # the caller sleeps on its batch
+        pipe.construct(board_size=19, batch_size=32)   # grows the batch: stops the batcher under the caller
+        th.join(timeout=10)
+        assert not th.is_alive(), "caller stayed blocked"
+        assert len(results) == 1 and "batcher was stopped" in results[0], results
+        pipe.batcher_config(32, 200)
+        assert pipe.eval(x, 19)["board_size"] == 19      # and the next call simply restarts it
+    finally:
+        pipe.destroy()
+
+
+def test_every_replica_receives_batches_with_fewer_threads_than_the_batch_size(eng, golden_weights_bin):
+    """Advisor finding of round 1: with fewer caller threads than n_gpus x batch_size the shared-ring batcher could
+    serialise on one GPU.  With one lane per replica every replica that has callers runs batches."""
+    from sayuri_b200 import synth
+    two = _n_gpus() >= 2
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 64, gpus=[0, 1] if two else [0, 0])
+    try:
+        pos = synth.synth_positions(8, 19, seed=77).reshape(8, -1)
+        rate = pipe.eval_throughput(pos, 19, 6, 1.0)          # 6 threads << 2 x 64
+        st = pipe.batcher_stats()
+        assert rate > 0 and st["workers"] == 4
+        assert st["batches"] >= 2 and st["positions"] / st["batches"] <= 6.01
+        # async feeders: 2 threads x 16 tickets in flight form larger batches than 2 blocking threads could
+        rate2 = pipe.eval_throughput_async(pos, 19, 2, 16, 1.0)
+        st2 = pipe.batcher_stats()
+        mean2 = (st2["positions"] - st["positions"]) / max(1, st2["batches"] - st["batches"])
+        assert rate2 > 0 and mean2 > 4, (rate2, mean2)
+    finally:
+        pipe.destroy()

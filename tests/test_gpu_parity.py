@@ -409,6 +409,58 @@ def test_scheduling_knobs_do_not_change_a_single_bit(eng):
                 pipe.destroy()
 
 
+def test_se_pooling_from_the_conv_epilogue_and_the_separate_pass_agree_with_the_oracle(eng, oracle_lib):
+    """The SE unit's pooling comes from partials the last convolution of the block writes in its epilogue (16-row groups on
+    the 19x19 canvas, 4-row groups on 9x9 / 13x13 canvases, fixed-order finalize) or, with fuse_se_pool = 0 and on canvases
+    with an odd row count per sample, from a separate pass over the tensor.  Both meet the 1e-4 bar against the oracle on
+    every block family, and the fused form is batch-invariant (bit-exact) like the rest of the path."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_sepool.bin")
+    stack = ["ResidualBlock-SE", "BottleneckBlock-SE", "MixerBlock-SE", "NestedBottleneckBlock-SE"]
+    synth.write_synth_net(path, (4, 64, 16, 16), seed=5, stack=stack)
+    orc = oracle_lib.Oracle(path)
+    for canvas, sizes in ((19, [19, 9, 13, 19, 7]), (13, [13, 9, 13]), (9, [9, 9, 5]), (12, [12, 9])):
+        planes = [synth.synth_positions(1, bs, seed=90 + i)[0].ravel() for i, bs in enumerate(sizes)]
+        offs = [i % 5 for i in range(len(sizes))]
+        refs = [orc.forward(planes[i], bs, offs[i]) for i, bs in enumerate(sizes)]
+        pipe = eng.B200ForwardPipe().initialize(path, canvas, 8, gpus=[0])
+        try:
+            for fuse in (1, 0):
+                pipe.set_option("fuse_se_pool", fuse)
+                out = pipe.batch_forward(0, planes, sizes, offs)
+                for i, bs in enumerate(sizes):
+                    _check(out[i], refs[i], bs)
+                if fuse:
+                    alone = pipe.batch_forward(0, planes[:1], sizes[:1], offs[:1])
+                    shifted = pipe.batch_forward(0, planes[1:] + planes[:1], sizes[1:] + sizes[:1], offs[1:] + offs[:1])
+                    for f in FIELDS:
+                        assert np.array_equal(alone[0][f], out[0][f]) and np.array_equal(shifted[-1][f], out[0][f]), (canvas, f)
+        finally:
+            pipe.destroy()
+
+
+def test_chunked_accumulation_settings_all_meet_the_bar(eng, oracle_lib):
+    """Split rung: the main accumulator is re-accumulated in fp32 RN every 9 / 3 / 1 taps (option chunk_taps; 0 = the
+    whole K in one TMEM accumulator).  Every setting meets 1e-4 on a shallow net; the deep nets are what
+    tests/test_gpu_fullnets.py pins with the default."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_test_chunks.bin")
+    synth.write_synth_net(path, (3, 192, 16, 16), seed=9, stack=["ResidualBlock", "BottleneckBlock-SE", "ResidualBlock-SE"])
+    orc = oracle_lib.Oracle(path)
+    sizes = [19, 13, 9, 19]
+    planes = [synth.synth_positions(1, bs, seed=190 + i)[0].ravel() for i, bs in enumerate(sizes)]
+    refs = [orc.forward(planes[i], bs, 0) for i, bs in enumerate(sizes)]
+    pipe = eng.B200ForwardPipe().initialize(path, 19, 4, gpus=[0])
+    try:
+        for ct in (9, 3, 1, 0):
+            pipe.set_option("chunk_taps", ct)
+            out = pipe.batch_forward(0, planes, sizes, [0] * 4)
+            for i, bs in enumerate(sizes):
+                _check(out[i], refs[i], bs)
+    finally:
+        pipe.destroy()
+
+
 def test_bottleneck_and_nested_bottleneck_blocks_match_reference_golden(eng, golden_blocks, golden_blocks_weights):
     """BottleneckBlock[-SE] / NestedBottleneckBlock[-SE] towers (blas_forward_pipe.cc:90-263) against
     outputs of the UNMODIFIED compiled reference, every board size in one mixed batch, 1e-4."""

@@ -23,7 +23,6 @@ synth.write_synth_net(path, a.net, seed=1)
 pipe = engine.B200ForwardPipe().initialize(path, 19, a.batch, gpus=[0], precision=a.precision)
 x = synth.synth_positions(min(a.batch, 32), 19, seed=3).reshape(-1, engine.PLANE_FLOATS)
 planes = [x[i % x.shape[0]] for i in range(a.batch)]
-pipe.set_option("conv_impl", a.impl)
 pipe.set_option("tail_split", a.tail_split)
 pipe.batch_forward(0, planes, [19] * a.batch, [0] * a.batch)
 pipe.set_option("stats", 1)

@@ -48,7 +48,6 @@ def run_case(shape, mode, n, seed):
     offsets = [i % 5 for i in range(n)]
     pipe = engine.B200ForwardPipe().initialize(path, 19, max(n, 4), gpus=[0], precision=prec)
     if bo == 2:
-        pipe.set_option("conv_impl", 2)
     out = pipe.batch_forward(0, planes, sizes, offsets)
     orc = Oracle(path)
     res = {"shape": shape, "mode": mode, "n": n, "trunk": 0.0, "prob": 0.0, "own": 0.0, "misc": 0.0, "scale": 0.0}
