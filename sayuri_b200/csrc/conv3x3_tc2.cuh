@@ -29,9 +29,10 @@
 // coherently over K (144 main MMAs at C = 256) and over the layers of a deep tower (measured, profiles/r02_precision_probe*:
 // 20bx256 trunk 5.7e-5 relative = 1.2e-3 absolute, 12x the fp32 noise floor).  Therefore:
 //   * the low-order products (lo*hi, hi*lo) have their own accumulator (small values: their truncation is harmless);
-//   * the MAIN product is accumulated in CHUNKS of `chunk_steps` (k-half, tap) steps (36 or 12 MMAs); each chunk starts
-//     from zero in one of two TMEM stages and is drained by the epilogue and added in fp32 round-to-nearest in registers
-//     (optionally scaled by 1 + the expected truncation loss of a chunk), while the next chunk runs in the other stage.
+//   * the MAIN product is accumulated in CHUNKS of one k-half (64 input channels x 9 taps = 36 MMAs); each chunk starts
+//     from zero in one of two TMEM stages and is drained by the epilogue and added in fp32 round-to-nearest in registers,
+//     scaled by 1 + the expected truncation loss of a chunk, while the next chunk runs in the other stage.  (Chunks of 3
+//     taps or 1 tap are 2x / 4x more accurate still but stall the issuer behind the epilogue: -12 % / -31 %, measured.)
 // SPLIT = false uses the hi parts only, one chunk per item (the reference's own --fp16 trade).
 //
 // Warp roles:  warp 0 : TMA producer for weight stages      warp 1 : tcgen05.mma issuer (leader CTA; converged, elected lane)
@@ -61,7 +62,7 @@ struct ConvParams {
     int pitch;               // P = N + 1
     int ntaps;               // 9 = 3x3 convolution, 1 = 1x1 convolution (centre tap only)
     int dbg;                 // ablation bits for profiling only: 1 skip stores, 2 skip activation+split math, 8 no tap shifts, 16 no weight stream, 64 no slab stream
-    int chunk_steps;         // SPLIT: (k-half, tap) steps per main-accumulator chunk; kh * ntaps = one chunk per item
+    int chunk_kh;            // SPLIT: k-halves (64 input channels x all taps) per main-accumulator chunk; kh = one chunk per item
     float chunk_scale;       // SPLIT: a drained chunk is multiplied by this (1 + expected truncation loss of a chunk)
     float* pool_part;        // POOL: [group][2][pool_c] sums and maxima of the output over groups of 2^pool_log2 canvas rows
     int pool_log2;           // 2..4; groups never straddle samples (the engine checks kGuardRows and SS are multiples)
@@ -262,10 +263,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t stage_stride = BN > 128 ? 2u * Cfg::kBStageBytes : (uint32_t)Cfg::kBStageBytes;
     const uint32_t kNB = resident ? (uint32_t)(p.kh * p.ntaps * Cfg::kParts)
                                   : (uint32_t)(Cfg::kNumBStages * Cfg::kBStageBytes) / stage_stride;
-    // main-accumulator chunks: the (k-half, tap) steps t = h * ntaps + tap of an item are cut every chunk_steps steps
-    const int T = KH * p.ntaps;
-    const int chunk_steps = SPLIT ? p.chunk_steps : T;
-    const int n_chunks = (T + chunk_steps - 1) / chunk_steps;
+    // main-accumulator chunks: the k-halves of an item are cut every chunk_kh k-halves (fp16 rung: one chunk per item)
+    const int chunk_kh = SPLIT ? p.chunk_kh : KH;
+    const int n_chunks = (KH + chunk_kh - 1) / chunk_kh;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -369,8 +369,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     } else if (warp == 1) {
         if (leader) {
             // ===================== MMA issuer (leader CTA only) =====================
-            // TMEM columns per CTA: main stage s at s * BN (s = chunk counter & 1); split rung: low-order accumulator of
-            // item j at (2 + (j & 1)) * BN.
+            // TMEM columns per CTA, split rung: [main 0 | lo 0 | main 1 | lo 1] x BN (main stage = chunk counter & 1, low-order
+            // accumulator = item counter & 1); fp16 rung: main stage s at s * BN.
             const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);
             constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
             const bool stats = p.stats != nullptr;
@@ -381,15 +381,22 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
                 const uint32_t ls = j & 1u, lph = (j >> 1) & 1u;
                 const uint32_t idesc = item < p.n_full ? idesc_whole : idesc_half;
-                const uint32_t d_lo = tmem_base + (2u + ls) * BN;
+                const uint32_t d_lo = tmem_base + (2u * ls + 1u) * BN;
                 if (SPLIT) {
                     if (stats) t0 = clock64();
                     mbar_wait(lo_empty + 8 * ls, lph ^ 1u, p.err, 8);
                     if (stats) t_wait_tmem += clock64() - t0;
                 }
                 uint32_t d_main = 0;
-                int in_chunk = 0;        // steps issued into the current chunk
+                int h_in_chunk = 0;      // k-halves issued into the current chunk
                 for (int h = 0; h < KH; ++h, ++a_it) {
+                    if (h_in_chunk == 0) {   // a new chunk: its accumulator stage must have been drained
+                        const uint32_t cs = cc & 1u, cph = (cc >> 1) & 1u;
+                        if (stats) t0 = clock64();
+                        mbar_wait(tmem_empty + 8 * cs, cph ^ 1u, p.err, 3);
+                        if (stats) t_wait_tmem += clock64() - t0;
+                        d_main = tmem_base + (SPLIT ? 2u * cs : cs) * BN;
+                    }
                     const uint32_t s = a_it % kNA, sph = (a_it / kNA) & 1u;
                     if (stats) t0 = clock64();
                     if (!((p.dbg & 64) && a_it >= kNA)) mbar_wait(a_full + 8 * s, sph, p.err, 4);
@@ -397,16 +404,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     tc_fence_after();
                     const uint32_t a_hi = slab_addr + s * Cfg::kSlabBytes;
                     for (int tap = 0; tap < p.ntaps; ++tap) {
-                        if (in_chunk == 0) {   // a new chunk: its accumulator stage must have been drained
-                            const uint32_t cs = cc & 1u, cph = (cc >> 1) & 1u;
-                            if (stats) t0 = clock64();
-                            mbar_wait(tmem_empty + 8 * cs, cph ^ 1u, p.err, 3);
-                            if (stats) t_wait_tmem += clock64() - t0;
-                            tc_fence_after();
-                            d_main = tmem_base + cs * BN;
-                        }
                         const int shift = (p.ntaps == 1 || (p.dbg & 8)) ? 0 : (tap / 3 - 1) * p.pitch + (tap % 3 - 1);   // 1 tap = 1x1 convolution
-                        const uint32_t first_main = in_chunk == 0 ? 0u : 1u;
+                        const uint32_t first_main = (h_in_chunk | tap) == 0 ? 0u : 1u;
                         const uint32_t first_lo = (h | tap) == 0 ? 0u : 1u;
                         const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
                         {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
@@ -448,19 +447,21 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                 if (!resident) bph ^= 1u;
                             }
                         }
-                        const bool last_step = h == KH - 1 && tap == p.ntaps - 1;
-                        if (++in_chunk == chunk_steps || last_step) {   // chunk complete: hand its stage to the epilogue
-                            if (elect_one()) {
-                                if (SPLIT && last_step) umma2_commit_mc(lo_full + 8 * ls, 3);
-                                umma2_commit_mc(tmem_full + 8 * (cc & 1u), 3);
-                            }
-                            __syncwarp();
-                            in_chunk = 0;
-                            ++cc;
+                    }
+                    const bool last_h = h == KH - 1;
+                    const bool chunk_done = ++h_in_chunk == chunk_kh || last_h;
+                    if (elect_one()) {
+                        umma2_commit_mc(a_empty + 8 * s, 3);
+                        if (chunk_done) {   // hand the chunk's accumulator stage (and, behind the last one, the low-order sums) to the epilogue
+                            if (SPLIT && last_h) umma2_commit_mc(lo_full + 8 * ls, 3);
+                            umma2_commit_mc(tmem_full + 8 * (cc & 1u), 3);
                         }
                     }
-                    if (elect_one()) umma2_commit_mc(a_empty + 8 * s, 3);
                     __syncwarp();
+                    if (chunk_done) {
+                        h_in_chunk = 0;
+                        ++cc;
+                    }
                 }
             }
             if (stats && lane == 0) {
@@ -531,7 +532,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         if (stats) t_wait_full += clock64() - t0;
                         tc_fence_after();
                         const long long t_d0 = stats ? clock64() : 0;
-                        const uint32_t t_main = lane_base + cs * BN + pbase;
+                        const uint32_t t_main = lane_base + 2u * cs * BN + pbase;
 #pragma unroll
                         for (int g = 0; g < Cfg::kMaxGroups; ++g) {
                             if (g * 16 < PC) {
@@ -555,7 +556,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     {   // the low-order accumulator of this item (committed together with the last chunk)
                         mbar_wait(lo_full + 8 * ls, lph, p.err, 9);
                         tc_fence_after();
-                        const uint32_t t_lo = lane_base + (2u + ls) * BN + pbase;
+                        const uint32_t t_lo = lane_base + (2u * ls + 1u) * BN + pbase;
 #pragma unroll
                         for (int g = 0; g < Cfg::kMaxGroups; ++g) {
                             if (g * 16 < PC) {

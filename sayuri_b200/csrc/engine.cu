@@ -436,7 +436,7 @@ struct sb_engine {
     int collect_stats = 0;
     int stats_launch = -1;   // conv launch index within a forward whose counters are kept (-1: every launch, last wins)
     int conv_dbg = 0;
-    int chunk_taps = 9;          // split rung: taps per main-accumulator chunk of a 3x3 conv (9 = one chunk per k-half, 3, 1)
+    int chunk_accumulate = 1;    // split rung: the main accumulator of a 3x3 conv is re-accumulated in fp32 RN per k-half (0 = whole K in TMEM)
     int acc_comp_ppb = 12;       // split rung: a drained chunk is scaled by 1 + ppb * 1e-9 * (main MMAs of the chunk): the expected
                                  // loss of the tensor core's truncating fp32 accumulation (measured: the TC - SIMT slope crosses
                                  // zero at 9-13 ppb on 1..41-layer towers, profiles/r02_precision_probe.log)
@@ -908,10 +908,10 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.pitch = e->geom.P;
         p.ntaps = c.L.taps;
         p.dbg = e->conv_dbg;
-        // split rung: the main accumulator is drained and re-accumulated in fp32 RN every `chunk_steps` (k-half, tap) steps
-        // (conv3x3_tc2.cuh, "Precision"); a 1x1 convolution (<= 24 main MMAs) is one chunk
-        p.chunk_steps = (c.L.taps == 9 && e->chunk_taps > 0) ? e->chunk_taps : c.L.kh * c.L.taps;   // chunk_taps 0: one chunk per item
-        p.chunk_scale = 1.0f + 1e-9f * (float)e->acc_comp_ppb * (float)(4 * std::min(p.chunk_steps, c.L.kh * c.L.taps));
+        // split rung: the main accumulator is drained and re-accumulated in fp32 RN after every k-half (conv3x3_tc2.cuh,
+        // "Precision"); a 1x1 convolution (<= 24 main MMAs) is one chunk
+        p.chunk_kh = (c.L.taps == 9 && e->chunk_accumulate) ? 1 : c.L.kh;
+        p.chunk_scale = 1.0f + 1e-9f * (float)e->acc_comp_ppb * (float)(4 * p.chunk_kh * c.L.taps);
         p.pool_part = pool ? s.pool_part : nullptr;
         p.pool_log2 = PoolLog2(e->geom);
         p.pool_groups = (n * e->geom.SS) >> std::max(p.pool_log2, 1);
@@ -2330,9 +2330,8 @@ int sb_conv_stats(sb_engine* e, int gpu, int slot, long long* out, int capacity)
 
 int sb_set_option(sb_engine* e, const char* key, int value) {
     if (!e || !key) return SB_ERR_INVALID;
-    if (!std::strcmp(key, "chunk_taps")) {   // split rung: 9 (one main-accumulator chunk per k-half), 3 or 1 taps per chunk
-        if (value != 1 && value != 3 && value != 9 && value != 0) return Fail(e, SB_ERR_INVALID, "chunk_taps must be 9, 3, 1 (or 0 = one chunk per item)");
-        e->chunk_taps = value;
+    if (!std::strcmp(key, "chunk_accumulate")) {   // split rung: 1 = fp32 RN re-accumulation of the main product per k-half (default)
+        e->chunk_accumulate = value ? 1 : 0;
         return SB_OK;
     }
     if (!std::strcmp(key, "acc_comp_ppb")) {

@@ -107,6 +107,13 @@ def load_library():
         raise RuntimeError("sayuri_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
                            "there is no CPU fallback" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
+    if os.environ.get("SAYURI_B200_LIB"):
+        # an older / experimental build for same-box A/B timing may lack newer entry points: give those a stub that raises
+        def _missing(*_a, **_k):
+            raise RuntimeError("this build of libsayuri_b200.so lacks the entry point")
+        for name in ABI_SYMBOLS:
+            if not hasattr(lib, name):
+                setattr(lib, name, type("Stub", (), {"__call__": staticmethod(_missing), "argtypes": None, "restype": None})())
     vp = ctypes.c_void_p
     lib.sb_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(SbNetDesc), ctypes.POINTER(SbWeights), _I, ctypes.c_int,
                               ctypes.c_int, ctypes.c_int, ctypes.c_int]

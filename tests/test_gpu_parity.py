@@ -440,9 +440,9 @@ def test_se_pooling_from_the_conv_epilogue_and_the_separate_pass_agree_with_the_
 
 
 def test_chunked_accumulation_settings_all_meet_the_bar(eng, oracle_lib):
-    """Split rung: the main accumulator is re-accumulated in fp32 RN every 9 / 3 / 1 taps (option chunk_taps; 0 = the
-    whole K in one TMEM accumulator).  Every setting meets 1e-4 on a shallow net; the deep nets are what
-    tests/test_gpu_fullnets.py pins with the default."""
+    """Split rung: the main accumulator is re-accumulated in fp32 RN after every k-half (option chunk_accumulate; 0 = the
+    whole K in one TMEM accumulator, the round-1 behaviour), with and without the truncation compensation.  Every setting
+    meets 1e-4 on a shallow net; the deep nets are what tests/test_gpu_fullnets.py pins with the defaults."""
     from sayuri_b200 import synth
     path = os.path.join(tempfile.gettempdir(), "sb_test_chunks.bin")
     synth.write_synth_net(path, (3, 192, 16, 16), seed=9, stack=["ResidualBlock", "BottleneckBlock-SE", "ResidualBlock-SE"])
@@ -452,8 +452,9 @@ def test_chunked_accumulation_settings_all_meet_the_bar(eng, oracle_lib):
     refs = [orc.forward(planes[i], bs, 0) for i, bs in enumerate(sizes)]
     pipe = eng.B200ForwardPipe().initialize(path, 19, 4, gpus=[0])
     try:
-        for ct in (9, 3, 1, 0):
-            pipe.set_option("chunk_taps", ct)
+        for chunk, comp in ((1, 12), (1, 0), (0, 0)):
+            pipe.set_option("chunk_accumulate", chunk)
+            pipe.set_option("acc_comp_ppb", comp)
             out = pipe.batch_forward(0, planes, sizes, [0] * 4)
             for i, bs in enumerate(sizes):
                 _check(out[i], refs[i], bs)

@@ -14,7 +14,7 @@ ap.add_argument("--net", default="10bx128")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--precision", type=int, default=0)
 ap.add_argument("--dbg", type=int, default=0)
-ap.add_argument("--impl", type=int, default=2)
+ap.add_argument("--option", action="append", default=[])
 ap.add_argument("--tail-split", type=int, default=1)
 ap.add_argument("--launch", type=int, default=2, help="conv launch index within the forward (2 = second tower conv)")
 a = ap.parse_args()
@@ -24,6 +24,8 @@ pipe = engine.B200ForwardPipe().initialize(path, 19, a.batch, gpus=[0], precisio
 x = synth.synth_positions(min(a.batch, 32), 19, seed=3).reshape(-1, engine.PLANE_FLOATS)
 planes = [x[i % x.shape[0]] for i in range(a.batch)]
 pipe.set_option("tail_split", a.tail_split)
+for kv in a.option:
+    pipe.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 pipe.batch_forward(0, planes, [19] * a.batch, [0] * a.batch)
 pipe.set_option("stats", 1)
 pipe.set_option("stats_launch", a.launch)

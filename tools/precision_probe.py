@@ -14,10 +14,10 @@ from oracle.oracle_py import Oracle  # noqa: E402
 from sayuri_b200 import engine, synth  # noqa: E402
 
 
-def trunks(path, planes, prec, chunk_taps=9, comp=0):
+def trunks(path, planes, prec, chunk=1, comp=0):
     pipe = engine.B200ForwardPipe().initialize(path, 19, 4, gpus=[0], precision=prec)
     try:
-        pipe.set_option("chunk_taps", chunk_taps)
+        pipe.set_option("chunk_accumulate", chunk)
         pipe.set_option("acc_comp_ppb", comp)
         pipe.batch_forward(0, planes, [19] * len(planes), [0] * len(planes))
         return [pipe.debug_read_trunk(0, 0, i, 19) for i in range(len(planes))]
@@ -25,7 +25,7 @@ def trunks(path, planes, prec, chunk_taps=9, comp=0):
         pipe.destroy()
 
 
-SETTINGS = [(0, 0), (9, 0), (3, 0), (1, 0), (9, 5), (9, 10), (9, 15), (3, 10)]
+SETTINGS = [(0, 0), (1, 0), (1, 8), (1, 12), (1, 16)]   # (chunk_accumulate, acc_comp_ppb)
 
 
 def main():
@@ -46,7 +46,7 @@ def main():
             t = np.concatenate([x.ravel() for x in tc]).astype(np.float64)
             d = t - s
             a, b = np.polyfit(s, d, 1)   # least-squares fit d = a * s + b
-            print("    chunk_taps %d comp %3d ppb: TC-oracle max %.3g rms %.3g | TC-SIMT slope %.3g offset %.3g resid-rms %.3g"
+            print("    chunk_accumulate %d comp %3d ppb: TC-oracle max %.3g rms %.3g | TC-SIMT slope %.3g offset %.3g resid-rms %.3g"
                   % (ct, comp, np.abs(t - r).max(), np.sqrt(np.mean((t - r) ** 2)), a, b, np.sqrt(np.mean((d - a * s - b) ** 2))), flush=True)
 
 
