@@ -124,6 +124,15 @@ class ClockSampler:
                 "power_w_max": max(r[3] for r in inside) if inside else None, "how": how}
 
 
+def workload_config(args, P, V):
+    """The SAME dict in both arms (the driver compares them): the workload, and how each arm treats caches / precision."""
+    return {"workload": "19x19 board, %s net (P=%d,V=%d, SE every 3rd block, mish), batch-%d NN forward per GPU" % (args.net, P, V, args.batch),
+            "net": args.net, "board": 19, "batch_per_gpu": args.batch,
+            "precision": "reference arm: fp32 Eigen; our arm: --precision (default fp32_split = fp32-faithful fp16 hi/lo split, fp32 accumulate)",
+            "l2": "our arm: 256 MiB buffer written between timed iterations (L2 flush); reference arm: CPU, not applicable",
+            "parallelism": "our arm: replica per GPU, weights broadcast over NCCL/NVLink; reference arm: host threads"}
+
+
 def weights_file(net, seed=20260417):
     path = os.path.join(tempfile.gettempdir(), "sb_bench_%s_seed%d.bin" % (net, seed))
     if not os.path.exists(path):
@@ -143,9 +152,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "gpu_launches": 0,
-            "config": {"workload": "19x19 board, %s net (P=%d,V=%d, SE every 3rd block, mish), batch-%d NN forward" % (args.net, P, V, args.batch),
-                       "net": args.net, "board": 19, "batch_per_gpu": args.batch}}
+            "data": "synthetic", "gpu_launches": 0, "config": workload_config(args, P, V)}
     if not Reference.available():
         line["unavailable"] = "oracle/_ref is not built (needs /root/reference at build time)"
         print(json.dumps(line), flush=True)
@@ -257,13 +264,23 @@ def run_ours(args, rank, local_rank, world):
     conv_flops = conv3x3_flops_per_eval(blocks, C, P, V) * B
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
     peak = peaks["tflops_sustained"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")   # dram bytes per launch from the committed ncu capture
+    # dram bytes per launch come from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum of
+    # one tower-conv launch); the entry names the sha256 of the kernel source it was taken from and is dropped (null) when
+    # that is not the source this library was built from, so the number cannot silently go stale
+    traffic, traffic_note = None, "no committed capture for this kernel source"
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tpath):
+        import hashlib
+        with open(os.path.join(ROOT, "sayuri_b200", "csrc", "conv3x3_tc2.cuh"), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
         with open(tpath) as f:
-            traffic = json.load(f).get(args.precision, {}).get("dram_bytes_per_launch")
+            ent = json.load(f).get(args.precision, {})
+        if ent.get("kernel_source_sha256") == sha:
+            traffic, traffic_note = ent.get("dram_bytes_per_launch"), ent.get("source", "")
+        elif ent:
+            traffic_note = "committed capture is of an older kernel source (sha mismatch): dropped"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": "conv3x3_tc2_kernel<%s, mish> (tcgen05 cta_group::2)" % ("split" if precision == engine.PRECISION_FP32_SPLIT else "fp16"),
                 "launches_per_step": conv_n, "kernel_ms_per_step": conv_ms,
                 "kernel_share_of_step": conv_share,
@@ -273,28 +290,38 @@ def run_ours(args, rank, local_rank, world):
                 "tensor_flops_issued_per_algorithmic": 3 * (400.0 / 361.0) if precision == engine.PRECISION_FP32_SPLIT else (400.0 / 361.0),
                 "note": "fp32-faithful rung issues 3 fp16 MMAs per algorithmic MAC (hi*hi + lo*hi + hi*lo) on a 400-row/361-cell canvas"}
 
-    # ---- (2) end to end through the C ABI: pinned host in, host out, 2 slots pipelined --------------
-    def e2e_loop(steps):
+    # ---- (2) end to end through the C ABI, 2 slots pipelined: host buffers in, host results out ---------------------
+    #      headline `e2e`: inputs in ordinary (pageable) host memory, as the front-end holds them; sb_submit packs every
+    #      position exactly into its 2.2 KB record in pinned staging (the product path: what crosses PCIe is the record);
+    #      `e2e_raw_fp32`: the same loop with 62 KB of fp32 planes per position DMA'd in place from pinned memory.
+    def e2e_loop(steps, src):
         for s in range(steps):
             slot = s & 1
             if s >= 2:
                 pipe.wait(0, slot, outs[slot])
-            pipe.submit(0, slot, pinned.array[slot], sizes, offs)
+            pipe.submit(0, slot, src[slot], sizes, offs)
         for s in range(max(steps - 2, 0), steps):
             pipe.wait(0, s & 1, outs[s & 1])
 
-    e2e_loop(max(args.warmup, 2))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(args.steps)
-    t_e2e = time.perf_counter() - t0
-    sampler.window(t0, t0 + t_e2e)
-    barrier()
-    t_e2e = reduce_max(t_e2e)
-    e2e = {"value": world * B * args.steps / t_e2e, "unit": UNIT,
-           "h2d_bytes_per_step": B * engine.PLANE_FLOATS * 4 + 2 * B * 4,
-           "d2h_bytes_per_step": B * (2 * 361 + 8) * 4,
+    def e2e_measure(src):
+        e2e_loop(max(args.warmup, 2), src)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps, src)
+        t = time.perf_counter() - t0
+        sampler.window(t0, t0 + t)
+        barrier()
+        return world * B * args.steps / reduce_max(t)
+
+    pageable = [np.array(pinned.array[k]) for k in range(2)]    # plain numpy memory: sb_submit takes its packing path
+    v_packed = e2e_measure(pageable)
+    v_raw = e2e_measure([pinned.array[0], pinned.array[1]])
+    out_bytes = B * (2 * 361 + 8) * 4
+    e2e = {"value": v_packed, "unit": UNIT, "h2d_bytes_per_step": B * 2252 + 2 * B * 4, "d2h_bytes_per_step": out_bytes,
+           "input": "fp32 planes in pageable host memory, packed exactly to 2252-byte records by sb_submit (4 host threads), records DMA'd from pinned staging",
            "timing": "host perf_counter around K pipelined sb_submit/sb_wait steps (2 slots), device idle on both sides"}
+    e2e_raw = {"value": v_raw, "unit": UNIT, "h2d_bytes_per_step": B * engine.PLANE_FLOATS * 4 + 2 * B * 4, "d2h_bytes_per_step": out_bytes,
+               "input": "fp32 planes in pinned host memory (sb_host_alloc), DMA'd in place"}
 
     # ---- (3) the single-position call of the plugin interface (NetworkForwardPipe::Forward -> sb_eval): T native
     #      host threads, fp32 planes in pageable memory, packing + H2D + forward + D2H + wake-up inside the region ----
@@ -319,12 +346,8 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16x3-split/f32-accum" if precision == engine.PRECISION_FP32_SPLIT else "f16/f32-accum",
             "data": "synthetic",
-            "config": {"workload": "19x19 board, %s net (P=%d,V=%d, SE every 3rd block, mish), batch-%d NN forward per GPU" % (args.net, P, V, B),
-                       "net": args.net, "board": 19, "batch_per_gpu": B, "precision": args.precision,
-                       "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                       "parallelism": "replica per GPU, weights NCCL-broadcast from rank 0",
-                       **({"options": args.option} if args.option else {})},
-            "clocks": clocks, "e2e": e2e, "e2e_eval": e2e_eval, "gpu_launches": int(launches), "roofline": roofline,
+            "config": workload_config(args, P, V), "precision": args.precision, "options": args.option,
+            "clocks": clocks, "e2e": e2e, "e2e_raw_fp32": e2e_raw, "e2e_eval": e2e_eval, "gpu_launches": int(launches), "roofline": roofline,
             "algorithmic_gflop_per_eval": algorithmic_flops_per_eval(blocks, C, P, V, n_se) / 1e9}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's Eigen forward on host cores -----
@@ -354,6 +377,21 @@ def run_ours(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
     pinned.free()
     pipe.destroy()
+    if dist is not None:
+        dist.barrier()
+    if rank == 0 and args.selfplay_games > 0:
+        # the other half of BASELINE.json's metric: self-play games/hour through the UNMODIFIED reference loop (19x19, 400
+        # visits) over our pipe, ONE process driving all N GPUs like the reference front-end (tools/selfplay_bench.py)
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "selfplay_bench.py"), "--preset", "config2", "--net", args.net,
+                                "--gpus", ",".join(str(g) for g in range(world)), "--parallel-games", str(args.selfplay_games * world),
+                                "--timeout", "3000"] + (["--fp16"] if args.precision == "fp16" else []),
+                               capture_output=True, text=True, timeout=3100)
+            sp = json.loads(r.stdout.strip().splitlines()[-1])
+            line["selfplay"] = sp
+            line["games_per_hour"] = sp["games_per_hour"]
+        except Exception as ex:
+            line["selfplay"] = {"error": repr(ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -375,6 +413,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-threads", type=int, default=512, help="host threads of the sb_eval leg (0 = skip)")
     ap.add_argument("--eval-seconds", type=float, default=2.0)
+    ap.add_argument("--selfplay-games", type=int, default=0, metavar="G",
+                    help="also play G parallel self-play games per GPU to the end through the unmodified reference loop (19x19, "
+                         "400 visits) and add games_per_hour to the line; takes minutes, off by default")
     ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
                     help="engine knob for A/B runs (sb_set_option), e.g. --option chunk_taps=3; recorded in config")
     args = ap.parse_args()

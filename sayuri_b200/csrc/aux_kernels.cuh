@@ -285,16 +285,25 @@ se_fc_kernel(const float* __restrict__ part, int gps, const int* __restrict__ bo
     float* hid = pool + 3 * C;      // [se]
     const float b_coeff = ((float)bs - 14.0f) / 10.f;   // se_unit.h:17-20
     const float* base = part + (size_t)b * gps * 2 * C;
-    for (int c = tid; c < C; c += 256) {
-        float s = 0.f, m = -5000.f;
-        for (int g = 0; g < gps; ++g) {      // fixed order over the row groups of the sample
-            s += base[(size_t)g * 2 * C + c];
-            m = fmaxf(m, base[(size_t)g * 2 * C + C + c]);
+    // thread t owns entry t of the 2C-float group records (t < C: the sum of channel t, else the maximum of channel t - C):
+    // every load of the CTA is one contiguous run; 8 groups are in flight at a time, added in group order
+    for (int t = tid; t < 2 * C; t += 256) {
+        const bool is_sum = t < C;
+        float r = is_sum ? 0.f : -5000.f;
+        for (int g0 = 0; g0 < gps; g0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (g0 + k < gps) ? base[(size_t)(g0 + k) * 2 * C + t] : (is_sum ? 0.f : -5000.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r = is_sum ? r + v[k] : fmaxf(r, v[k]);
         }
-        const float mean = s / (float)(bs * bs);
-        pool[c] = mean;
-        pool[C + c] = mean * b_coeff;
-        pool[2 * C + c] = m;
+        if (is_sum) {
+            const float mean = r / (float)(bs * bs);
+            pool[t] = mean;
+            pool[C + t] = mean * b_coeff;
+        } else {
+            pool[C + t] = r;      // pool[2C + c]
+        }
     }
     __syncthreads();
     fc_tail_8lanes(w1, pool, 3 * C, se, [&](int o, float v) { hid[o] = activate_t<ACT>(v + b1[o]); });   // squeeze, activation

@@ -1527,6 +1527,21 @@ static void BatchWorker(sb_engine* e, Batcher* Bp, int gpu, int k) {
     }
 }
 
+// Measurement aid: with SAYURI_B200_STATS_FILE set in the environment a thread appends "seconds batches positions" every
+// 250 ms, so that a front-end run that is cut short (tools/selfplay_bench.py --window) still yields its evaluation rate.
+static void StatsWriter(Batcher* Bp, std::string path) {
+    const auto t0 = std::chrono::steady_clock::now();
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return;
+    while (!Bp->quit.load(std::memory_order_relaxed)) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(250));
+        const double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::fprintf(f, "%.3f %lld %lld\n", t, (long long)Bp->n_batches.load(), (long long)Bp->n_positions.load());
+        std::fflush(f);
+    }
+    std::fclose(f);
+}
+
 // Stops the workers and FAILS every position that was claimed but not yet evaluated (its caller returns SB_ERR_STATE):
 // nobody stays blocked on a batch that will never run.  The Batcher object itself is retired, not deleted: a caller that
 // loaded the pointer just before the stop finds `quit` set and leaves.  Its pinned buffers are released once no call
@@ -1608,6 +1623,7 @@ static Batcher* StartBatcher(sb_engine* e) {
     e->batchers.push_back(std::move(B));
     for (int g2 = 0; g2 < n_lanes; ++g2)
         for (int k = 0; k < kBatcherSlots; ++k) raw->workers.emplace_back(BatchWorker, e, raw, g2, k);
+    if (const char* stats_path = std::getenv("SAYURI_B200_STATS_FILE")) raw->workers.emplace_back(StatsWriter, raw, std::string(stats_path));
     e->batcher.store(raw, std::memory_order_release);
     return raw;
 }

@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sayuri_b200 import engine, synth  # noqa: E402
 
-REF = os.path.join(ROOT, "oracle", "_ref", "sayuri_cudnn_bench")
+# SAYURI_CUDNN_BENCH=sayuri_cudnn_bench_ptx90 selects the as-shipped build (SIMT kernels JIT-compiled from compute_90 PTX)
+REF = os.path.join(ROOT, "oracle", "_ref", os.environ.get("SAYURI_CUDNN_BENCH", "sayuri_cudnn_bench"))
 
 
 def ours(path, pos, batch, precision, seconds):
