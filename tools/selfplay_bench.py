@@ -80,7 +80,7 @@ def main():
     for q in cfg["queries"]:
         cmd += ["--selfplay-query", q]
     if not cpu_pipe:
-        cmd += ["--fp16"] if a.fp16 else ["--no-fp16"]
+        cmd += [] if a.fp16 else ["--no-fp16"]   # fp16 is the front-end's default (config.cc:33); there is no --fp16 flag
         for g in gpus:
             cmd += ["-g", str(g)]
     if a.batch_size > 0:
@@ -144,6 +144,8 @@ def main():
                              "mean_batch": round((last[2] - mid[2]) / max(1, last[1] - mid[1]), 1), "nn_evals_total": last[2],
                              "note": "window run: games were cut, games/hour is NOT measured"}
         res["games_per_hour"] = None
+        if "window" not in res:
+            res["log_tail"] = lines[-12:]
     elif not finished:
         res["log_tail"] = lines[-8:]
     shutil.rmtree(out, ignore_errors=True)
