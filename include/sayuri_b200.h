@@ -217,6 +217,26 @@ int sb_eval_submit(sb_engine* e, const float* planes, int board_size, int policy
 int sb_eval_poll(sb_engine* e, sb_eval_ticket* ticket, sb_output* out);
 int sb_eval_wait(sb_engine* e, sb_eval_ticket* ticket, sb_output* out);
 
+/* Network::GetOutput(state, Network::kAverage) (src/neural/network.cc:258-282): the 8 symmetric views of one position,
+ * each post-processed like Network::TransformResult + ActivatePolicy (network.cc:361-428: inverse symmetry, tanh ownership,
+ * softmax wdl, winrates, score x 20, error transforms, policy softmax with `temperature` over board + pass) and averaged.
+ * The reference makes 8 serial Forward calls; here the views are built from the identity view `planes` (43 * bs * bs,
+ * Encoder::SymmetryPlanes, encoder.cc:80-98) and travel as 8 tickets from the calling thread, i.e. in ONE batch. */
+typedef struct sb_symm8_result {
+    float probabilities[SB_MAX_INTERSECTIONS]; /* averaged softmax policy, native order, identity orientation */
+    float ownership[SB_MAX_INTERSECTIONS];     /* averaged tanh ownership                                    */
+    float pass_probability;
+    float wdl[3];
+    float wdl_winrate;
+    float stm_winrate;
+    float final_score;
+    float q_error;
+    float score_error;
+    int board_size;
+} sb_symm8_result;
+int sb_eval_symm8(sb_engine* e, const float* planes, int board_size, int policy_offset, float temperature,
+                  sb_symm8_result* out);
+
 /* BatchForwardPipe::SetForwardingSize (batch_size <= max_batch; <= 0 keeps) and the --gpu-waittime analogue in
  * microseconds (< 0 keeps; default 200). */
 int sb_batcher_config(sb_engine* e, int batch_size, int wait_us);

@@ -1969,6 +1969,92 @@ int sb_eval_submit(sb_engine* e, const float* planes, int board_size, int policy
 int sb_eval_poll(sb_engine* e, sb_eval_ticket* ticket, sb_output* out) { return EvalFinish(e, ticket, out, false); }
 int sb_eval_wait(sb_engine* e, sb_eval_ticket* ticket, sb_output* out) { return EvalFinish(e, ticket, out, true); }
 
+// Network::GetOutput(state, kAverage), /root/reference/src/neural/network.cc:258-282: the reference evaluates the 8 symmetric
+// views of a position with 8 SERIAL Forward calls, post-processes each (TransformResult :361-411, ActivatePolicy :413-428) and
+// averages.  Here the 8 views are built from the identity view (Encoder::SymmetryPlanes, encoder.cc:80-98: view[i] =
+// planes[T(i)]), submitted as 8 tickets from the calling thread — they land in ONE batch — and post-processed with the
+// same formulas in the same order.
+static inline int SymmIndex(int n, int symm, int idx) {   // Symmetry::GetSymmetry, /root/reference/src/game/symmetry.cc:97-123
+    int x = idx % n, y = idx / n;
+    if (symm & 4) std::swap(x, y);
+    if (symm & 2) x = n - 1 - x;
+    if (symm & 1) y = n - 1 - y;
+    return y * n + x;
+}
+
+int sb_eval_symm8(sb_engine* e, const float* planes, int board_size, int policy_offset, float temperature, sb_symm8_result* out) {
+    if (!e || !planes || !out) return SB_ERR_INVALID;
+    if (board_size < 2 || board_size > SB_MAX_BOARD_SIZE) return Fail(e, SB_ERR_INVALID, "board size out of range");
+    if (!(temperature > 0.f)) return Fail(e, SB_ERR_INVALID, "temperature must be positive");
+    const int ns = board_size * board_size;
+    std::vector<float> views((size_t)8 * SB_INPUT_CHANNELS * ns);
+    std::vector<int> table((size_t)8 * ns);
+    for (int s = 0; s < 8; ++s) {
+        int* t = table.data() + (size_t)s * ns;
+        for (int i = 0; i < ns; ++i) t[i] = SymmIndex(board_size, s, i);
+        float* v = views.data() + (size_t)s * SB_INPUT_CHANNELS * ns;
+        for (int c = 0; c < SB_INPUT_CHANNELS; ++c)
+            for (int i = 0; i < ns; ++i) v[(size_t)c * ns + i] = planes[(size_t)c * ns + t[i]];
+    }
+    sb_eval_ticket tk[8];
+    int n_sub = 0, rc = SB_OK;
+    for (; n_sub < 8; ++n_sub) {
+        rc = EvalBegin(e, views.data() + (size_t)n_sub * SB_INPUT_CHANNELS * ns, board_size, policy_offset, &tk[n_sub]);
+        if (rc) break;
+    }
+    std::unique_ptr<sb_output[]> raw(new sb_output[8]);
+    for (int s = 0; s < n_sub; ++s) {
+        const int r2 = EvalFinish(e, &tk[s], &raw[s], true);
+        if (r2 && !rc) rc = r2;
+    }
+    if (rc) return rc;
+
+    std::memset(out, 0, sizeof(*out));
+    out->board_size = board_size;
+    auto softplus_sq = [](float x) {
+        if (x <= 20.f) x = std::log(1.f + std::exp(x));
+        return (x * x) / 4.f;
+    };
+    std::vector<float> logits(ns + 1), prob(ns + 1);
+    for (int s = 0; s < 8; ++s) {
+        const sb_output& r = raw[s];
+        const int* t = table.data() + (size_t)s * ns;
+        // TransformResult: inverse symmetry (result[T(i)] = view[i]), tanh on the ownership
+        for (int i = 0; i < ns; ++i) logits[t[i]] = r.probabilities[i];
+        logits[ns] = r.pass_probability;
+        // ActivatePolicy: softmax over the board and the pass move with temperature (utils/logits.h:22-39, double accumulator)
+        const float alpha = *std::max_element(logits.begin(), logits.end());
+        double denom = 0.0;
+        for (int i = 0; i <= ns; ++i) {
+            const double val = std::exp((double)(logits[i] - alpha) / (double)temperature);
+            denom += val;
+            prob[i] = (float)val;
+        }
+        for (int i = 0; i <= ns; ++i) prob[i] = (float)((double)prob[i] / denom);
+        for (int i = 0; i < ns; ++i) out->probabilities[i] += prob[i] / 8;
+        out->pass_probability += prob[ns] / 8;
+        for (int i = 0; i < ns; ++i) out->ownership[t[i]] += std::tanh(r.ownership[i]) / 8;
+        float w[3];
+        {
+            const float a3 = std::max(r.wdl[0], std::max(r.wdl[1], r.wdl[2]));
+            double d3 = 0.0;
+            for (int k = 0; k < 3; ++k) {
+                const double val = std::exp((double)(r.wdl[k] - a3));
+                d3 += val;
+                w[k] = (float)val;
+            }
+            for (int k = 0; k < 3; ++k) w[k] = (float)((double)w[k] / d3);
+        }
+        for (int k = 0; k < 3; ++k) out->wdl[k] += w[k] / 8;
+        out->wdl_winrate += ((w[0] - w[2] + 1.f) / 2) / 8;
+        out->stm_winrate += ((std::tanh(r.stm_winrate) + 1.f) / 2) / 8;
+        out->final_score += (20 * r.final_score) / 8;
+        out->q_error += (float)(0.25 * softplus_sq(r.q_error)) / 8;
+        out->score_error += (150 * softplus_sq(r.score_error)) / 8;
+    }
+    return SB_OK;
+}
+
 int sb_batcher_config(sb_engine* e, int batch_size, int wait_us) {
     if (!e) return SB_ERR_INVALID;
     if (batch_size > e->max_batch) return Fail(e, SB_ERR_INVALID, "batch size exceeds max_batch");

@@ -72,6 +72,13 @@ class SbPackedPosition(ctypes.Structure):
                 ("reserved", ctypes.c_int32)]
 
 
+class SbSymm8Result(ctypes.Structure):
+    _fields_ = [("probabilities", ctypes.c_float * MAX_INTERSECTIONS), ("ownership", ctypes.c_float * MAX_INTERSECTIONS),
+                ("pass_probability", ctypes.c_float), ("wdl", ctypes.c_float * 3), ("wdl_winrate", ctypes.c_float),
+                ("stm_winrate", ctypes.c_float), ("final_score", ctypes.c_float), ("q_error", ctypes.c_float),
+                ("score_error", ctypes.c_float), ("board_size", ctypes.c_int)]
+
+
 class SbEvalTicket(ctypes.Structure):
     _fields_ = [("owner", ctypes.c_void_p), ("batch", ctypes.c_void_p), ("seq", ctypes.c_uint32), ("index", ctypes.c_int32),
                 ("lane", ctypes.c_int32), ("flags", ctypes.c_int32), ("board_size", ctypes.c_int32), ("offset", ctypes.c_int32)]
@@ -93,6 +100,7 @@ ABI_SYMBOLS = [
     "sb_get_block_desc", "sb_get_dw_desc", "sb_host_net_load", "sb_host_net_free", "sb_host_net_desc", "sb_host_net_tensor",
     "sb_pack_position", "sb_unpack_position", "sb_eval", "sb_batcher_config", "sb_batcher_stats", "sb_eval_throughput",
     "sb_eval_submit", "sb_eval_poll", "sb_eval_wait", "sb_eval_throughput_async", "sb_weights_broadcast", "sb_weights_stats",
+    "sb_eval_symm8",
 ]
 
 _lib = None
@@ -166,6 +174,7 @@ def load_library():
     lib.sb_eval_submit.argtypes = [vp, _F, ctypes.c_int, ctypes.c_int, ctypes.POINTER(SbEvalTicket)]
     lib.sb_eval_poll.argtypes = [vp, ctypes.POINTER(SbEvalTicket), ctypes.c_void_p]
     lib.sb_eval_wait.argtypes = [vp, ctypes.POINTER(SbEvalTicket), ctypes.c_void_p]
+    lib.sb_eval_symm8.argtypes = [vp, _F, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.POINTER(SbSymm8Result)]
     lib.sb_weights_broadcast.argtypes = [vp]
     lib.sb_weights_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     _lib = lib
@@ -417,6 +426,18 @@ class B200ForwardPipe:
         out = np.zeros(1, dtype=OUTPUT_DTYPE)
         self._check(self._lib.sb_eval_wait(self._h, ctypes.byref(ticket), out.ctypes.data))
         return out[0]
+
+    def eval_symm8(self, planes, board_size, offset=0, temperature=1.0):
+        """Network::GetOutput(state, kAverage): the 8 symmetric views in one batch, post-processed and averaged."""
+        a = np.ascontiguousarray(planes, dtype=np.float32).ravel()
+        if a.size < INPUT_CHANNELS * board_size * board_size:
+            raise ValueError("planes array smaller than 43*bs*bs")
+        r = SbSymm8Result()
+        self._check(self._lib.sb_eval_symm8(self._h, a.ctypes.data_as(_F), board_size, offset, temperature, ctypes.byref(r)))
+        s = board_size * board_size
+        return dict(probabilities=np.array(r.probabilities[:s], np.float32), ownership=np.array(r.ownership[:s], np.float32),
+                    pass_probability=r.pass_probability, wdl=np.array(r.wdl[:], np.float32), wdl_winrate=r.wdl_winrate,
+                    stm_winrate=r.stm_winrate, final_score=r.final_score, q_error=r.q_error, score_error=r.score_error)
 
     def batcher_config(self, batch_size=0, wait_us=-1):
         self._check(self._lib.sb_batcher_config(self._h, batch_size, wait_us))

@@ -158,3 +158,50 @@ def test_every_replica_receives_batches_with_fewer_threads_than_the_batch_size(e
         assert rate2 > 0 and mean2 > 4, (rate2, mean2)
     finally:
         pipe.destroy()
+
+
+def test_symmetry_ensemble_matches_eight_oracle_forwards_post_processed_like_the_reference(eng, golden_weights_bin, oracle_lib):
+    """sb_eval_symm8 = Network::GetOutput(state, kAverage) (network.cc:258-282): 8 symmetric views, TransformResult +
+    ActivatePolicy on each, averaged.  Expected values: the CPU oracle on each view (symmetry tables pinned bit-exact to the
+    reference in tests/test_oracle.py) and the reference's formulas in numpy; all 8 views travel in ONE batch."""
+    from sayuri_b200 import synth
+    orc = oracle_lib.Oracle(golden_weights_bin)
+    pipe = eng.B200ForwardPipe().initialize(golden_weights_bin, 19, 16, gpus=[0])
+    try:
+        for bs, temp, off in ((19, 1.0, 0), (9, 0.8, 2), (13, 1.3, 4)):
+            s = bs * bs
+            x = synth.synth_positions(1, bs, seed=700 + bs)[0].reshape(43, s)
+            exp = dict(prob=np.zeros(s + 1), own=np.zeros(s), wdl=np.zeros(3), wdl_winrate=0.0, stm=0.0, score=0.0, qe=0.0, se=0.0)
+            for symm in range(8):
+                t = oracle_lib.Oracle.symmetry_table(bs, symm)          # T(i)
+                r = orc.forward(x[:, t].ravel(), bs, off)                 # view[i] = planes[T(i)]
+                logits = np.zeros(s + 1)
+                logits[t] = r["prob"]                                     # result[T(i)] = view output[i]
+                logits[s] = r["misc"][0]
+                z = np.exp((logits - logits.max()) / temp)
+                exp["prob"] += z / z.sum() / 8
+                own = np.zeros(s)
+                own[t] = np.tanh(r["own"])
+                exp["own"] += own / 8
+                w = np.exp(r["misc"][1:4] - r["misc"][1:4].max())
+                w /= w.sum()
+                exp["wdl"] += w / 8
+                exp["wdl_winrate"] += (w[0] - w[2] + 1) / 2 / 8
+                exp["stm"] += (np.tanh(r["misc"][4]) + 1) / 2 / 8
+                exp["score"] += 20 * r["misc"][5] / 8
+                sp = lambda v: (np.log1p(np.exp(v)) if v <= 20 else v) ** 2 / 4
+                exp["qe"] += 0.25 * sp(r["misc"][6]) / 8
+                exp["se"] += 150 * sp(r["misc"][7]) / 8
+            before = pipe.batcher_stats()
+            got = pipe.eval_symm8(x.ravel(), bs, off, temp)
+            after = pipe.batcher_stats()
+            assert after["positions"] - before["positions"] == 8 and after["batches"] - before["batches"] == 1
+            np.testing.assert_allclose(got["probabilities"], exp["prob"][:s], rtol=0, atol=2e-6)
+            assert abs(got["pass_probability"] - exp["prob"][s]) < 2e-6
+            np.testing.assert_allclose(got["ownership"], exp["own"], rtol=0, atol=2e-5)
+            np.testing.assert_allclose(got["wdl"], exp["wdl"], rtol=0, atol=1e-5)
+            assert abs(got["wdl_winrate"] - exp["wdl_winrate"]) < 1e-5 and abs(got["stm_winrate"] - exp["stm"]) < 1e-5
+            assert abs(got["final_score"] - exp["score"]) < 2e-3 and abs(got["q_error"] - exp["qe"]) < 1e-4
+            assert abs(got["score_error"] - exp["se"]) < 2e-2      # 150 x a 1e-4-accurate quantity
+    finally:
+        pipe.destroy()
