@@ -193,23 +193,51 @@ __device__ __forceinline__ bool last_cta_of_sample(int* counter, int n_ctas, int
     return last;
 }
 
-// Small fully-connected layer y = W x (+ b) for the per-sample tails: 8 adjacent lanes share one output and stride its
-// inputs (a 32-byte run per step), all outputs of a pass are computed concurrently by the 256 threads, a fixed 3-step
-// shuffle tree finishes each output.  (One warp per output with the outputs of a warp in sequence made these tails
-// 11 us of pure latency per sample.)  x in shared memory; calls `emit(o, sum)` from the first lane of each output.
+// Small fully-connected layer y = W x (+ b) for the per-sample tails (256 threads).  L = 1, 2, 4 or 8 adjacent lanes share one
+// output (L chosen so that all outputs of the layer are computed in as few passes as possible: 256 outputs -> one thread
+// each, 32 outputs -> 8 lanes each); a lane strides the input in 16-byte pieces and issues up to 8 weight loads before
+// it starts to accumulate, a fixed shuffle tree over the L lanes finishes each output.  These tails are pure latency (one
+// CTA per sample, weights from L2): with one warp per output and the outputs of a warp in sequence they took 11 us, with
+// scalar strided loads and 8 sequential passes for the 2C excite outputs 18 us per SE unit.  x in shared memory, 16-byte
+// aligned; calls `emit(o, sum)` from the first lane of each output.  The summation order depends only on (in, out).
 template <typename Emit>
 __device__ __forceinline__ void fc_tail_8lanes(const float* __restrict__ w, const float* x, int in, int out, Emit emit) {
-    const int sub = threadIdx.x & 7;
-    for (int o0 = 0; o0 < out; o0 += 32) {
-        const int o = o0 + (threadIdx.x >> 3);
+    int L = 8;
+    while (L > 1 && out * L > 256) L >>= 1;
+    const int sub = threadIdx.x & (L - 1);
+    const int per_pass = 256 / L;
+    const bool vec = (in & 3) == 0;
+    for (int o0 = 0; o0 < out; o0 += per_pass) {
+        const int o = o0 + threadIdx.x / L;
         float acc = 0.f;
         if (o < out) {
             const float* wr = w + (size_t)o * in;
-            for (int i = sub; i < in; i += 8) acc += wr[i] * x[i];
+            if (vec) {
+                const float4* w4 = reinterpret_cast<const float4*>(wr);
+                const float4* x4 = reinterpret_cast<const float4*>(x);
+                const int n4 = in >> 2;
+                for (int c0 = sub; c0 < n4; c0 += 8 * L) {
+                    float4 wv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) wv[k] = (c0 + k * L < n4) ? w4[c0 + k * L] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (c0 + k * L < n4) {
+                            const float4 xv = x4[c0 + k * L];
+                            acc += wv[k].x * xv.x;
+                            acc += wv[k].y * xv.y;
+                            acc += wv[k].z * xv.z;
+                            acc += wv[k].w * xv.w;
+                        }
+                    }
+                }
+            } else {
+                for (int i = sub; i < in; i += L) acc += wr[i] * x[i];
+            }
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (L > 1) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (L > 2) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (L > 4) acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         if (o < out && sub == 0) emit(o, acc);
     }
 }
