@@ -14,6 +14,12 @@
 //                                                    GameState: every link-time override sits under that call, so
 //                                                    plain and override builds must print the same digest; also
 //                                                    prints the time per encoded position
+//   pass_alive_harness ladder <games> <seed> [size]  Board::GetLadderMap (board.cc:1618-1688, whatever this binary links: the
+//                                                    reference's in the plain build, the link-time override in the _fast
+//                                                    build) against sb_go::LadderMap (host_go/ladder.h) on a copy of the
+//                                                    board's string arrays, on every position of seeded random games;
+//                                                    prints mismatches, an FNV digest of all maps and ns per map
+//   pass_alive_harness dumpladder <games> <seed> <file>   ladder fixtures: board arrays + the map this binary's Board::GetLadderMap gives
 //   pass_alive_harness dump  <games> <seed> <file>   fixture file for tests/test_pass_alive.py (positions + the
 //                                                    REFERENCE's answers), format in tests/test_pass_alive.py
 #include <chrono>
@@ -37,6 +43,7 @@
 #include "neural/encoder.h"
 
 #include "../sayuri_b200/csrc/host_go/pass_alive.h"
+#include "../sayuri_b200/csrc/host_go/ladder.h"
 
 namespace {
 
@@ -296,6 +303,108 @@ int Dump(int games, std::uint64_t seed, const char* path) {
 
 }  // namespace
 
+sb_go::LadderBoard LadderView(const Board& b) {
+    sb_go::LadderBoard lb;
+    std::memcpy(lb.state, b.state_.data(), sizeof(lb.state));
+    std::memcpy(lb.neighbours, b.neighbours_.data(), sizeof(lb.neighbours));
+    std::memcpy(lb.next, b.strings_.next_.data(), sizeof(lb.next));
+    std::memcpy(lb.parent, b.strings_.parent_.data(), sizeof(lb.parent));
+    std::memcpy(lb.liberties, b.strings_.liberties_.data(), sizeof(lb.liberties));
+    std::memcpy(lb.stones, b.strings_.stones_.data(), sizeof(lb.stones));
+    lb.ko_move = b.ko_move_;
+    lb.board_size = b.board_size_;
+    lb.stride = b.letter_box_size_;
+    for (int k = 0; k < 4; ++k) lb.dir[k] = b.directions_[k];
+    return lb;
+}
+
+// Ladders need fights: random play with a bias towards ataris (a move next to a string with two liberties)
+template <typename F> void PlayLadderGame(int size, std::uint64_t& rng, F&& visit) {
+    Board board;
+    board.Reset(size);
+    int color = kBlack, passes = 0;
+    const int max_moves = size * size * 2;
+    visit(board);
+    for (int move = 0; move < max_moves && passes < 2; ++move) {
+        std::vector<int> cand, sharp;
+        for (int i = 0; i < board.GetEmptyCount(); ++i) {
+            const int vtx = board.GetEmpty(i);
+            if (!board.IsLegalMove(vtx, color) || board.IsRealEye(vtx, color)) continue;
+            cand.push_back(vtx);
+            for (int k = 0; k < 4; ++k) {
+                const int a = vtx + board.directions_[k];
+                if (board.state_[a] == !color && board.strings_.GetLiberty(board.strings_.GetParent(a)) <= 2) {
+                    sharp.push_back(vtx);
+                    break;
+                }
+            }
+        }
+        if (cand.empty() || SplitMix(rng) % 131 == 0) {
+            board.PlayMoveAssumeLegal(kPass, color);
+            ++passes;
+        } else {
+            const auto& from = (!sharp.empty() && SplitMix(rng) % 3 != 0) ? sharp : cand;
+            board.PlayMoveAssumeLegal(from[SplitMix(rng) % from.size()], color);
+            passes = 0;
+        }
+        color = !color;
+        visit(board);
+    }
+}
+
+int Ladder(int games, std::uint64_t seed, int only_size, const char* dump_path) {
+    std::uint64_t rng = seed;
+    long positions = 0, mismatches = 0, marked = 0, with_ladder = 0;
+    std::uint64_t digest = 1469598103934665603ull;
+    double t_member = 0, t_header = 0;
+    FILE* f = dump_path ? std::fopen(dump_path, "wb") : nullptr;
+    static const int sizes[] = {5, 7, 9, 9, 11, 13, 13, 15, 17, 19, 19, 19};
+    for (int g = 0; g < games; ++g) {
+        const int size = only_size ? only_size : sizes[g % 12];
+        PlayLadderGame(size, rng, [&](const Board& b) {
+            ++positions;
+            const int n = b.GetNumIntersections();
+            const auto t0 = std::chrono::steady_clock::now();
+            const std::vector<LadderType> member = b.GetLadderMap();
+            const auto t1 = std::chrono::steady_clock::now();
+            const sb_go::LadderBoard lb = LadderView(b);
+            std::uint8_t ours[kNumIntersections];
+            sb_go::LadderMap(lb, ours);
+            const auto t2 = std::chrono::steady_clock::now();
+            t_member += std::chrono::duration<double>(t1 - t0).count();
+            t_header += std::chrono::duration<double>(t2 - t1).count();
+            bool bad = false, any = false;
+            for (int i = 0; i < n; ++i) {
+                bad |= (int)member[i] != (int)ours[i];
+                any |= member[i] != LadderType::kNotLadder;
+                marked += member[i] != LadderType::kNotLadder;
+                digest = (digest ^ (std::uint64_t)member[i]) * 1099511628211ull;
+            }
+            with_ladder += any;
+            if (bad && mismatches++ < 3) {
+                std::fprintf(stderr, "LADDER MISMATCH size %d\n%s", b.GetBoardSize(), b.GetBoardString(kNullVertex, true).c_str());
+                for (int y = b.GetBoardSize() - 1; y >= 0; --y) {
+                    for (int x = 0; x < b.GetBoardSize(); ++x) std::fprintf(stderr, "%d", (int)member[y * b.GetBoardSize() + x]);
+                    std::fprintf(stderr, "   ");
+                    for (int x = 0; x < b.GetBoardSize(); ++x) std::fprintf(stderr, "%d", (int)ours[y * b.GetBoardSize() + x]);
+                    std::fprintf(stderr, "\n");
+                }
+            }
+            if (f && any && (positions % 7 == 0)) {   // a sample of the positions that do contain a ladder
+                std::fwrite(&lb, sizeof(lb), 1, f);
+                std::uint8_t exp[kNumIntersections] = {0};
+                for (int i = 0; i < n; ++i) exp[i] = (std::uint8_t)member[i];
+                std::fwrite(exp, 1, kNumIntersections, f);
+            }
+        });
+    }
+    if (f) std::fclose(f);
+    std::printf("{\"games\": %d, \"positions\": %ld, \"positions_with_a_ladder\": %ld, \"marked_points\": %ld, \"mismatches\": %ld, "
+                "\"digest\": \"%016llx\", \"ns_per_map_member\": %.0f, \"ns_per_map_header\": %.0f}\n",
+                games, positions, with_ladder, marked, mismatches, (unsigned long long)digest, 1e9 * t_member / positions, 1e9 * t_header / positions);
+    return mismatches ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
     static char a0[] = "pass_alive_harness", a1[] = "--quiet";
     char* args[] = {a0, a1};
@@ -304,6 +413,8 @@ int main(int argc, char** argv) {
     if (argc >= 4 && !std::strcmp(argv[1], "encoder")) return EncoderDigest(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argc >= 5 ? std::atoi(argv[4]) : 0);
     if (argc >= 4 && !std::strcmp(argv[1], "digest")) return Digest(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10));
     if (argc >= 5 && !std::strcmp(argv[1], "time")) return Time(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), std::atoi(argv[4]));
+    if (argc >= 4 && !std::strcmp(argv[1], "ladder")) return Ladder(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argc >= 5 ? std::atoi(argv[4]) : 0, nullptr);
+    if (argc >= 5 && !std::strcmp(argv[1], "dumpladder")) return Ladder(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), 0, argv[4]);
     if (argc >= 5 && !std::strcmp(argv[1], "dump")) return Dump(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argv[4]);
     std::fprintf(stderr, "usage: pass_alive_harness check <games> <seed> | time <games> <seed> <size> | dump <games> <seed> <file>\n");
     return 2;

@@ -114,3 +114,30 @@ def test_whole_encoder_is_bit_identical_under_the_link_time_overrides_when_prese
     a = json.loads(subprocess.run([plain, "encoder", "21", "4"], check=True, capture_output=True, text=True).stdout)
     b = json.loads(subprocess.run([fast, "encoder", "21", "4"], check=True, capture_output=True, text=True).stdout)
     assert a["encoded_positions"] == b["encoded_positions"] > 3000 and a["digest"] == b["digest"]
+
+
+def test_ladder_map_replays_reference_fixtures(tmp_path):
+    """sb_go::LadderMap (host_go/ladder.h, the link-time replacement of Board::GetLadderMap) on 933 positions of seeded
+    fight-heavy random games, board sizes 5..19, against the REFERENCE's answers stored with them.  No reference needed."""
+    exe, raw = str(tmp_path / "replay"), str(tmp_path / "cases.bin")
+    subprocess.run(["g++", "-std=c++17", "-O2", os.path.join(ROOT, "tests", "ladder_replay.cc"), "-o", exe], check=True)
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "ladder_cases.bin.gz"), "rb") as g, open(raw, "wb") as f:
+        f.write(g.read())
+    r = subprocess.run([exe, raw], capture_output=True, text=True)
+    stats = json.loads(r.stdout)
+    assert r.returncode == 0 and stats["mismatches"] == 0, stats
+    assert stats["records"] > 900 and stats["records_19x19"] > 300 and stats["marked_points"] > 4000
+
+
+def test_ladder_map_matches_reference_function_live_when_present():
+    """Function against function in one process (the unmodified Board::GetLadderMap vs sb_go::LadderMap on a copy of the
+    board's string arrays), then the front-end's caller through the actual link-time override: same digest of all maps."""
+    plain, fast = os.path.join(REF, "pass_alive_harness"), os.path.join(REF, "pass_alive_harness_fast")
+    if not (os.path.exists(plain) and os.path.exists(fast)):
+        pytest.skip("oracle/_ref not built")
+    a = json.loads(subprocess.run([plain, "ladder", "150", "3"], capture_output=True, text=True).stdout)
+    assert a["mismatches"] == 0 and a["positions"] > 30000 and a["positions_with_a_ladder"] > 10000, a
+    b = json.loads(subprocess.run([fast, "ladder", "150", "3"], capture_output=True, text=True).stdout)
+    assert b["mismatches"] == 0 and b["digest"] == a["digest"] and b["positions"] == a["positions"]
+    # in the override build the member function is ours: no slower than the header called directly (same code)
+    assert b["ns_per_map_member"] < 2.5 * b["ns_per_map_header"]

@@ -25,12 +25,12 @@ def trunks(path, planes, prec, chunk=1, comp=0):
         pipe.destroy()
 
 
-SETTINGS = [(0, 0), (1, 0), (1, 8), (1, 12), (1, 16)]   # (chunk_accumulate, acc_comp_ppb)
+SETTINGS = [(0, 0), (0, 8), (0, 12), (1, 0), (1, 12)]   # (chunk_accumulate, acc_comp_ppb)
 
 
 def main():
     planes = [synth.synth_positions(1, 19, seed=4000 + 17 * i)[0].ravel() for i in range(2)]
-    for C, blocks in ((256, 1), (256, 20), (192, 15), (128, 10)):
+    for C, blocks in ((128, 10), (96, 6), (128, 20), (192, 15)):
         path = os.path.join(tempfile.gettempdir(), "sb_prec_%d_%d.bin" % (C, blocks))
         synth.write_synth_net(path, (blocks, C, 32, 32), seed=20260417, stack=["ResidualBlock"] * blocks)
         orc = Oracle(path)
