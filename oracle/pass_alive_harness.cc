@@ -20,6 +20,7 @@
 //                                                    board's string arrays, on every position of seeded random games;
 //                                                    prints mismatches, an FNV digest of all maps and ns per map
 //   pass_alive_harness dumpladder <games> <seed> <file>   ladder fixtures: board arrays + the map this binary's Board::GetLadderMap gives
+//   pass_alive_harness encparts <games> <seed> <size>  us per call of each stage of Encoder::EncoderFeatures / GetPlanes (identity symmetry)
 //   pass_alive_harness dump  <games> <seed> <file>   fixture file for tests/test_pass_alive.py (positions + the
 //                                                    REFERENCE's answers), format in tests/test_pass_alive.py
 #include <chrono>
@@ -405,6 +406,51 @@ int Ladder(int games, std::uint64_t seed, int only_size, const char* dump_path) 
     return mismatches ? 1 : 0;
 }
 
+int EncoderParts(int games, std::uint64_t seed, int size) {
+    std::uint64_t rng = seed;
+    double t[8] = {0};
+    long n = 0;
+    const Encoder& enc = Encoder::Get();
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
+    for (int g = 0; g < games; ++g) {
+        GameState state;
+        state.Reset(size, 7.5f, kArea);
+        int passes = 0;
+        for (int move = 0; move < size * size * 2 && passes < 2; ++move) {
+            const int color = state.GetToMove();
+            int vtx = kPass;
+            for (int attempt = 0; attempt < 30; ++attempt) {
+                const int v = state.GetVertex(SplitMix(rng) % size, SplitMix(rng) % size);
+                if (state.IsLegalMove(v, color) && !state.board_.IsRealEye(v, color)) {
+                    vtx = v;
+                    break;
+                }
+            }
+            state.PlayMove(vtx, color);
+            passes = vtx == kPass ? passes + 1 : 0;
+            const int ns = size * size;
+            std::vector<float> planes(43 * ns, 0.f);
+            auto it = planes.begin();
+            auto board = state.GetPastBoard(0);
+            auto a = now(); enc.EncoderHistoryMove(state, it, 5); t[0] += since(a);
+            a = now(); enc.FillKoMove(board.get(), it + 24 * ns); t[1] += since(a);
+            a = now(); enc.FillArea(board.get(), color, kArea, it + 25 * ns, 5); t[2] += since(a);
+            a = now(); enc.FillLiberties(board.get(), it + 29 * ns); t[3] += since(a);
+            a = now(); enc.FillLadder(board.get(), it + 33 * ns); t[4] += since(a);
+            a = now(); enc.FillMisc(board.get(), color, kArea, 0.f, 7.5f, it + 37 * ns, 5); t[5] += since(a);
+            a = now(); { const std::vector<float> p2 = enc.GetPlanes(state, 0, 5); t[6] += since(a); }
+            a = now(); { const InputData in = enc.GetInputs(state, 0, 5); t[7] += since(a); }
+            ++n;
+        }
+    }
+    const char* names[8] = {"EncoderHistoryMove", "FillKoMove", "FillArea", "FillLiberties", "FillLadder", "FillMisc", "GetPlanes(total)", "GetInputs(total)"};
+    std::printf("{\"positions\": %ld", n);
+    for (int i = 0; i < 8; ++i) std::printf(", \"%s_us\": %.2f", names[i], 1e6 * t[i] / n);
+    std::printf("}\n");
+    return 0;
+}
+
 int main(int argc, char** argv) {
     static char a0[] = "pass_alive_harness", a1[] = "--quiet";
     char* args[] = {a0, a1};
@@ -413,6 +459,7 @@ int main(int argc, char** argv) {
     if (argc >= 4 && !std::strcmp(argv[1], "encoder")) return EncoderDigest(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argc >= 5 ? std::atoi(argv[4]) : 0);
     if (argc >= 4 && !std::strcmp(argv[1], "digest")) return Digest(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10));
     if (argc >= 5 && !std::strcmp(argv[1], "time")) return Time(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), std::atoi(argv[4]));
+    if (argc >= 5 && !std::strcmp(argv[1], "encparts")) return EncoderParts(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), std::atoi(argv[4]));
     if (argc >= 4 && !std::strcmp(argv[1], "ladder")) return Ladder(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argc >= 5 ? std::atoi(argv[4]) : 0, nullptr);
     if (argc >= 5 && !std::strcmp(argv[1], "dumpladder")) return Ladder(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), 0, argv[4]);
     if (argc >= 5 && !std::strcmp(argv[1], "dump")) return Dump(std::atoi(argv[2]), std::strtoull(argv[3], nullptr, 10), argv[4]);
