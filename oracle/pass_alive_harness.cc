@@ -39,9 +39,9 @@
 #define private public
 #include "game/board.h"
 #include "game/game_state.h"
-#undef private
 #include "config.h"
 #include "neural/encoder.h"
+#undef private
 
 #include "../sayuri_b200/csrc/host_go/pass_alive.h"
 #include "../sayuri_b200/csrc/host_go/ladder.h"
