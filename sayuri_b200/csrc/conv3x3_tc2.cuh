@@ -61,7 +61,8 @@ struct ConvParams {
     int n_full, n_units;     // whole items, and whole items + half units of the tail wave
     int pitch;               // P = N + 1
     int ntaps;               // 9 = 3x3 convolution, 1 = 1x1 convolution (centre tap only)
-    int dbg;                 // ablation bits for profiling only: 1 skip stores, 2 skip activation+split math, 8 no tap shifts, 16 no weight stream, 64 no slab stream
+    int dbg;                 // ablation bits for profiling only: 1 skip stores, 2 skip activation+split math, 8 no tap shifts, 16 no weight stream, 64 no slab stream,
+                             // 128 general MMA issue loop also for 3x3 convolutions (A/B against the unrolled one; same MMAs in the same order)
     int chunk_kh;            // SPLIT: k-halves (64 input channels x all taps) per main-accumulator chunk; kh = one chunk per item
     float chunk_scale;       // SPLIT: a drained chunk is multiplied by this (1 + expected truncation loss of a chunk)
     float* pool_part;        // POOL: [group][2][pool_c] sums and maxima of the output over groups of 2^pool_log2 canvas rows
@@ -234,6 +235,137 @@ __device__ __forceinline__ int pool_first(int lane, int L) {   // first channel 
     return first;
 }
 
+// Barrier wait of the MMA issuer: one try_wait on the fast path; only a wait that really blocks enters the bounded spin
+// (and is what the `wait_*` cycle counters of sb_conv_stats then measure).
+__device__ __forceinline__ void mbar_wait_issuer(uint32_t bar, uint32_t parity, int* err, int site, bool stats, long long& t_acc) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = stats ? clock64() : 0;
+    mbar_wait(bar, parity, err, site);
+    if (stats) t_acc += clock64() - t0;
+}
+
+// Barrier addresses and ring geometry the MMA issuer needs (shared::cta addresses of the leader CTA).
+struct Conv2Issue {
+    uint32_t tmem_base, slab_addr, bst_addr;
+    uint32_t a_full, a_empty, tmem_full, tmem_empty, lo_full, lo_empty, b_full, b_empty;
+    uint32_t kNB, stage_stride;
+    int chunk_kh, cluster_id, n_clusters, n_items;
+    bool resident;
+};
+
+// MMA issue for 3x3 convolutions: ONE elected thread runs the whole loop nest, the nine taps of a k-half are straight-line
+// code.  The general loop below (per tap: barrier wait, elect, re-derive both descriptors from loop counters, 4-8 MMAs,
+// commit) spends ~60 SASS instructions of a single warp — R2UR moves, uniform-datapath chains, reconvergence brackets —
+// on every 4 MMAs: measured 93 cycles per N = 128 MMA on the fp16 rung with RESIDENT weights and no barrier waits at all
+// (tools/conv_stats.py, total - waits), against 64 cycles of tensor-pipe time: the issuing warp, not the tensor core, set
+// the pace, and every wait on its critical path (a successful try_wait costs ~11 cycles, 432 of them per split item) added
+// to it.  Here the tap shifts and stage addresses are formed once per k-half, the per-MMA work is one 64-bit add per
+// descriptor, and a wait that succeeds at once costs one instruction and one branch.  Same MMAs, same order, same
+// accumulators as the general loop: results are bit-identical (test_scheduling_knobs_do_not_change_a_single_bit).
+template <bool SPLIT>
+__device__ __forceinline__ void conv2_issue_taps9(const ConvParams& p, const Conv2Issue& q, long long* stats_out) {
+    using Cfg = Conv2Cfg<SPLIT>;
+    constexpr uint32_t kNA = Cfg::kNumSlabs;
+    constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
+    constexpr uint64_t kALo = Cfg::kSlabPartBytes >> 4;     // hi slab part -> lo slab part
+    const int KH = p.kh, BN = p.bn, pitch = p.pitch;
+    const bool stats = stats_out != nullptr;
+    const bool elected = elect_one();   // the whole warp runs the loops (uniform control flow), this lane issues
+    const bool wait_w = !(p.dbg & 16), no_slab = (p.dbg & 64) != 0, resident = q.resident;
+    const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);
+    long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0;
+    const long long t_begin = stats ? clock64() : 0;
+    uint32_t j = 0, cc = 0, a_it = 0;
+    uint32_t as = 0, aph = 0;   // slab ring position and phase
+    uint32_t bs = 0, bph = 0;   // weight ring position and phase
+    for (int item = q.cluster_id; item < q.n_items; item += q.n_clusters, ++j) {
+        const uint32_t ls = j & 1u, lph = (j >> 1) & 1u;
+        const uint32_t idesc = item < p.n_full ? idesc_whole : idesc_half;
+        const uint32_t d_lo = q.tmem_base + (2u * ls + 1u) * BN;
+        if (SPLIT) {
+            mbar_wait_issuer(q.lo_empty + 8 * ls, lph ^ 1u, p.err, 8, stats, t_wait_tmem);
+        }
+        uint32_t d_main = 0;
+        int h_in_chunk = 0;
+        for (int h = 0; h < KH; ++h, ++a_it) {
+            if (h_in_chunk == 0) {
+                const uint32_t cs = cc & 1u, cph = (cc >> 1) & 1u;
+                mbar_wait_issuer(q.tmem_empty + 8 * cs, cph ^ 1u, p.err, 3, stats, t_wait_tmem);
+                d_main = q.tmem_base + (SPLIT ? 2u * cs : cs) * BN;
+            }
+            if (!(no_slab && a_it >= kNA)) mbar_wait_issuer(q.a_full + 8 * as, aph, p.err, 4, stats, t_wait_slab);
+            tc_fence_after();
+            // descriptor of the un-shifted tile; a tap shift of s rows is +s in the 16-byte start-address field
+            const uint64_t a_base = umma_desc_nosw(q.slab_addr + as * Cfg::kSlabBytes + (uint32_t)kSlabMargin * 16u, kSlabRows2 * 16u, 128u);
+            const uint32_t first_main = h_in_chunk == 0 ? 0u : 1u;
+            const uint32_t first_lo = h == 0 ? 0u : 1u;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int shift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
+                const uint64_t ad0 = a_base + (uint64_t)(int64_t)shift;
+                {   // weights hi x activations hi -> main ; x activations lo -> low-order accumulator
+                    if (wait_w && !(resident && j > 0)) mbar_wait_issuer(q.b_full + 8 * bs, bph, p.err, 5, stats, t_wait_b);
+                    tc_fence_after();
+                    const uint64_t bd0 = umma_desc_sw128(q.bst_addr + bs * q.stage_stride);
+                    if (elected) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma2_f16(d_main, ad0 + kAStep * k, bd0 + 2 * k, idesc, (tap == 0 && k == 0) ? first_main : 1u);
+                            if (SPLIT) umma2_f16(d_lo, ad0 + kALo + kAStep * k, bd0 + 2 * k, idesc, (tap == 0 && k == 0) ? first_lo : 1u);
+                        }
+                        if (!resident) umma2_commit_mc(q.b_empty + 8 * bs, 3);
+                    }
+                    __syncwarp();
+                    if (++bs == q.kNB) {
+                        bs = 0;
+                        if (!resident) bph ^= 1u;
+                    }
+                }
+                if (SPLIT) {   // weights lo x activations hi -> low-order accumulator
+                    if (wait_w && !(resident && j > 0)) mbar_wait_issuer(q.b_full + 8 * bs, bph, p.err, 6, stats, t_wait_b);
+                    tc_fence_after();
+                    const uint64_t bd0 = umma_desc_sw128(q.bst_addr + bs * q.stage_stride);
+                    if (elected) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma2_f16(d_lo, ad0 + kAStep * k, bd0 + 2 * k, idesc, 1u);
+                        if (!resident) umma2_commit_mc(q.b_empty + 8 * bs, 3);
+                    }
+                    __syncwarp();
+                    if (++bs == q.kNB) {
+                        bs = 0;
+                        if (!resident) bph ^= 1u;
+                    }
+                }
+            }
+            const bool last_h = h == KH - 1;
+            const bool chunk_done = ++h_in_chunk == q.chunk_kh || last_h;
+            if (elected) {
+                umma2_commit_mc(q.a_empty + 8 * as, 3);
+                if (chunk_done) {   // hand the chunk's accumulator stage (and, behind the last one, the low-order sums) to the epilogue
+                    if (SPLIT && last_h) umma2_commit_mc(q.lo_full + 8 * ls, 3);
+                    umma2_commit_mc(q.tmem_full + 8 * (cc & 1u), 3);
+                }
+            }
+            __syncwarp();
+            if (chunk_done) {
+                h_in_chunk = 0;
+                ++cc;
+            }
+            if (++as == kNA) {
+                as = 0;
+                aph ^= 1u;
+            }
+        }
+    }
+    if (stats && elected) {
+        stats_out[0] = clock64() - t_begin;
+        stats_out[1] = t_wait_tmem;
+        stats_out[2] = t_wait_slab;
+        stats_out[3] = t_wait_b;
+        stats_out[6] = j;
+    }
+}
+
 template <bool SPLIT, int ACT, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<SPLIT>::kThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -267,7 +399,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int chunk_kh = SPLIT ? p.chunk_kh : KH;
     const int n_chunks = (KH + chunk_kh - 1) / chunk_kh;
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role branches and their loop state stay in uniform registers
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -311,7 +443,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     __syncthreads();
     cluster_sync_all();     // barriers of both CTAs are initialised before any remote arrive / TMA credit
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     if (threadIdx.x == 0) pdl_launch_dependents();   // the next layer may start its prologue whenever SMs free up
 
     if (warp == 3) {
@@ -367,8 +499,21 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (leader) {
-            // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && p.ntaps == 9 && !(p.dbg & (8 | 128))) {
+            // ===================== MMA issuer (leader CTA only), 3x3 convolutions: one elected thread, taps unrolled =====================
+            {
+                Conv2Issue q;
+                q.tmem_base = tmem_base; q.slab_addr = slab_addr; q.bst_addr = bst_addr;
+                q.a_full = a_full; q.a_empty = a_empty; q.tmem_full = tmem_full; q.tmem_empty = tmem_empty;
+                q.lo_full = lo_full; q.lo_empty = lo_empty; q.b_full = b_full; q.b_empty = b_empty;
+                q.kNB = kNB; q.stage_stride = stage_stride;
+                q.chunk_kh = chunk_kh; q.cluster_id = cluster_id; q.n_clusters = n_clusters; q.n_items = n_items;
+                q.resident = resident;
+                conv2_issue_taps9<SPLIT>(p, q, p.stats ? p.stats + (size_t)cluster_id * 8 : nullptr);
+            }
+            __syncwarp();
+        } else if (leader) {
+            // ===================== MMA issuer (leader CTA only), general form (1x1 convolutions) =====================
             // TMEM columns per CTA, split rung: [main 0 | lo 0 | main 1 | lo 1] x BN (main stage = chunk counter & 1, low-order
             // accumulator = item counter & 1); fp16 rung: main stage s at s * BN.
             const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);

@@ -386,8 +386,8 @@ def test_tail_wave_split_is_bit_exact(eng):
 
 
 def test_scheduling_knobs_do_not_change_a_single_bit(eng):
-    """Resident weights (fp16 rung), programmatic dependent launch, the small-batch N-tile split and chained forwards
-    only change WHEN and WHERE the same MMAs run: outputs are bit-identical with every knob on and off."""
+    """Resident weights (fp16 rung), programmatic dependent launch, the small-batch N-tile split, chained forwards and the
+    form of the MMA issue loop only change WHEN and WHERE the same MMAs run: outputs are bit-identical with every knob on and off."""
     from sayuri_b200 import synth
     path = os.path.join(tempfile.gettempdir(), "sb_test_4bx128.bin")
     synth.write_synth_net(path, (4, 128, 16, 16), seed=77)
@@ -405,6 +405,12 @@ def test_scheduling_knobs_do_not_change_a_single_bit(eng):
                         pipe.set_option(knob, 1)
                         for f in FIELDS:
                             assert np.array_equal(base[f], other[f]), (prec, n, knob, value, f)
+                # the unrolled single-thread MMA issuer of the 3x3 convolutions against the general issue loop (conv_dbg 128)
+                pipe.set_option("conv_dbg", 128)
+                other = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
+                pipe.set_option("conv_dbg", 0)
+                for f in FIELDS:
+                    assert np.array_equal(base[f], other[f]), (prec, n, "general MMA issue loop", f)
             finally:
                 pipe.destroy()
 
