@@ -69,6 +69,11 @@ struct ConvParams {
     int pool_log2;           // 2..4; groups never straddle samples (the engine checks kGuardRows and SS are multiples)
     int pool_groups;         // groups covered by the batch; groups beyond are not written
     int pool_c;              // channel stride of pool_part
+    // Layer overlap (see "Cross-layer dependencies" below): completion counters per 256-row super tile, in units of
+    // (output columns) x (epilogue quadrant warps); a super tile of a launch is complete at 8 * n_ntiles * bn.
+    int* done_out;           // counters of THIS launch's output, nullptr = not signalled
+    const int* done_in;      // counters of the launch that wrote the input tensor; nullptr = whole-grid dependency (griddepcontrol.wait)
+    int done_in_full;        // value of a complete super tile in done_in
     int* err;                // device int, receives a site code if a barrier wait times out
     long long* stats;        // optional [grid][8] cycle counters (see sb_conv_stats), nullptr = off
 };
@@ -76,6 +81,20 @@ struct ConvParams {
 // Split rung: 2 activation-slab buffers and a 12-stage weight ring measured best (profiles/r01s2_ring_depth.log: +2.4 % on
 // 10bx128, +3.5 % on 20bx256 over 3 slabs + 8 stages; 16 stages: +2 % / +3 %) — the weight stream is what the MMA
 // issuer waits for, a third slab buffer is not.  Overridable for experiments.
+// Epilogue warps per TMEM lane quadrant (= column parts of an accumulator row), a template parameter of the kernel.
+// Measured after the MMA issue loop stopped being the limiter (profiles/r02_epilogue_parts.log, 10bx128, batch 256): the
+// epilogue of 2 warps per scheduler is latency-bound (tcgen05.ld waits, ex2/rcp chains, residual loads) and takes as long
+// per item as the MMAs; 4 parts: split 151 k -> 159 k evals/s, fp16 335 k -> 362 k.  The N = 256 tiles of the fp16 rung
+// (C > 128) are tensor-bound and lose 3 % to the extra warps: they keep 2.
+#ifndef SB_TC2_EPI_PARTS_SPLIT
+#define SB_TC2_EPI_PARTS_SPLIT 4
+#endif
+#ifndef SB_TC2_EPI_PARTS_FP16
+#define SB_TC2_EPI_PARTS_FP16 4    // N <= 128
+#endif
+#ifndef SB_TC2_EPI_PARTS_FP16_WIDE
+#define SB_TC2_EPI_PARTS_FP16_WIDE 2   // N > 128
+#endif
 #ifndef SB_TC2_NA
 #define SB_TC2_NA 2      // activation-slab buffers (split rung)
 #endif
@@ -85,7 +104,7 @@ struct ConvParams {
 constexpr int kTileRows2 = 128;                              // rows per CTA per item
 constexpr int kSlabRows2 = kTileRows2 + 2 * kSlabMargin;     // 176
 
-template <bool SPLIT>
+template <bool SPLIT, int PARTS = 2>
 struct Conv2Cfg {
     static constexpr int kParts = SPLIT ? 2 : 1;
     static constexpr int kSlabPartBytes = kSlabRows2 * 128;          // [8 chunks][176 rows][16 B]
@@ -101,13 +120,11 @@ struct Conv2Cfg {
     static constexpr int kOffBias = kOffBar + 512;
     static constexpr int kSmemBytes = kOffBias + kMaxConvWidth * 4 + 1024;
     static constexpr int kTmemCols = 512;
-    // Epilogue column parts per TMEM lane quadrant = epilogue warps per scheduler.  2 on both rungs: 4 parts (16 epilogue
-    // warps, 640 threads) measured 2 % SLOWER on the fp16 rung (265 k vs 271 k evals/s) and 13 % slower on 1x1-conv
-    // heavy towers — after the resident-weight change that rung is bound by the tensor core's operand reads from
-    // shared memory (~95 cycles per N=128 MMA instead of 64), not by the epilogue.
-    static constexpr int kEpiParts = 2;
+    // Epilogue column parts per TMEM lane quadrant = epilogue warps per scheduler (see SB_TC2_EPI_PARTS_* above).
+    static constexpr int kEpiParts = PARTS;
     static constexpr int kThreads = 128 + kEpiParts * 128;
-    static constexpr int kMaxGroups = 128 / kEpiParts / 16;   // 16-column groups per epilogue thread (BN <= 128)
+    static constexpr int kMaxGroups = 128 / kEpiParts / 16;   // 16-column groups per epilogue thread and pass (BN <= 128: one pass)
+    static constexpr int kPassCols = kMaxGroups * 16;         // a longer run of columns (N = 256 tiles of the fp16 rung) takes several passes
     static_assert(kNumBStages <= 18 && kNumSlabs <= 4, "barrier block layout");
     static_assert(kSlabPartBytes % 1024 == 0, "slab parts must keep the weight stages 1024-byte aligned");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
@@ -235,13 +252,51 @@ __device__ __forceinline__ int pool_first(int lane, int L) {   // first channel 
     return first;
 }
 
-// Barrier wait of the MMA issuer: one try_wait on the fast path; only a wait that really blocks enters the bounded spin
-// (and is what the `wait_*` cycle counters of sb_conv_stats then measure).
+// ---- Cross-layer dependencies ------------------------------------------------------------------------------------
+// A convolution launch whose input was written by the previous convolution launch does not wait for that whole grid
+// (griddepcontrol.wait): item st needs rows of the input's super tiles st-1, st, st+1 only (its slab reaches 24 rows into
+// the neighbours).  Every epilogue warp of the producing launch, after its last store of an item, adds its column count
+// to done[st] with a gpu-scope release; the slab producer of the consuming launch acquires done[st-1 .. st+1] before the
+// first TMA load of an item (plus a generic->async proxy fence), and every epilogue warp acquires done[st] before it
+// prefetches residual pieces (the residual tensor is the input of the producing launch: complete for these rows by
+// transitivity, the engine enables the mode only then).  With programmatic dependent launch the CTAs of layer l+1 become
+// resident as the CTA pairs of layer l run out of items and start on the tiles that are ready: the partial last wave
+// (400 items over 74 pairs = 5.4 waves) and the launch ramp of one layer are filled with the next layer's work.
+// No deadlock: a dependent grid starts only after EVERY CTA of the primary has started (each triggers at its top), so a
+// counter that is waited for is always owned by a resident or finished CTA.  Buffers are re-used across layers
+// (x -> t -> u -> t ...): a tile is overwritten by layer l+2 only after layer l+1's tiles st-1 .. st+1 — the only readers
+// of those rows — have completed, which is exactly what the slab producer waited for.
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu(int* ptr, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// Bounded like mbar_wait: a protocol bug surfaces as a launch failure with a site code, never as a hung GPU.
+__device__ __forceinline__ void wait_tile_done(const int* ctr, int full, int* err, int site) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        if (ld_acquire_gpu(ctr) >= full) return;
+        __nanosleep(64);
+    }
+    if (err) atomicExch(err, site);
+    __threadfence_system();
+    __trap();
+}
+
+// Barrier wait of the MMA issuer: one try_wait on the fast path, the bounded spin behind it.
 __device__ __forceinline__ void mbar_wait_issuer(uint32_t bar, uint32_t parity, int* err, int site, bool stats, long long& t_acc) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = stats ? clock64() : 0;
-    mbar_wait(bar, parity, err, site);
-    if (stats) t_acc += clock64() - t0;
+    if (!stats) {
+        if (mbar_try_wait(bar, parity)) return;
+        mbar_wait(bar, parity, err, site);
+    } else {   // counters on: the whole wait is timed (try_wait itself may block for a while before it reports failure)
+        const long long t0 = clock64();
+        mbar_wait(bar, parity, err, site);
+        t_acc += clock64() - t0;
+    }
 }
 
 // Barrier addresses and ring geometry the MMA issuer needs (shared::cta addresses of the leader CTA).
@@ -366,13 +421,13 @@ __device__ __forceinline__ void conv2_issue_taps9(const ConvParams& p, const Con
     }
 }
 
-template <bool SPLIT, int ACT, bool POOL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<SPLIT>::kThreads, 1)
+template <bool SPLIT, int ACT, bool POOL, int PARTS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<SPLIT, PARTS>::kThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                    const __grid_constant__ CUtensorMap tmWq_hi, const __grid_constant__ CUtensorMap tmWq_lo,
                    const ConvParams p) {
-    using Cfg = Conv2Cfg<SPLIT>;
+    using Cfg = Conv2Cfg<SPLIT, PARTS>;
     const int KH = p.kh, BN = p.bn;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -448,7 +503,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 
     if (warp == 3) {
         // ===================== activation-slab producer (own 128-row tile, +-24 rows) =====================
-        pdl_wait();   // the slabs are the previous layer's output
+        const bool tile_deps = p.done_in != nullptr;
+        if (!tile_deps) pdl_wait();   // the slabs are the previous layer's output
         uint32_t it = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
             const int st = conv_unit(item, p).st;
@@ -458,6 +514,12 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 if ((p.dbg & 64) && it >= kNA) continue;   // ablation: no slab traffic after the first fills
                 mbar_wait(a_empty + 8 * s, ph ^ 1u, p.err, 1);
                 if (elect_one()) {
+                    if (tile_deps && h == 0) {   // the producing launch has finished the super tiles this slab reads
+                        if (st > 0) wait_tile_done(p.done_in + st - 1, p.done_in_full, p.err, 10);
+                        wait_tile_done(p.done_in + st, p.done_in_full, p.err, 11);
+                        if (st + 1 < p.n_super) wait_tile_done(p.done_in + st + 1, p.done_in_full, p.err, 12);
+                        fence_proxy_async_global();
+                    }
                     const uint32_t full0 = mapa_u32(a_full + 8 * s, 0);
                     if (leader) mbar_arrive_expect_tx(a_full + 8 * s, 2u * Cfg::kSlabBytes);
 #pragma unroll
@@ -631,16 +693,24 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const uint32_t empty0 = mapa_u32(tmem_empty, 0);   // leader's tmem_empty[0]; [1] is +8
         const uint32_t lo_empty0 = mapa_u32(lo_empty, 0);
         const float chunk_scale = p.chunk_scale;
-        pdl_wait();   // residual reads, and our stores may overwrite a buffer the previous layer still reads
+        const bool tile_deps = p.done_in != nullptr;
+        if (!tile_deps) pdl_wait();   // residual reads, and our stores may overwrite a buffer the previous layer still reads
         for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
             const ConvUnit w = conv_unit(item, p);
             const int st = w.st;
+            if (tile_deps && p.res_hi != nullptr) {
+                // the residual rows of this tile are final (see "Cross-layer dependencies"); the acquire also invalidates
+                // this SM's L1 (LDG.STRONG.GPU + CCTL.IVALL), so the plain loads below cannot hit a line cached before
+                // the rows were written (each 128-byte line of a tile is read by one warp only)
+                if (lane == 0) wait_tile_done(p.done_in + st, p.done_in_full, p.err, 13);
+                __syncwarp();
+            }
             // columns of this thread: w.bn split into kEpiParts runs rounded to the 16-column ld granule (may be 0);
-            // a run longer than 64 columns (N = 256 tiles of the fp16 rung) is processed in passes of 64
+            // a run longer than kPassCols columns (N = 256 tiles of the fp16 rung) is processed in passes
             const int c_run = ((w.bn + Cfg::kEpiParts - 1) / Cfg::kEpiParts + 15) & ~15;
             const int cbase = min(part * c_run, w.bn);
             const int HC = min(c_run, w.bn - cbase);
-            const int n_pass = max(1, (HC + 63) >> 6);     // 1 on the split rung (BN <= 128)
+            const int n_pass = max(1, (HC + Cfg::kPassCols - 1) / Cfg::kPassCols);     // 1 on the split rung (BN <= 128)
             const uint32_t ls = j & 1u, lph = (j >> 1) & 1u;
 
             const int row = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 + q * 32 + lane;
@@ -650,8 +720,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
             for (int pass = 0; pass < n_pass; ++pass) {
-                const int pbase = cbase + pass * 64;            // first column of this pass inside the N tile
-                const int PC = min(64, HC - pass * 64);         // columns of this pass (multiple of 16, may be 0)
+                const int pbase = cbase + pass * Cfg::kPassCols;            // first column of this pass inside the N tile
+                const int PC = min(Cfg::kPassCols, HC - pass * Cfg::kPassCols);   // columns of this pass (multiple of 16, may be 0)
                 // Everything the epilogue needs from global memory is requested BEFORE waiting for the accumulators:
                 // the mask byte and the residual pieces of the first 16-column group; the pieces of group g+1 are
                 // requested while group g is computed (a load issued at its point of use stalled ~1 us per group).
@@ -827,6 +897,13 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             }
                         }
                     }
+                }
+            }
+            if (p.done_out != nullptr && HC > 0) {   // this warp's part of the tile is stored: publish it to the next layer
+                __syncwarp();
+                if (lane == 0) {
+                    fence_proxy_async_global();   // the consumer reads these rows with TMA (async proxy)
+                    red_release_gpu(p.done_out + st, HC);
                 }
             }
         }

@@ -290,6 +290,11 @@ struct ActBuf {
     int channels = 0;   // padded to a multiple of 64
     int rows = 0;       // R
     CUtensorMap tm3_hi, tm3_lo;     // 176-row slabs
+    // layer overlap (conv3x3_tc2.cuh, "Cross-layer dependencies"): set while the tensor holds the output of a convolution
+    // launch of the forward being enqueued that publishes per-tile completion counters
+    const int* done = nullptr;      // the counters, nullptr = written by something else (whole-grid dependency)
+    int done_full = 0;              // value of a complete super tile
+    const ActBuf* done_src = nullptr;   // the input tensor of that launch
 };
 
 struct Slot {
@@ -323,6 +328,8 @@ struct Slot {
     int* d_err = nullptr;
     int n = 0;                 // samples of the batch in flight / last uploaded
     int conv_counter = 0;      // conv launches of the forward being enqueued on this slot (option "stats_launch")
+    int* d_done = nullptr;     // [kMaxDoneLaunches][done_stride] per-tile completion counters of the conv launches of a forward
+    int done_stride = 0;
     bool busy = false;
     std::vector<int> sizes, offsets;
 };
@@ -449,6 +456,12 @@ struct sb_engine {
     int pdl_aux = 1;     // ... and for the unpack / SE / head kernels between them: 0 off, 1 for batches <= 64 (measured:
                          // -2.0..-2.5 % per forward at batch 32, +-1 % noise at batch 256; profiles/r01s2_pdl_aux_ab.md), 2 always
     int tail_split = 1;  // split the items of a partial last wave into N-halves (conv3x3_tc2)
+    int layer_overlap = 1;   // convolution launches depend on their producer tile by tile instead of grid by grid
+                             // (conv3x3_tc2.cuh, "Cross-layer dependencies"; needs use_pdl): 0 off, 1 split rung at batches
+                             // <= 64, 2 always.  Measured (profiles/r02_layer_overlap.md): -2..-4 % per forward at batch
+                             // 1..64 on the split rung; nothing at batch 256 (the SMs are held by the previous layer's CTAs
+                             // anyway); -8 % THROUGHPUT on the fp16 rung, whose epilogue warps are the critical path and pay
+                             // for the gpu-scope release per item
     int pack_inputs = 1; // pageable inputs travel as compact exact records (host_pack.cc); 0 = always fp32 staging
     int pack_threads = 4;
     int batcher_batch = 0;      // 0 = max_batch
@@ -479,6 +492,13 @@ static std::string g_create_error;
 namespace sb {
 
 static bool Split(const sb_engine* e) { return e->precision != SB_PRECISION_FP16; }
+static bool LayerOverlap(const sb_engine* e, int n) {
+    if (!e->use_pdl || e->precision == SB_PRECISION_SIMT_DEBUG) return false;
+    return e->layer_overlap == 2 || (e->layer_overlap == 1 && Split(e) && n <= 64);
+}
+// epilogue warps per TMEM lane quadrant of the conv kernel, per rung (conv3x3_tc2.cuh)
+constexpr int kMaxDoneLaunches = 256;   // conv launches of a forward that can publish per-tile completion counters
+constexpr int kPartsSplit = SB_TC2_EPI_PARTS_SPLIT, kPartsFp16 = SB_TC2_EPI_PARTS_FP16, kPartsFp16Wide = SB_TC2_EPI_PARTS_FP16_WIDE;
 
 static void FreeSlot(Slot& s) {
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -507,6 +527,8 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.pass5);
     cudaFree(s.misc15);
     cudaFree(s.d_stats);
+    cudaFree(s.d_done);
+    s.d_done = nullptr;
     cudaFreeHost(s.h_err);
     s = Slot{};
 }
@@ -586,6 +608,9 @@ static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int
         SB_CUDA(cudaMalloc(&s.misc15, (size_t)e->max_batch * 15 * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.d_stats, (size_t)r.sm_count * 8 * sizeof(long long)));
         SB_CUDA(cudaMemset(s.d_stats, 0, (size_t)r.sm_count * 8 * sizeof(long long)));
+        s.done_stride = e->geom.n_super(e->max_batch) + 1;
+        SB_CUDA(cudaMalloc(&s.d_done, (size_t)kMaxDoneLaunches * s.done_stride * sizeof(int)));
+        SB_CUDA(cudaMemset(s.d_done, 0, (size_t)kMaxDoneLaunches * s.done_stride * sizeof(int)));
         SB_CUDA(cudaHostAlloc(&s.h_err, sizeof(int), cudaHostAllocMapped));
         *s.h_err = 0;
         SB_CUDA(cudaHostGetDevicePointer(&s.d_err, s.h_err, 0));
@@ -670,11 +695,13 @@ static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* b
     // widths can coexist in one process
     for (int act = 0; act < 8; ++act) {
         SB_DISPATCH_ACT(act, ACT,
-            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
-            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes)));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, ACT, false, kPartsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, ACT, false, kPartsFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes));
+            SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, ACT, false, kPartsFp16Wide>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes)));
     }
-    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, kIdentity, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
-    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, kIdentity, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes));
+    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<true, kIdentity, true, kPartsSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<true>::kSmemBytes));
+    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, kIdentity, true, kPartsFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes));
+    SB_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<false, kIdentity, true, kPartsFp16Wide>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg<false>::kSmemBytes));
 }
 
 
@@ -893,6 +920,7 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
                                                           res ? res->hi : nullptr, res ? res->lo : nullptr, s.mask,
                                                           c.L.cout, n_super * kSuperRows, e->geom.P, c.L.taps, act, out.hi,
                                                           out.lo, out.rows);
+        out.done = nullptr;
     } else {
         ConvParams p;
         p.out_hi = out.hi;
@@ -918,6 +946,13 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         p.pool_c = e->net_shape.channels;
         p.err = s.d_err;
         p.stats = (e->collect_stats && (e->stats_launch < 0 || e->stats_launch == s.conv_counter)) ? s.d_stats : nullptr;
+        // layer overlap: this launch publishes per-tile completion counters; it depends on its producer tile by tile when
+        // the input is the output of a launch that published them and the residual (if any) is that launch's own input
+        const bool overlap = LayerOverlap(e, n) && s.conv_counter < kMaxDoneLaunches;
+        p.done_out = overlap ? s.d_done + (size_t)s.conv_counter * s.done_stride : nullptr;
+        const bool tile_deps = overlap && in.done != nullptr && (res == nullptr || res == in.done_src);
+        p.done_in = tile_deps ? in.done : nullptr;
+        p.done_in_full = in.done_full;
         s.conv_counter++;
         // Small batches: narrow the N tile (bn >> level) while all items still fit in one wave, so that a handful of
         // positions is spread over up to 4x more CTA pairs (latency of the single-position / GTP case).
@@ -941,6 +976,9 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         if (e->tail_split && !p.resident && items2 > pairs && rem > 0 && 2 * rem <= pairs && level + 1 < c.levels) n_tail = rem;
         p.n_full = items2 - n_tail;
         p.n_units = items2 + n_tail;
+        out.done = p.done_out;
+        out.done_full = 8 * p.n_ntiles * p.bn;
+        out.done_src = &in;
         const CUtensorMap& w_hi = c.tm2_hi[level];
         const CUtensorMap& w_lo = c.tm2_lo[level];
         const CUtensorMap& wq_hi = c.tm2_hi[level + 1];
@@ -948,7 +986,9 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         // launched with the programmatic-stream-serialization attribute: see pdl_wait() in conv3x3_tc2.cuh
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid2);
-        cfg.blockDim = dim3(Split(e) ? Conv2Cfg<true>::kThreads : Conv2Cfg<false>::kThreads);
+        const bool wide = !Split(e) && p.bn > 128;   // N = 256 tiles of the fp16 rung: tensor-bound, fewer epilogue warps
+        cfg.blockDim = dim3(Split(e) ? Conv2Cfg<true, kPartsSplit>::kThreads
+                                     : wide ? Conv2Cfg<false, kPartsFp16Wide>::kThreads : Conv2Cfg<false, kPartsFp16>::kThreads);
         cfg.stream = s.stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -959,19 +999,25 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
             if (act != kIdentity) throw CudaError{"internal error: pooled convolution with an activation"};
             if (Split(e)) {
                 cfg.dynamicSmemBytes = Conv2Cfg<true>::kSmemBytes;
-                SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, kIdentity, true>, in.tm3_hi, in.tm3_lo, w_hi, w_lo, wq_hi, wq_lo, p));
+                SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, kIdentity, true, kPartsSplit>, in.tm3_hi, in.tm3_lo, w_hi, w_lo, wq_hi, wq_lo, p));
             } else {
                 cfg.dynamicSmemBytes = Conv2Cfg<false>::kSmemBytes;
-                SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, kIdentity, true>, in.tm3_hi, in.tm3_hi, w_hi, w_hi, wq_hi, wq_hi, p));
+                if (wide) SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, kIdentity, true, kPartsFp16Wide>, in.tm3_hi, in.tm3_hi, w_hi, w_hi, wq_hi, wq_hi, p));
+                else SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, kIdentity, true, kPartsFp16>, in.tm3_hi, in.tm3_hi, w_hi, w_hi, wq_hi, wq_hi, p));
             }
         } else if (Split(e)) {
             cfg.dynamicSmemBytes = Conv2Cfg<true>::kSmemBytes;
-            SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, ACT, false>, in.tm3_hi, in.tm3_lo, w_hi,
+            SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, ACT, false, kPartsSplit>, in.tm3_hi, in.tm3_lo, w_hi,
                                                                   w_lo, wq_hi, wq_lo, p)));
         } else {
             cfg.dynamicSmemBytes = Conv2Cfg<false>::kSmemBytes;
-            SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT, false>, in.tm3_hi, in.tm3_hi, w_hi,
-                                                                  w_hi, wq_hi, wq_hi, p)));
+            if (wide) {
+                SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT, false, kPartsFp16Wide>, in.tm3_hi, in.tm3_hi,
+                                                                      w_hi, w_hi, wq_hi, wq_hi, p)));
+            } else {
+                SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT, false, kPartsFp16>, in.tm3_hi, in.tm3_hi,
+                                                                      w_hi, w_hi, wq_hi, wq_hi, p)));
+            }
         }
     }
     SB_CUDA(cudaGetLastError());
@@ -1004,6 +1050,7 @@ static void LaunchDw(sb_engine* e, Slot& s, const DwLayout& d, const uint8_t* bl
     const size_t smem = ((size_t)d.k * d.k * 8 + 8 + (size_t)(128 + 2 * halo) * 8) * sizeof(float);
     SB_DISPATCH_ACT(act, ACT, (dwconv_kernel<ACT><<<grid, 128, smem, s.stream>>>(in.hi, in.lo, out.hi, out.lo, Split(e), w, b, s.d_meta,
                                                                               e->geom, n, n_rows, in.rows, out.rows, d.k, add_input)));
+    out.done = nullptr;   // not a convolution launch: consumers depend on the whole grid
     SB_CUDA(cudaGetLastError());
     e->launches++;
 }
@@ -1021,6 +1068,12 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     auto F = [&](size_t off) { return reinterpret_cast<const float*>(r.blob + off); };
 
     s.conv_counter = 0;
+    for (ActBuf* b : {&s.in, &s.x, &s.t, &s.u, &s.ia, &s.ib, &s.ic, &s.pv, &s.pq}) b->done = nullptr;
+    if (LayerOverlap(e, n)) {   // per-tile completion counters of this forward's convolution launches
+        size_t n_conv = 3;   // input, head entry, RepLK 1x1
+        for (const auto& blk : r.bconv) n_conv += blk.size();
+        SB_CUDA(cudaMemsetAsync(s.d_done, 0, std::min<size_t>(n_conv, kMaxDoneLaunches) * s.done_stride * sizeof(int), s.stream));
+    }
     const int pool_log2 = PoolLog2(g);
     const bool pool_fused = e->fuse_se_pool && pool_log2 > 0 && e->precision != SB_PRECISION_SIMT_DEBUG;
     auto mark = [&]() { if (tm) tm->Mark(s.stream); };   // brackets groups of non-convolution kernels (profiling pass)
@@ -1098,6 +1151,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
                                                 u->hi, u->lo, (const __half*)se_skip->hi, (const __half*)se_skip->lo, split,
                                                 (const uint8_t*)s.mask, (const float*)s.gb, g, C, u->rows, n_rows));
             SB_CUDA(cudaGetLastError());
+            u->done = nullptr;   // rewritten in place by se_apply
             e->launches += 2;
             mark();
         }
@@ -2478,6 +2532,10 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     }
     if (!std::strcmp(key, "pdl_aux")) {
         e->pdl_aux = value < 0 ? 0 : value > 2 ? 2 : value;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "layer_overlap")) {
+        e->layer_overlap = std::min(std::max(value, 0), 2);
         return SB_OK;
     }
     if (!std::strcmp(key, "tail_split")) {

@@ -40,5 +40,8 @@ print("net %s batch %d precision %d dbg %d tail_split %d launch %d: %d clusters;
 for i, n in enumerate(names):
     col = st[:, i]
     print("  %-16s mean %10.0f  min %10.0f  max %10.0f" % (n, col.mean(), col.min(), col.max()))
+for n_it in sorted(set(st[:, 6].astype(int))):
+    sel = st[st[:, 6] == n_it]
+    print("  pairs with %d units: %3d   mma_total mean %8.0f   epi_total mean %8.0f" % (n_it, sel.shape[0], sel[:, 0].mean(), sel[:, 5].mean()))
 busy = st[:, 0] - st[:, 1] - st[:, 2] - st[:, 3]
 print("  mma issue+exec (total - waits) per item: mean %.0f cycles" % (busy / np.maximum(st[:, 6], 1)).mean())
