@@ -74,6 +74,7 @@ struct ConvParams {
     int* done_out;           // counters of THIS launch's output, nullptr = not signalled
     const int* done_in;      // counters of the launch that wrote the input tensor; nullptr = whole-grid dependency (griddepcontrol.wait)
     int done_in_full;        // value of a complete super tile in done_in
+    int rot;                 // items are dealt round-robin to the CTA pairs starting at pair (n_pairs - rot) % n_pairs: rotates from layer to layer of a chain
     int* err;                // device int, receives a site code if a barrier wait times out
     long long* stats;        // optional [grid][8] cycle counters (see sb_conv_stats), nullptr = off
 };
@@ -117,8 +118,7 @@ struct Conv2Cfg {
     static constexpr int kNumBStages = SPLIT ? SB_TC2_NB : 18;
     static constexpr int kOffB = kNumSlabs * kSlabBytes;
     static constexpr int kOffBar = kOffB + kNumBStages * kBStageBytes;
-    static constexpr int kOffBias = kOffBar + 512;
-    static constexpr int kSmemBytes = kOffBias + kMaxConvWidth * 4 + 1024;
+    static constexpr int kSmemBytes = kOffBar + 512 + 1024;   // + slack for the 1024-byte alignment of the base
     static constexpr int kTmemCols = 512;
     // Epilogue column parts per TMEM lane quadrant = epilogue warps per scheduler (see SB_TC2_EPI_PARTS_* above).
     static constexpr int kEpiParts = PARTS;
@@ -255,8 +255,8 @@ __device__ __forceinline__ int pool_first(int lane, int L) {   // first channel 
 // ---- Cross-layer dependencies ------------------------------------------------------------------------------------
 // A convolution launch whose input was written by the previous convolution launch does not wait for that whole grid
 // (griddepcontrol.wait): item st needs rows of the input's super tiles st-1, st, st+1 only (its slab reaches 24 rows into
-// the neighbours).  Every epilogue warp of the producing launch, after its last store of an item, adds its column count
-// to done[st] with a gpu-scope release; the slab producer of the consuming launch acquires done[st-1 .. st+1] before the
+// the neighbours).  When the epilogue warps of a CTA have stored their parts of an item, its publisher warp adds the CTA's
+// share to done[st] with a gpu-scope release; the slab producer of the consuming launch acquires done[st-1 .. st+1] before the
 // first TMA load of an item (plus a generic->async proxy fence), and every epilogue warp acquires done[st] before it
 // prefetches residual pieces (the residual tensor is the input of the producing launch: complete for these rows by
 // transitivity, the engine enables the mode only then).  With programmatic dependent launch the CTAs of layer l+1 become
@@ -287,6 +287,40 @@ __device__ __forceinline__ void wait_tile_done(const int* ctr, int full, int* er
     __trap();
 }
 
+// The three super tiles a slab of item st reads (st - 1 and st + 1 where they exist), polled together: one round trip.
+__device__ __forceinline__ void wait_tiles_done3(const int* done, int st, int n_super, int full, int* err, int site) {
+    const int* c0 = done + (st > 0 ? st - 1 : st);
+    const int* c1 = done + st;
+    const int* c2 = done + (st + 1 < n_super ? st + 1 : st);
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        const int v0 = ld_acquire_gpu(c0), v1 = ld_acquire_gpu(c1), v2 = ld_acquire_gpu(c2);
+        if (v0 >= full && v1 >= full && v2 >= full) return;
+        __nanosleep(64);
+    }
+    if (err) atomicExch(err, site);
+    __threadfence_system();
+    __trap();
+}
+
+__device__ __forceinline__ void st_release_cta_shared(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_deps_ctr(uint32_t addr, uint32_t want, int* err, int site) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        if (ld_acquire_cta_shared(addr) >= want) return;
+    }
+    if (err) atomicExch(err, site);
+    __threadfence_system();
+    __trap();
+}
+
 // Barrier wait of the MMA issuer: one try_wait on the fast path, the bounded spin behind it.
 __device__ __forceinline__ void mbar_wait_issuer(uint32_t bar, uint32_t parity, int* err, int site, bool stats, long long& t_acc) {
     if (!stats) {
@@ -299,26 +333,70 @@ __device__ __forceinline__ void mbar_wait_issuer(uint32_t bar, uint32_t parity, 
     }
 }
 
+// ---- Chains of convolutions in one launch --------------------------------------------------------------------------
+// The kernel runs a CHAIN of up to kMaxChain convolutions: every warp role loops over the layers, its ring positions,
+// barrier phases and TMEM stages carried from one layer into the next.  Layer l+1 depends on layer l tile by tile (the
+// completion counters above), so a CTA pair that has finished its items of layer l starts on layer l+1 at once, while its
+// own epilogue warps still work on layer l's last item and other pairs are still inside layer l: the launch ramp, the
+// drain of the last epilogue and the partial last wave of EVERY layer boundary inside a chain disappear (they cost ~25 %
+// of a 10bx128 tower launch at batch 256: 109 k cycles per launch against 5.4 items x 15.8 k).  Items are dealt
+// round-robin from a start that rotates by the layer's remainder (`rot`), so the pairs that took the extra item of one
+// layer are not the ones that take it in the next.  The engine chains launches that share the kernel instantiation, the
+// grid, the weight-ring geometry and the resident-weights mode; a launch that is not chained is a chain of one.
+// Co-residency: the grid never exceeds one CTA per SM, and forwards of one GPU are serialised (chain_forwards), so every
+// CTA a counter is waited on becomes resident without needing any of the waiters to finish.
+// Who releases the completion counters.  fp16 rung: a publisher warp per CTA (the epilogue warps are its critical path and
+// only arrive on a CTA-local barrier).  Split rung: every epilogue warp releases its own share, deferred until the
+// accumulators of its next item are drained — by then the stores it covers are long done and the release is cheap; the
+// epilogue has slack there, and the publisher form measured 4 % slower (profiles/r02_conv_chain.md).
+#ifndef SB_TC2_PUBLISHER_SPLIT
+#define SB_TC2_PUBLISHER_SPLIT 0
+#endif
+#ifndef SB_TC2_PUBLISHER_FP16
+#define SB_TC2_PUBLISHER_FP16 1
+#endif
+constexpr int kMaxChain = 8;
+struct ConvLayer {
+    CUtensorMap tmA_hi, tmA_lo;     // input activations (lo unused when !SPLIT)
+    CUtensorMap tmW_hi, tmW_lo;     // weights at N = bn
+    CUtensorMap tmWq_hi, tmWq_lo;   // weights at N = bn / 2 (half units of a tail wave)
+    ConvParams p;
+};
+struct ConvChain {
+    int n_layers;
+    ConvLayer layer[kMaxChain];
+};
+
 // Barrier addresses and ring geometry the MMA issuer needs (shared::cta addresses of the leader CTA).
 struct Conv2Issue {
     uint32_t tmem_base, slab_addr, bst_addr;
     uint32_t a_full, a_empty, tmem_full, tmem_empty, lo_full, lo_empty, b_full, b_empty;
     uint32_t kNB, stage_stride;
-    int chunk_kh, cluster_id, n_clusters, n_items;
+    int chunk_kh, first_item, n_clusters, n_items;
     bool resident;
 };
+// Ring positions and phases of the MMA issuer, carried across the layers of a chain.
+struct Conv2IssueState {
+    uint32_t j = 0;     // items issued so far (low-order accumulator stage = j & 1)
+    uint32_t cc = 0;    // main-accumulator chunks issued so far (stage = cc & 1)
+    uint32_t a_it = 0;  // slabs consumed so far
+    uint32_t as = 0, aph = 0;   // slab ring position and phase
+    uint32_t bs = 0, bph = 0;   // weight ring position and phase
+};
 
-// MMA issue for 3x3 convolutions: ONE elected thread runs the whole loop nest, the nine taps of a k-half are straight-line
-// code.  The general loop below (per tap: barrier wait, elect, re-derive both descriptors from loop counters, 4-8 MMAs,
-// commit) spends ~60 SASS instructions of a single warp — R2UR moves, uniform-datapath chains, reconvergence brackets —
-// on every 4 MMAs: measured 93 cycles per N = 128 MMA on the fp16 rung with RESIDENT weights and no barrier waits at all
+// MMA issue for 3x3 convolutions: the nine taps of a k-half are straight-line code, the loop state is warp-uniform.
+// The general loop below (per tap: barrier wait, elect, re-derive both descriptors from loop counters, 4-8 MMAs, commit)
+// spent ~60 SASS instructions of a single warp — R2UR moves, uniform-datapath chains, reconvergence brackets — on every
+// 4 MMAs: measured 93 cycles per N = 128 MMA on the fp16 rung with RESIDENT weights and no barrier waits at all
 // (tools/conv_stats.py, total - waits), against 64 cycles of tensor-pipe time: the issuing warp, not the tensor core, set
 // the pace, and every wait on its critical path (a successful try_wait costs ~11 cycles, 432 of them per split item) added
 // to it.  Here the tap shifts and stage addresses are formed once per k-half, the per-MMA work is one 64-bit add per
 // descriptor, and a wait that succeeds at once costs one instruction and one branch.  Same MMAs, same order, same
 // accumulators as the general loop: results are bit-identical (test_scheduling_knobs_do_not_change_a_single_bit).
+// Resident weights (fp16 rung): the stages of a layer are waited for on the layer's first item only and handed back to
+// the producer (for the next layer of a chain) behind the MMAs of its last item.
 template <bool SPLIT>
-__device__ __forceinline__ void conv2_issue_taps9(const ConvParams& p, const Conv2Issue& q, long long* stats_out) {
+__device__ __forceinline__ void conv2_issue_taps9(const ConvParams& p, const Conv2Issue& q, Conv2IssueState& S, long long* stats_out) {
     using Cfg = Conv2Cfg<SPLIT>;
     constexpr uint32_t kNA = Cfg::kNumSlabs;
     constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
@@ -330,28 +408,28 @@ __device__ __forceinline__ void conv2_issue_taps9(const ConvParams& p, const Con
     const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);
     long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0;
     const long long t_begin = stats ? clock64() : 0;
-    uint32_t j = 0, cc = 0, a_it = 0;
-    uint32_t as = 0, aph = 0;   // slab ring position and phase
-    uint32_t bs = 0, bph = 0;   // weight ring position and phase
-    for (int item = q.cluster_id; item < q.n_items; item += q.n_clusters, ++j) {
-        const uint32_t ls = j & 1u, lph = (j >> 1) & 1u;
+    uint32_t jl = 0;   // items of THIS layer issued so far
+    for (int item = q.first_item; item < q.n_items; item += q.n_clusters, ++S.j, ++jl) {
+        const uint32_t ls = S.j & 1u, lph = (S.j >> 1) & 1u;
         const uint32_t idesc = item < p.n_full ? idesc_whole : idesc_half;
         const uint32_t d_lo = q.tmem_base + (2u * ls + 1u) * BN;
+        const bool fill = !resident || jl == 0;                                   // the stages are (re)filled for this item
+        const bool hand_back = !resident || item + q.n_clusters >= q.n_items;     // ... and free again behind its MMAs
         if (SPLIT) {
             mbar_wait_issuer(q.lo_empty + 8 * ls, lph ^ 1u, p.err, 8, stats, t_wait_tmem);
         }
         uint32_t d_main = 0;
         int h_in_chunk = 0;
-        for (int h = 0; h < KH; ++h, ++a_it) {
+        for (int h = 0; h < KH; ++h, ++S.a_it) {
             if (h_in_chunk == 0) {
-                const uint32_t cs = cc & 1u, cph = (cc >> 1) & 1u;
+                const uint32_t cs = S.cc & 1u, cph = (S.cc >> 1) & 1u;
                 mbar_wait_issuer(q.tmem_empty + 8 * cs, cph ^ 1u, p.err, 3, stats, t_wait_tmem);
                 d_main = q.tmem_base + (SPLIT ? 2u * cs : cs) * BN;
             }
-            if (!(no_slab && a_it >= kNA)) mbar_wait_issuer(q.a_full + 8 * as, aph, p.err, 4, stats, t_wait_slab);
+            if (!(no_slab && S.a_it >= kNA)) mbar_wait_issuer(q.a_full + 8 * S.as, S.aph, p.err, 4, stats, t_wait_slab);
             tc_fence_after();
             // descriptor of the un-shifted tile; a tap shift of s rows is +s in the 16-byte start-address field
-            const uint64_t a_base = umma_desc_nosw(q.slab_addr + as * Cfg::kSlabBytes + (uint32_t)kSlabMargin * 16u, kSlabRows2 * 16u, 128u);
+            const uint64_t a_base = umma_desc_nosw(q.slab_addr + S.as * Cfg::kSlabBytes + (uint32_t)kSlabMargin * 16u, kSlabRows2 * 16u, 128u);
             const uint32_t first_main = h_in_chunk == 0 ? 0u : 1u;
             const uint32_t first_lo = h == 0 ? 0u : 1u;
 #pragma unroll
@@ -359,76 +437,192 @@ __device__ __forceinline__ void conv2_issue_taps9(const ConvParams& p, const Con
                 const int shift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
                 const uint64_t ad0 = a_base + (uint64_t)(int64_t)shift;
                 {   // weights hi x activations hi -> main ; x activations lo -> low-order accumulator
-                    if (wait_w && !(resident && j > 0)) mbar_wait_issuer(q.b_full + 8 * bs, bph, p.err, 5, stats, t_wait_b);
+                    if (wait_w && fill) mbar_wait_issuer(q.b_full + 8 * S.bs, S.bph, p.err, 5, stats, t_wait_b);
                     tc_fence_after();
-                    const uint64_t bd0 = umma_desc_sw128(q.bst_addr + bs * q.stage_stride);
+                    const uint64_t bd0 = umma_desc_sw128(q.bst_addr + S.bs * q.stage_stride);
                     if (elected) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             umma2_f16(d_main, ad0 + kAStep * k, bd0 + 2 * k, idesc, (tap == 0 && k == 0) ? first_main : 1u);
                             if (SPLIT) umma2_f16(d_lo, ad0 + kALo + kAStep * k, bd0 + 2 * k, idesc, (tap == 0 && k == 0) ? first_lo : 1u);
                         }
-                        if (!resident) umma2_commit_mc(q.b_empty + 8 * bs, 3);
+                        if (hand_back) umma2_commit_mc(q.b_empty + 8 * S.bs, 3);
                     }
                     __syncwarp();
-                    if (++bs == q.kNB) {
-                        bs = 0;
-                        if (!resident) bph ^= 1u;
+                    if (++S.bs == q.kNB) {
+                        S.bs = 0;
+                        if (!resident) S.bph ^= 1u;
                     }
                 }
                 if (SPLIT) {   // weights lo x activations hi -> low-order accumulator
-                    if (wait_w && !(resident && j > 0)) mbar_wait_issuer(q.b_full + 8 * bs, bph, p.err, 6, stats, t_wait_b);
+                    if (wait_w && fill) mbar_wait_issuer(q.b_full + 8 * S.bs, S.bph, p.err, 6, stats, t_wait_b);
                     tc_fence_after();
-                    const uint64_t bd0 = umma_desc_sw128(q.bst_addr + bs * q.stage_stride);
+                    const uint64_t bd0 = umma_desc_sw128(q.bst_addr + S.bs * q.stage_stride);
                     if (elected) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma2_f16(d_lo, ad0 + kAStep * k, bd0 + 2 * k, idesc, 1u);
-                        if (!resident) umma2_commit_mc(q.b_empty + 8 * bs, 3);
+                        if (hand_back) umma2_commit_mc(q.b_empty + 8 * S.bs, 3);
                     }
                     __syncwarp();
-                    if (++bs == q.kNB) {
-                        bs = 0;
-                        if (!resident) bph ^= 1u;
+                    if (++S.bs == q.kNB) {
+                        S.bs = 0;
+                        if (!resident) S.bph ^= 1u;
                     }
                 }
             }
             const bool last_h = h == KH - 1;
             const bool chunk_done = ++h_in_chunk == q.chunk_kh || last_h;
             if (elected) {
-                umma2_commit_mc(q.a_empty + 8 * as, 3);
+                umma2_commit_mc(q.a_empty + 8 * S.as, 3);
                 if (chunk_done) {   // hand the chunk's accumulator stage (and, behind the last one, the low-order sums) to the epilogue
                     if (SPLIT && last_h) umma2_commit_mc(q.lo_full + 8 * ls, 3);
-                    umma2_commit_mc(q.tmem_full + 8 * (cc & 1u), 3);
+                    umma2_commit_mc(q.tmem_full + 8 * (S.cc & 1u), 3);
                 }
             }
             __syncwarp();
             if (chunk_done) {
                 h_in_chunk = 0;
-                ++cc;
+                ++S.cc;
             }
-            if (++as == kNA) {
-                as = 0;
-                aph ^= 1u;
+            if (++S.as == kNA) {
+                S.as = 0;
+                S.aph ^= 1u;
             }
         }
     }
+    if (resident) S.bph ^= 1u;   // every stage barrier of a resident layer completes exactly once
     if (stats && elected) {
         stats_out[0] = clock64() - t_begin;
         stats_out[1] = t_wait_tmem;
         stats_out[2] = t_wait_slab;
         stats_out[3] = t_wait_b;
-        stats_out[6] = j;
+        stats_out[6] = jl;
     }
+}
+
+// General MMA issue loop: any tap count (1 = 1x1 convolution), the ablation bits of ConvParams::dbg, per-wait counters.
+template <bool SPLIT>
+__device__ __forceinline__ void conv2_issue_general(const ConvParams& p, const Conv2Issue& q, Conv2IssueState& S, long long* stats_out) {
+    using Cfg = Conv2Cfg<SPLIT>;
+    constexpr uint32_t kNA = Cfg::kNumSlabs;
+    constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
+    const int KH = p.kh, BN = p.bn;
+    const bool stats = stats_out != nullptr, resident = q.resident;
+    const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);
+    long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0, t0 = 0;
+    const long long t_begin = stats ? clock64() : 0;
+    uint32_t jl = 0;
+    for (int item = q.first_item; item < q.n_items; item += q.n_clusters, ++S.j, ++jl) {
+        const uint32_t ls = S.j & 1u, lph = (S.j >> 1) & 1u;
+        const uint32_t idesc = item < p.n_full ? idesc_whole : idesc_half;
+        const uint32_t d_lo = q.tmem_base + (2u * ls + 1u) * BN;
+        const bool fill = !resident || jl == 0;
+        const bool hand_back = !resident || item + q.n_clusters >= q.n_items;
+        if (SPLIT) {
+            if (stats) t0 = clock64();
+            mbar_wait(q.lo_empty + 8 * ls, lph ^ 1u, p.err, 8);
+            if (stats) t_wait_tmem += clock64() - t0;
+        }
+        uint32_t d_main = 0;
+        int h_in_chunk = 0;      // k-halves issued into the current chunk
+        for (int h = 0; h < KH; ++h, ++S.a_it) {
+            if (h_in_chunk == 0) {   // a new chunk: its accumulator stage must have been drained
+                const uint32_t cs = S.cc & 1u, cph = (S.cc >> 1) & 1u;
+                if (stats) t0 = clock64();
+                mbar_wait(q.tmem_empty + 8 * cs, cph ^ 1u, p.err, 3);
+                if (stats) t_wait_tmem += clock64() - t0;
+                d_main = q.tmem_base + (SPLIT ? 2u * cs : cs) * BN;
+            }
+            if (stats) t0 = clock64();
+            if (!((p.dbg & 64) && S.a_it >= kNA)) mbar_wait(q.a_full + 8 * S.as, S.aph, p.err, 4);
+            if (stats) t_wait_slab += clock64() - t0;
+            tc_fence_after();
+            const uint32_t a_hi = q.slab_addr + S.as * Cfg::kSlabBytes;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int shift = (p.ntaps == 1 || (p.dbg & 8)) ? 0 : (tap / 3 - 1) * p.pitch + (tap % 3 - 1);   // 1 tap = 1x1 convolution
+                const uint32_t first_main = (h_in_chunk | tap) == 0 ? 0u : 1u;
+                const uint32_t first_lo = (h | tap) == 0 ? 0u : 1u;
+                const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
+                {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
+                    if (stats) t0 = clock64();
+                    if (!(p.dbg & 16) && fill) mbar_wait(q.b_full + 8 * S.bs, S.bph, p.err, 5);
+                    if (stats) t_wait_b += clock64() - t0;
+                    tc_fence_after();
+                    const uint64_t bd0 = umma_desc_sw128(q.bst_addr + S.bs * q.stage_stride);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma2_f16(d_main, ad0 + kAStep * k, bd0 + 2 * k, idesc, (k == 0) ? first_main : 1u);
+                            if (SPLIT)
+                                umma2_f16(d_lo, ad0 + (Cfg::kSlabPartBytes >> 4) + kAStep * k, bd0 + 2 * k, idesc,
+                                          (k == 0) ? first_lo : 1u);
+                        }
+                        if (hand_back) umma2_commit_mc(q.b_empty + 8 * S.bs, 3);
+                    }
+                    __syncwarp();
+                    if (++S.bs == q.kNB) {
+                        S.bs = 0;
+                        if (!resident) S.bph ^= 1u;
+                    }
+                }
+                if (SPLIT) {   // weights lo x activations hi -> lo accumulator
+                    if (stats) t0 = clock64();
+                    if (!(p.dbg & 16) && fill) mbar_wait(q.b_full + 8 * S.bs, S.bph, p.err, 6);
+                    if (stats) t_wait_b += clock64() - t0;
+                    tc_fence_after();
+                    const uint64_t bd0 = umma_desc_sw128(q.bst_addr + S.bs * q.stage_stride);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma2_f16(d_lo, ad0 + kAStep * k, bd0 + 2 * k, idesc, 1u);
+                        if (hand_back) umma2_commit_mc(q.b_empty + 8 * S.bs, 3);
+                    }
+                    __syncwarp();
+                    if (++S.bs == q.kNB) {
+                        S.bs = 0;
+                        if (!resident) S.bph ^= 1u;
+                    }
+                }
+            }
+            const bool last_h = h == KH - 1;
+            const bool chunk_done = ++h_in_chunk == q.chunk_kh || last_h;
+            if (elect_one()) {
+                umma2_commit_mc(q.a_empty + 8 * S.as, 3);
+                if (chunk_done) {   // hand the chunk's accumulator stage (and, behind the last one, the low-order sums) to the epilogue
+                    if (SPLIT && last_h) umma2_commit_mc(q.lo_full + 8 * ls, 3);
+                    umma2_commit_mc(q.tmem_full + 8 * (S.cc & 1u), 3);
+                }
+            }
+            __syncwarp();
+            if (chunk_done) {
+                h_in_chunk = 0;
+                ++S.cc;
+            }
+            if (++S.as == kNA) {
+                S.as = 0;
+                S.aph ^= 1u;
+            }
+        }
+    }
+    if (resident) S.bph ^= 1u;
+    if (stats && (threadIdx.x & 31) == 0) {
+        stats_out[0] = clock64() - t_begin;
+        stats_out[1] = t_wait_tmem;
+        stats_out[2] = t_wait_slab;
+        stats_out[3] = t_wait_b;
+        stats_out[6] = jl;
+    }
+}
+
+// first item of a cluster in a layer: round-robin from a start that rotates with the layer (ConvParams::rot)
+__device__ __forceinline__ int conv_first_item(int cluster_id, int n_clusters, const ConvParams& p) {
+    const int v = cluster_id + p.rot;
+    return v >= n_clusters ? v - n_clusters : v;
 }
 
 template <bool SPLIT, int ACT, bool POOL, int PARTS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<SPLIT, PARTS>::kThreads, 1)
-conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                   const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                   const __grid_constant__ CUtensorMap tmWq_hi, const __grid_constant__ CUtensorMap tmWq_lo,
-                   const ConvParams p) {
+conv3x3_tc2_kernel(const __grid_constant__ ConvChain chain) {
     using Cfg = Conv2Cfg<SPLIT, PARTS>;
-    const int KH = p.kh, BN = p.bn;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -440,28 +634,18 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t tmem_full = bar_addr + 64, tmem_empty = bar_addr + 80;         // [2] each: main accumulator stages (chunks)
     const uint32_t lo_full = bar_addr + 96, lo_empty = bar_addr + 112;            // [2] each: low-order accumulators (items)
     const uint32_t b_full = bar_addr + 128, b_empty = bar_addr + 288;             // [<= 18] each
+    const uint32_t stored = bar_addr + 456;                                       // [4]: the epilogue warps of THIS CTA have stored an item
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + Cfg::kOffBar + 448);
-    float* sbias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
+    const uint32_t deps_ctr = bar_addr + 488;   // items of this CTA whose input tiles the slab producer has seen complete
     constexpr uint32_t kNA = Cfg::kNumSlabs;
-    // resident weights: the ring is exactly one item's worth of stages, filled once, never recycled
-    const bool resident = p.resident != 0;
-    // a weight stage holds this CTA's N-half of one [BN][64] block: 8 KB slots for BN <= 128, 16 KB (two slots) for the
-    // N = 256 tiles of the fp16 rung, which therefore has half as many stages in the same ring
-    const uint32_t stage_stride = BN > 128 ? 2u * Cfg::kBStageBytes : (uint32_t)Cfg::kBStageBytes;
-    const uint32_t kNB = resident ? (uint32_t)(p.kh * p.ntaps * Cfg::kParts)
-                                  : (uint32_t)(Cfg::kNumBStages * Cfg::kBStageBytes) / stage_stride;
-    // main-accumulator chunks: the k-halves of an item are cut every chunk_kh k-halves (fp16 rung: one chunk per item)
-    const int chunk_kh = SPLIT ? p.chunk_kh : KH;
-    const int n_chunks = (KH + chunk_kh - 1) / chunk_kh;
+    constexpr bool kPublisher = SPLIT ? (SB_TC2_PUBLISHER_SPLIT != 0) : (SB_TC2_PUBLISHER_FP16 != 0);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role branches and their loop state stay in uniform registers
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int n_items = p.n_units;   // whole items + half units of the tail wave (conv_unit)
-
-    for (int i = threadIdx.x; i < p.cout && i < kMaxConvWidth; i += blockDim.x) sbias[i] = p.bias[i];
+    const int n_layers = chain.n_layers;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < (int)kNA; ++i) {
@@ -474,20 +658,23 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             mbar_init(lo_full + 8 * i, 1);
             mbar_init(lo_empty + 8 * i, 2 * 4 * Cfg::kEpiParts);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(stored + 8 * i, 4 * Cfg::kEpiParts);
         for (int i = 0; i < Cfg::kNumBStages; ++i) {
             mbar_init(b_full + 8 * i, 1);
             mbar_init(b_empty + 8 * i, 1);
         }
+        st_release_cta_shared(deps_ctr, 0u);
         fence_barrier_init();
-        tma_prefetch_desc(&tmA_hi);
-        tma_prefetch_desc(&tmW_hi);
+        const ConvLayer& L0 = chain.layer[0];
+        tma_prefetch_desc(&L0.tmA_hi);
+        tma_prefetch_desc(&L0.tmW_hi);
         if (SPLIT) {
-            tma_prefetch_desc(&tmA_lo);
-            tma_prefetch_desc(&tmW_lo);
+            tma_prefetch_desc(&L0.tmA_lo);
+            tma_prefetch_desc(&L0.tmW_lo);
         }
-        if (p.n_units > p.n_full) {
-            tma_prefetch_desc(&tmWq_hi);
-            if (SPLIT) tma_prefetch_desc(&tmWq_lo);
+        if (L0.p.n_units > L0.p.n_full) {
+            tma_prefetch_desc(&L0.tmWq_hi);
+            if (SPLIT) tma_prefetch_desc(&L0.tmWq_lo);
         }
     }
     if (warp == 2) {
@@ -499,211 +686,175 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     cluster_sync_all();     // barriers of both CTAs are initialised before any remote arrive / TMA credit
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
-    if (threadIdx.x == 0) pdl_launch_dependents();   // the next layer may start its prologue whenever SMs free up
+    if (threadIdx.x == 0) pdl_launch_dependents();   // the next launch may start its prologue whenever SMs free up
 
     if (warp == 3) {
         // ===================== activation-slab producer (own 128-row tile, +-24 rows) =====================
-        const bool tile_deps = p.done_in != nullptr;
-        if (!tile_deps) pdl_wait();   // the slabs are the previous layer's output
-        uint32_t it = 0;
-        for (int item = cluster_id; item < n_items; item += n_clusters) {
-            const int st = conv_unit(item, p).st;
-            const int row_lo = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 - kSlabMargin;
-            for (int h = 0; h < KH; ++h, ++it) {
-                const uint32_t s = it % kNA, ph = (it / kNA) & 1u;
-                if ((p.dbg & 64) && it >= kNA) continue;   // ablation: no slab traffic after the first fills
-                mbar_wait(a_empty + 8 * s, ph ^ 1u, p.err, 1);
-                if (elect_one()) {
-                    if (tile_deps && h == 0) {   // the producing launch has finished the super tiles this slab reads
-                        if (st > 0) wait_tile_done(p.done_in + st - 1, p.done_in_full, p.err, 10);
-                        wait_tile_done(p.done_in + st, p.done_in_full, p.err, 11);
-                        if (st + 1 < p.n_super) wait_tile_done(p.done_in + st + 1, p.done_in_full, p.err, 12);
-                        fence_proxy_async_global();
+        uint32_t it = 0, s = 0, ph = 0;   // slabs loaded so far, ring position and phase
+        uint32_t n_dep = 0;               // items started so far (all layers)
+        for (int l = 0; l < n_layers; ++l) {
+            const ConvLayer& L = chain.layer[l];
+            const ConvParams& p = L.p;
+            const int KH = p.kh;
+            const bool tile_deps = p.done_in != nullptr;
+            if (!tile_deps) pdl_wait();   // the slabs are the previous launch's output (only the first layer of a chain)
+            for (int item = conv_first_item(cluster_id, n_clusters, p); item < p.n_units; item += n_clusters) {
+                const int st = conv_unit(item, p).st;
+                const int row_lo = kGuardRows + st * kSuperRows + (int)rank * kTileRows2 - kSlabMargin;
+                for (int h = 0; h < KH; ++h, ++it) {
+                    if ((p.dbg & 64) && it >= kNA) continue;   // ablation: no slab traffic after the first fills
+                    if (tile_deps && h == 0) {   // the producing layer has finished the super tiles this slab reads
+                        if (lane == 0) {
+                            wait_tiles_done3(p.done_in, st, p.n_super, p.done_in_full, p.err, 10);
+                            st_release_cta_shared(deps_ctr, n_dep + 1u);   // ... which the epilogue warps of this CTA learn here
+                        }
+                        __syncwarp();
                     }
-                    const uint32_t full0 = mapa_u32(a_full + 8 * s, 0);
-                    if (leader) mbar_arrive_expect_tx(a_full + 8 * s, 2u * Cfg::kSlabBytes);
+                    if (h == 0) ++n_dep;
+                    mbar_wait(a_empty + 8 * s, ph ^ 1u, p.err, 1);
+                    if (elect_one()) {
+                        if (tile_deps) fence_proxy_async_global();   // rows written through the generic proxy, read by TMA
+                        const uint32_t full0 = mapa_u32(a_full + 8 * s, 0);
+                        if (leader) mbar_arrive_expect_tx(a_full + 8 * s, 2u * Cfg::kSlabBytes);
 #pragma unroll
-                    for (int part = 0; part < Cfg::kParts; ++part) {
-                        tma2_load_3d(slab_addr + s * Cfg::kSlabBytes + part * Cfg::kSlabPartBytes, part ? &tmA_lo : &tmA_hi, 0,
-                                     row_lo, h * 8, full0);
+                        for (int part = 0; part < Cfg::kParts; ++part) {
+                            tma2_load_3d(slab_addr + s * Cfg::kSlabBytes + part * Cfg::kSlabPartBytes, part ? &L.tmA_lo : &L.tmA_hi, 0,
+                                         row_lo, h * 8, full0);
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == kNA) {
+                        s = 0;
+                        ph ^= 1u;
                     }
                 }
-                __syncwarp();
             }
         }
     } else if (warp == 0) {
         // ===================== weight-stage producer (own N-half of every block) =====================
         uint32_t s = 0, ph = 0;   // ring position and phase, advanced incrementally (kNB is a run-time value)
-        for (int item = cluster_id; item < n_items && !(p.dbg & 16); item += n_clusters) {
-            if (resident && item != cluster_id) break;     // everything is already in shared memory
-            const ConvUnit w = conv_unit(item, p);
-            const int HB = w.bn >> 1;                      // weight rows staged by this CTA
-            const bool whole = w.bn == BN;
-            for (int h = 0; h < KH; ++h) {
-                for (int tap = 0; tap < p.ntaps; ++tap) {
+        for (int l = 0; l < n_layers; ++l) {
+            const ConvLayer& L = chain.layer[l];
+            const ConvParams& p = L.p;
+            const int KH = p.kh, BN = p.bn;
+            const bool resident = p.resident != 0;
+            const uint32_t stage_stride = BN > 128 ? 2u * Cfg::kBStageBytes : (uint32_t)Cfg::kBStageBytes;
+            const uint32_t kNB = resident ? (uint32_t)(p.kh * p.ntaps * Cfg::kParts)
+                                          : (uint32_t)(Cfg::kNumBStages * Cfg::kBStageBytes) / stage_stride;
+            const int first = conv_first_item(cluster_id, n_clusters, p);
+            for (int item = first; item < p.n_units && !(p.dbg & 16); item += n_clusters) {
+                if (resident && item != first) break;     // everything is already in shared memory
+                const ConvUnit w = conv_unit(item, p);
+                const int HB = w.bn >> 1;                      // weight rows staged by this CTA
+                const bool whole = w.bn == BN;
+                for (int h = 0; h < KH; ++h) {
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
 #pragma unroll
-                    for (int part = 0; part < Cfg::kParts; ++part) {
-                        mbar_wait(b_empty + 8 * s, ph ^ 1u, p.err, 2);
-                        if (elect_one()) {
-                            const uint32_t full0 = mapa_u32(b_full + 8 * s, 0);
-                            if (leader) mbar_arrive_expect_tx(b_full + 8 * s, 2u * (uint32_t)HB * 128u);
-                            tma2_load_2d(bst_addr + s * stage_stride,
-                                         whole ? (part ? &tmW_lo : &tmW_hi) : (part ? &tmWq_lo : &tmWq_hi),
-                                         tap * (KH * 64) + h * 64, w.n0 + (int)rank * HB, full0);
-                        }
-                        __syncwarp();
-                        if (++s == kNB) {
-                            s = 0;
-                            ph ^= 1u;
+                        for (int part = 0; part < Cfg::kParts; ++part) {
+                            mbar_wait(b_empty + 8 * s, ph ^ 1u, p.err, 2);
+                            if (elect_one()) {
+                                const uint32_t full0 = mapa_u32(b_full + 8 * s, 0);
+                                if (leader) mbar_arrive_expect_tx(b_full + 8 * s, 2u * (uint32_t)HB * 128u);
+                                tma2_load_2d(bst_addr + s * stage_stride,
+                                             whole ? (part ? &L.tmW_lo : &L.tmW_hi) : (part ? &L.tmWq_lo : &L.tmWq_hi),
+                                             tap * (KH * 64) + h * 64, w.n0 + (int)rank * HB, full0);
+                            }
+                            __syncwarp();
+                            if (++s == kNB) {
+                                s = 0;
+                                ph ^= 1u;
+                            }
                         }
                     }
                 }
             }
         }
+    } else if (warp == 2) {
+        // ===================== publisher: per-tile completion counters for the next layer / launch =====================
+        // The epilogue warps only arrive on a CTA-local barrier when their part of an item is stored; the gpu-scope
+        // release (MEMBAR.ALL.GPU: wait for the stores to be visible at L2) is paid here, off the epilogue's path
+        // (as a release per epilogue warp it cost the fp16 rung 8 %).  Cumulativity makes the one release cover the
+        // stores of all arriving warps, as in a grid-wide barrier built on bar.sync + one fencing thread.
+        // Four barriers in rotation: an epilogue warp cannot run four items ahead of another one (they share two TMEM
+        // stages), so an arrival never lands in the phase of an item that is still being stored.
+        uint32_t jp = 0;   // published items so far
+        for (int l = 0; l < n_layers && kPublisher; ++l) {
+            const ConvParams& p = chain.layer[l].p;
+            if (p.done_out == nullptr) continue;
+            for (int item = conv_first_item(cluster_id, n_clusters, p); item < p.n_units; item += n_clusters, ++jp) {
+                const ConvUnit w = conv_unit(item, p);
+                mbar_wait(stored + 8 * (jp & 3u), (jp >> 2) & 1u, p.err, 14);
+                if (lane == 0) {
+                    fence_proxy_async_global();   // the consumer reads these rows with TMA (async proxy)
+                    red_release_gpu(p.done_out + w.st, 4 * w.bn);   // 4 lane quadrants x the unit's columns, from each CTA of the pair
+                }
+                __syncwarp();
+            }
+        }
     } else if (warp == 1) {
-        if (leader && p.ntaps == 9 && !(p.dbg & (8 | 128))) {
-            // ===================== MMA issuer (leader CTA only), 3x3 convolutions: one elected thread, taps unrolled =====================
-            {
+        if (leader) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            // TMEM columns per CTA, split rung: [main 0 | lo 0 | main 1 | lo 1] x BN (main stage = chunk counter & 1, low-order
+            // accumulator = item counter & 1); fp16 rung: main stage s at s * BN.
+            Conv2IssueState S;
+            for (int l = 0; l < n_layers; ++l) {
+                const ConvParams& p = chain.layer[l].p;
                 Conv2Issue q;
                 q.tmem_base = tmem_base; q.slab_addr = slab_addr; q.bst_addr = bst_addr;
                 q.a_full = a_full; q.a_empty = a_empty; q.tmem_full = tmem_full; q.tmem_empty = tmem_empty;
                 q.lo_full = lo_full; q.lo_empty = lo_empty; q.b_full = b_full; q.b_empty = b_empty;
-                q.kNB = kNB; q.stage_stride = stage_stride;
-                q.chunk_kh = chunk_kh; q.cluster_id = cluster_id; q.n_clusters = n_clusters; q.n_items = n_items;
-                q.resident = resident;
-                conv2_issue_taps9<SPLIT>(p, q, p.stats ? p.stats + (size_t)cluster_id * 8 : nullptr);
+                q.resident = p.resident != 0;
+                // a weight stage holds this CTA's N-half of one [BN][64] block: 8 KB slots for BN <= 128, 16 KB (two slots) for
+                // the N = 256 tiles of the fp16 rung, which therefore has half as many stages in the same ring; resident
+                // weights: the ring is exactly one item's worth of stages, filled once per layer
+                q.stage_stride = p.bn > 128 ? 2u * Cfg::kBStageBytes : (uint32_t)Cfg::kBStageBytes;
+                q.kNB = q.resident ? (uint32_t)(p.kh * p.ntaps * Cfg::kParts) : (uint32_t)(Cfg::kNumBStages * Cfg::kBStageBytes) / q.stage_stride;
+                // main-accumulator chunks: the k-halves of an item are cut every chunk_kh k-halves (fp16 rung: one chunk per item)
+                q.chunk_kh = SPLIT ? p.chunk_kh : p.kh;
+                q.first_item = conv_first_item(cluster_id, n_clusters, p);
+                q.n_clusters = n_clusters;
+                q.n_items = p.n_units;   // whole items + half units of the tail wave (conv_unit)
+                long long* stats_out = p.stats ? p.stats + (size_t)cluster_id * 8 : nullptr;
+                if (p.ntaps == 9 && !(p.dbg & (8 | 128))) conv2_issue_taps9<SPLIT>(p, q, S, stats_out);
+                else conv2_issue_general<SPLIT>(p, q, S, stats_out);
             }
             __syncwarp();
-        } else if (leader) {
-            // ===================== MMA issuer (leader CTA only), general form (1x1 convolutions) =====================
-            // TMEM columns per CTA, split rung: [main 0 | lo 0 | main 1 | lo 1] x BN (main stage = chunk counter & 1, low-order
-            // accumulator = item counter & 1); fp16 rung: main stage s at s * BN.
-            const uint32_t idesc_whole = umma_idesc_f16(256, BN), idesc_half = umma_idesc_f16(256, BN >> 1);
-            constexpr uint64_t kAStep = 2 * kSlabRows2 * 16 / 16;   // one K=16 step = two channel chunks
-            const bool stats = p.stats != nullptr;
-            uint32_t a_it = 0, j = 0, cc = 0;
-            uint32_t bs = 0, bph = 0;   // weight ring position and phase (incremental: kNB is a run-time value)
-            long long t_wait_tmem = 0, t_wait_slab = 0, t_wait_b = 0, t0 = 0;
-            const long long t_begin = stats ? clock64() : 0;
-            for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
-                const uint32_t ls = j & 1u, lph = (j >> 1) & 1u;
-                const uint32_t idesc = item < p.n_full ? idesc_whole : idesc_half;
-                const uint32_t d_lo = tmem_base + (2u * ls + 1u) * BN;
-                if (SPLIT) {
-                    if (stats) t0 = clock64();
-                    mbar_wait(lo_empty + 8 * ls, lph ^ 1u, p.err, 8);
-                    if (stats) t_wait_tmem += clock64() - t0;
-                }
-                uint32_t d_main = 0;
-                int h_in_chunk = 0;      // k-halves issued into the current chunk
-                for (int h = 0; h < KH; ++h, ++a_it) {
-                    if (h_in_chunk == 0) {   // a new chunk: its accumulator stage must have been drained
-                        const uint32_t cs = cc & 1u, cph = (cc >> 1) & 1u;
-                        if (stats) t0 = clock64();
-                        mbar_wait(tmem_empty + 8 * cs, cph ^ 1u, p.err, 3);
-                        if (stats) t_wait_tmem += clock64() - t0;
-                        d_main = tmem_base + (SPLIT ? 2u * cs : cs) * BN;
-                    }
-                    const uint32_t s = a_it % kNA, sph = (a_it / kNA) & 1u;
-                    if (stats) t0 = clock64();
-                    if (!((p.dbg & 64) && a_it >= kNA)) mbar_wait(a_full + 8 * s, sph, p.err, 4);
-                    if (stats) t_wait_slab += clock64() - t0;
-                    tc_fence_after();
-                    const uint32_t a_hi = slab_addr + s * Cfg::kSlabBytes;
-                    for (int tap = 0; tap < p.ntaps; ++tap) {
-                        const int shift = (p.ntaps == 1 || (p.dbg & 8)) ? 0 : (tap / 3 - 1) * p.pitch + (tap % 3 - 1);   // 1 tap = 1x1 convolution
-                        const uint32_t first_main = (h_in_chunk | tap) == 0 ? 0u : 1u;
-                        const uint32_t first_lo = (h | tap) == 0 ? 0u : 1u;
-                        const uint64_t ad0 = umma_desc_nosw(a_hi + (uint32_t)(kSlabMargin + shift) * 16u, kSlabRows2 * 16u, 128u);
-                        {   // weights hi x activations hi -> main ; x activations lo -> lo accumulator
-                            if (stats) t0 = clock64();
-                            if (!(p.dbg & 16) && !(resident && j > 0)) mbar_wait(b_full + 8 * bs, bph, p.err, 5);
-                            if (stats) t_wait_b += clock64() - t0;
-                            tc_fence_after();
-                            const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * stage_stride);
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    umma2_f16(d_main, ad0 + kAStep * k, bd0 + 2 * k, idesc, (k == 0) ? first_main : 1u);
-                                    if (SPLIT)
-                                        umma2_f16(d_lo, ad0 + (Cfg::kSlabPartBytes >> 4) + kAStep * k, bd0 + 2 * k, idesc,
-                                                  (k == 0) ? first_lo : 1u);
-                                }
-                                if (!resident) umma2_commit_mc(b_empty + 8 * bs, 3);   // resident stages are never recycled
-                            }
-                            __syncwarp();
-                            if (++bs == kNB) {
-                                bs = 0;
-                                if (!resident) bph ^= 1u;
-                            }
-                        }
-                        if (SPLIT) {   // weights lo x activations hi -> lo accumulator
-                            if (stats) t0 = clock64();
-                            if (!(p.dbg & 16) && !(resident && j > 0)) mbar_wait(b_full + 8 * bs, bph, p.err, 6);
-                            if (stats) t_wait_b += clock64() - t0;
-                            tc_fence_after();
-                            const uint64_t bd0 = umma_desc_sw128(bst_addr + bs * stage_stride);
-                            if (elect_one()) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) umma2_f16(d_lo, ad0 + kAStep * k, bd0 + 2 * k, idesc, 1u);
-                                if (!resident) umma2_commit_mc(b_empty + 8 * bs, 3);   // resident stages are never recycled
-                            }
-                            __syncwarp();
-                            if (++bs == kNB) {
-                                bs = 0;
-                                if (!resident) bph ^= 1u;
-                            }
-                        }
-                    }
-                    const bool last_h = h == KH - 1;
-                    const bool chunk_done = ++h_in_chunk == chunk_kh || last_h;
-                    if (elect_one()) {
-                        umma2_commit_mc(a_empty + 8 * s, 3);
-                        if (chunk_done) {   // hand the chunk's accumulator stage (and, behind the last one, the low-order sums) to the epilogue
-                            if (SPLIT && last_h) umma2_commit_mc(lo_full + 8 * ls, 3);
-                            umma2_commit_mc(tmem_full + 8 * (cc & 1u), 3);
-                        }
-                    }
-                    __syncwarp();
-                    if (chunk_done) {
-                        h_in_chunk = 0;
-                        ++cc;
-                    }
-                }
-            }
-            if (stats && lane == 0) {
-                long long* st = p.stats + (size_t)cluster_id * 8;
-                st[0] = clock64() - t_begin;
-                st[1] = t_wait_tmem;
-                st[2] = t_wait_slab;
-                st[3] = t_wait_b;
-                st[6] = j;
-            }
         }
     } else if (warp >= 4) {
         // ===================== epilogue: 4 * kEpiParts warps; warp%4 = TMEM lane quadrant, (warp-4)/4 = column part =====================
-        // kEpiParts warps per scheduler: each thread owns 1/kEpiParts of an accumulator row (<= 64 / 32 registers), so
-        // the dependent ALU/MUFU chains of one warp are hidden behind the other.
+        // kEpiParts warps per scheduler: each thread owns 1/kEpiParts of an accumulator row, so the dependent ALU/MUFU
+        // chains, tcgen05.ld waits and residual loads of one warp are hidden behind the others.
         const int q = warp & 3;
         const int part = (warp - 4) >> 2;                      // which column part of the accumulator row
-        const bool stats = p.stats != nullptr;
-        uint32_t j = 0, cc = 0;
-        long long t_wait_full = 0, t_drain = 0;
-        const long long t_begin = stats ? clock64() : 0;
+        uint32_t j = 0, cc = 0;                                // items / main chunks drained so far (all layers)
+        uint32_t jp = 0;                                       // items handed to the publisher warp so far
+        int* pend_ptr = nullptr;                               // !SB_TC2_PUBLISHER: completion counter of the previous item, not yet released
+        int pend_val = 0;
         const uint32_t empty0 = mapa_u32(tmem_empty, 0);   // leader's tmem_empty[0]; [1] is +8
         const uint32_t lo_empty0 = mapa_u32(lo_empty, 0);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int l = 0; l < n_layers; ++l) {
+        const ConvParams& p = chain.layer[l].p;
+        const int KH = p.kh, BN = p.bn;
+        const int chunk_kh = SPLIT ? p.chunk_kh : KH;
+        const int n_chunks = (KH + chunk_kh - 1) / chunk_kh;
+        const bool stats = p.stats != nullptr;
+        long long t_wait_full = 0, t_drain = 0;
+        const long long t_begin = stats ? clock64() : 0;
         const float chunk_scale = p.chunk_scale;
         const bool tile_deps = p.done_in != nullptr;
-        if (!tile_deps) pdl_wait();   // residual reads, and our stores may overwrite a buffer the previous layer still reads
-        for (int item = cluster_id; item < n_items; item += n_clusters, ++j) {
+        if (!tile_deps) pdl_wait();   // residual reads, and our stores may overwrite a buffer the previous launch still reads
+        for (int item = conv_first_item(cluster_id, n_clusters, p); item < p.n_units; item += n_clusters, ++j) {
             const ConvUnit w = conv_unit(item, p);
             const int st = w.st;
             if (tile_deps && p.res_hi != nullptr) {
-                // the residual rows of this tile are final (see "Cross-layer dependencies"); the acquire also invalidates
-                // this SM's L1 (LDG.STRONG.GPU + CCTL.IVALL), so the plain loads below cannot hit a line cached before
-                // the rows were written (each 128-byte line of a tile is read by one warp only)
-                if (lane == 0) wait_tile_done(p.done_in + st, p.done_in_full, p.err, 13);
-                __syncwarp();
+                // The residual rows of this tile are final once this CTA's slab producer has seen the input tiles of the item
+                // complete (see "Cross-layer dependencies"): it says so through a counter in shared memory, normally long
+                // before we get here (it works one item ahead).  Its gpu-scope acquire also invalidated this SM's L1
+                // (LDG.STRONG.GPU + CCTL.IVALL) after the rows were published, so the plain loads below cannot hit a line
+                // cached before they were written (a polling acquire per epilogue warp and item did the same at the price of
+                // an L2 round trip in front of every residual prefetch and 16 L1 invalidations per item).
+                wait_deps_ctr(deps_ctr, j + 1u, p.err, 13);
             }
             // columns of this thread: w.bn split into kEpiParts runs rounded to the 16-column ld granule (may be 0);
             // a run longer than kPassCols columns (N = 256 tiles of the fp16 rung) is processed in passes
@@ -717,7 +868,6 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const bool live = p.mask[row] != 0;
             const bool has_res = live && p.res_hi != nullptr && !(p.dbg & 1);
             const size_t chunk_stride = (size_t)p.rows * 8;
-            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
             for (int pass = 0; pass < n_pass; ++pass) {
                 const int pbase = cbase + pass * Cfg::kPassCols;            // first column of this pass inside the N tile
@@ -816,6 +966,14 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     if (stats) t_drain += clock64() - t_d0;
                 }
 
+                if (!kPublisher && pend_ptr != nullptr) {   // the previous item's stores were issued an MMA phase ago: the release finds them done
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_proxy_async_global();
+                        red_release_gpu(pend_ptr, pend_val);
+                    }
+                    pend_ptr = nullptr;
+                }
 #pragma unroll
                 for (int g = 0; g < Cfg::kMaxGroups; ++g) {
                     if (g * 16 < PC) {
@@ -830,9 +988,20 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                 rl[(g + 1) & 1][1] = *reinterpret_cast<const uint4*>(p.res_lo + n1);
                             }
                         }
+                        // the 16 biases of this group: same address in every lane (one transaction each, L1 / constant path);
+                        // bias blocks are padded to the N tile by the host
                         float v[16];
+                        {
+                            const float4* bp = reinterpret_cast<const float4*>(p.bias + w.n0 + pbase + c0);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sbias[w.n0 + pbase + c0 + i];
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 b4 = __ldg(bp + i);
+                                v[4 * i + 0] = acc[c0 + 4 * i + 0] + b4.x;
+                                v[4 * i + 1] = acc[c0 + 4 * i + 1] + b4.y;
+                                v[4 * i + 2] = acc[c0 + 4 * i + 2] + b4.z;
+                                v[4 * i + 3] = acc[c0 + 4 * i + 3] + b4.w;
+                            }
+                        }
                         if (has_res) {
                             const __half* hh0 = reinterpret_cast<const __half*>(&rh[g & 1][0]);
                             const __half* hh1 = reinterpret_cast<const __half*>(&rh[g & 1][1]);
@@ -879,12 +1048,12 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                 ps[i] = v[i];                       // already 0 on dead rows
                                 pm[i] = live ? v[i] : -5000.f;
                             }
-                            const int L = p.pool_log2;
-                            if (L == 4) pool_reduce16<4>(ps, pm, lane);
-                            else if (L == 3) pool_reduce16<3>(ps, pm, lane);
+                            const int PL = p.pool_log2;
+                            if (PL == 4) pool_reduce16<4>(ps, pm, lane);
+                            else if (PL == 3) pool_reduce16<3>(ps, pm, lane);
                             else pool_reduce16<2>(ps, pm, lane);
-                            const int gi = (row - kGuardRows) >> L;
-                            const int cnt = 16 >> L, first = pool_first(lane, L);
+                            const int gi = (row - kGuardRows) >> PL;
+                            const int cnt = 16 >> PL, first = pool_first(lane, PL);
                             if (gi < p.pool_groups && ch0 + first < p.cout) {
                                 float* dst = p.pool_part + (size_t)gi * 2 * p.pool_c + ch0 + first;
 #pragma unroll
@@ -899,20 +1068,32 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     }
                 }
             }
-            if (p.done_out != nullptr && HC > 0) {   // this warp's part of the tile is stored: publish it to the next layer
-                __syncwarp();
-                if (lane == 0) {
-                    fence_proxy_async_global();   // the consumer reads these rows with TMA (async proxy)
-                    red_release_gpu(p.done_out + st, HC);
+            if (p.done_out != nullptr) {   // this warp's part of the tile is stored: tell the publisher warp
+                if (kPublisher) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(stored + 8 * (jp & 3u));
+                    ++jp;
+                } else if (HC > 0) {
+                    if (item + n_clusters >= p.n_units) {   // last item of the layer: nothing to hide the release behind
+                        __syncwarp();
+                        if (lane == 0) {
+                            fence_proxy_async_global();
+                            red_release_gpu(p.done_out + st, HC);
+                        }
+                    } else {
+                        pend_ptr = p.done_out + st;
+                        pend_val = HC;
+                    }
                 }
             }
         }
         if (stats && leader && warp == 4 && lane == 0) {
-            long long* st = p.stats + (size_t)cluster_id * 8;
-            st[4] = t_wait_full;
-            st[5] = clock64() - t_begin;
-            st[7] = t_drain;
+            long long* so = p.stats + (size_t)cluster_id * 8;
+            so[4] = t_wait_full;
+            so[5] = clock64() - t_begin;
+            so[7] = t_drain;
         }
+        }   // layers
     }
 
     tc_fence_before();

@@ -297,6 +297,13 @@ struct ActBuf {
     const ActBuf* done_src = nullptr;   // the input tensor of that launch
 };
 
+// A chain of convolution launches waiting to be issued as ONE kernel (conv3x3_tc2.cuh, "Chains of convolutions in one launch").
+struct PendingChain {
+    ConvChain chain{};
+    bool split = false, wide = false, pool = false;
+    int act = 0, grid2 = 0, resident = 0, ring_key = 0, last_rem = 0, bn = 0;
+};
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -330,6 +337,7 @@ struct Slot {
     int conv_counter = 0;      // conv launches of the forward being enqueued on this slot (option "stats_launch")
     int* d_done = nullptr;     // [kMaxDoneLaunches][done_stride] per-tile completion counters of the conv launches of a forward
     int done_stride = 0;
+    PendingChain* pending = nullptr;   // convolution launches collected into the next chained launch
     bool busy = false;
     std::vector<int> sizes, offsets;
 };
@@ -456,6 +464,9 @@ struct sb_engine {
     int pdl_aux = 1;     // ... and for the unpack / SE / head kernels between them: 0 off, 1 for batches <= 64 (measured:
                          // -2.0..-2.5 % per forward at batch 32, +-1 % noise at batch 256; profiles/r01s2_pdl_aux_ab.md), 2 always
     int tail_split = 1;  // split the items of a partial last wave into N-halves (conv3x3_tc2)
+    int conv_chain = 1;      // consecutive convolution launches of one kernel instantiation run as ONE launch, layer l+1
+                             // starting on its tiles while layer l is still being finished elsewhere (conv3x3_tc2.cuh)
+    long long chained_layers = 0;   // convolutions issued as part of a multi-layer launch (sb_launch_count counts launches)
     int layer_overlap = 1;   // convolution launches depend on their producer tile by tile instead of grid by grid
                              // (conv3x3_tc2.cuh, "Cross-layer dependencies"; needs use_pdl): 0 off, 1 split rung at batches
                              // <= 64, 2 always.  Measured (profiles/r02_layer_overlap.md): -2..-4 % per forward at batch
@@ -492,6 +503,12 @@ static std::string g_create_error;
 namespace sb {
 
 static bool Split(const sb_engine* e) { return e->precision != SB_PRECISION_FP16; }
+// Convolutions are chained into one launch when option conv_chain is on, programmatic dependent launch is on and forwards of a
+// GPU are serialised (the co-residency argument of the kernel needs that).
+static bool ChainMode(const sb_engine* e) {
+    return e->conv_chain && e->use_pdl && e->chain_forwards && e->precision != SB_PRECISION_SIMT_DEBUG;
+}
+
 static bool LayerOverlap(const sb_engine* e, int n) {
     if (!e->use_pdl || e->precision == SB_PRECISION_SIMT_DEBUG) return false;
     return e->layer_overlap == 2 || (e->layer_overlap == 1 && Split(e) && n <= 64);
@@ -529,6 +546,8 @@ static void FreeSlot(Slot& s) {
     cudaFree(s.d_stats);
     cudaFree(s.d_done);
     s.d_done = nullptr;
+    delete s.pending;
+    s.pending = nullptr;
     cudaFreeHost(s.h_err);
     s = Slot{};
 }
@@ -608,6 +627,7 @@ static void AllocSlotVec(sb_engine* e, Replica& r, std::vector<Slot>& slots, int
         SB_CUDA(cudaMalloc(&s.misc15, (size_t)e->max_batch * 15 * sizeof(float)));
         SB_CUDA(cudaMalloc(&s.d_stats, (size_t)r.sm_count * 8 * sizeof(long long)));
         SB_CUDA(cudaMemset(s.d_stats, 0, (size_t)r.sm_count * 8 * sizeof(long long)));
+        s.pending = new PendingChain();
         s.done_stride = e->geom.n_super(e->max_batch) + 1;
         SB_CUDA(cudaMalloc(&s.d_done, (size_t)kMaxDoneLaunches * s.done_stride * sizeof(int)));
         SB_CUDA(cudaMemset(s.d_done, 0, (size_t)kMaxDoneLaunches * s.done_stride * sizeof(int)));
@@ -909,6 +929,39 @@ struct ConvTimer {
     }
 };
 
+static void FlushChain(sb_engine* e, Slot& s) {
+    PendingChain& pc = *s.pending;
+    if (pc.chain.n_layers == 0) return;
+    // launched with the programmatic-stream-serialization attribute: see pdl_wait() in conv3x3_tc2.cuh
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pc.grid2);
+    cfg.blockDim = dim3(pc.split ? Conv2Cfg<true, kPartsSplit>::kThreads
+                                 : pc.wide ? Conv2Cfg<false, kPartsFp16Wide>::kThreads : Conv2Cfg<false, kPartsFp16>::kThreads);
+    cfg.stream = s.stream;
+    cfg.dynamicSmemBytes = pc.split ? Conv2Cfg<true>::kSmemBytes : Conv2Cfg<false>::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const ConvChain& ch = pc.chain;
+    if (pc.pool) {   // the last convolution of an SE block: identity activation, pooling partials from the epilogue
+        if (pc.split) SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, kIdentity, true, kPartsSplit>, ch));
+        else if (pc.wide) SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, kIdentity, true, kPartsFp16Wide>, ch));
+        else SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, kIdentity, true, kPartsFp16>, ch));
+    } else if (pc.split) {
+        SB_DISPATCH_ACT(pc.act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, ACT, false, kPartsSplit>, ch)));
+    } else if (pc.wide) {
+        SB_DISPATCH_ACT(pc.act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT, false, kPartsFp16Wide>, ch)));
+    } else {
+        SB_DISPATCH_ACT(pc.act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT, false, kPartsFp16>, ch)));
+    }
+    SB_CUDA(cudaGetLastError());
+    e->launches++;
+    if (pc.chain.n_layers > 1) e->chained_layers += pc.chain.n_layers;
+    pc.chain.n_layers = 0;
+}
+
 static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, const ActBuf& in, ActBuf& out,
                        const ActBuf* res, int act, int n, ConvTimer* tm, bool pool = false) {
     const int n_super = e->geom.n_super(n);
@@ -921,107 +974,103 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
                                                           c.L.cout, n_super * kSuperRows, e->geom.P, c.L.taps, act, out.hi,
                                                           out.lo, out.rows);
         out.done = nullptr;
-    } else {
-        ConvParams p;
-        p.out_hi = out.hi;
-        p.out_lo = out.lo;
-        p.res_hi = res ? res->hi : nullptr;
-        p.res_lo = res ? res->lo : nullptr;
-        p.bias = reinterpret_cast<const float*>(r.blob + c.L.bias);
-        p.mask = s.mask;
-        p.cout = c.L.cout;
-        p.rows = out.rows;
-        p.kh = c.L.kh;
-        p.n_super = n_super;
-        p.pitch = e->geom.P;
-        p.ntaps = c.L.taps;
-        p.dbg = e->conv_dbg;
-        // split rung: the main accumulator is drained and re-accumulated in fp32 RN after every k-half (conv3x3_tc2.cuh,
-        // "Precision"); a 1x1 convolution (<= 24 main MMAs) is one chunk
-        p.chunk_kh = (c.L.taps == 9 && e->chunk_accumulate) ? 1 : c.L.kh;
-        p.chunk_scale = 1.0f + 1e-9f * (float)e->acc_comp_ppb * (float)(4 * p.chunk_kh * c.L.taps);
-        p.pool_part = pool ? s.pool_part : nullptr;
-        p.pool_log2 = PoolLog2(e->geom);
-        p.pool_groups = (n * e->geom.SS) >> std::max(p.pool_log2, 1);
-        p.pool_c = e->net_shape.channels;
-        p.err = s.d_err;
-        p.stats = (e->collect_stats && (e->stats_launch < 0 || e->stats_launch == s.conv_counter)) ? s.d_stats : nullptr;
-        // layer overlap: this launch publishes per-tile completion counters; it depends on its producer tile by tile when
-        // the input is the output of a launch that published them and the residual (if any) is that launch's own input
-        const bool overlap = LayerOverlap(e, n) && s.conv_counter < kMaxDoneLaunches;
-        p.done_out = overlap ? s.d_done + (size_t)s.conv_counter * s.done_stride : nullptr;
-        const bool tile_deps = overlap && in.done != nullptr && (res == nullptr || res == in.done_src);
-        p.done_in = tile_deps ? in.done : nullptr;
-        p.done_in_full = in.done_full;
-        s.conv_counter++;
-        // Small batches: narrow the N tile (bn >> level) while all items still fit in one wave, so that a handful of
-        // positions is spread over up to 4x more CTA pairs (latency of the single-position / GTP case).
-        int level = 0;
-        const int max_pairs = r.sm_count / 2;
-        while (e->small_batch_split && level + 1 < c.levels && level < 2 &&
-               n_super * (c.L.coutp / (c.bn0 >> (level + 1))) <= max_pairs)
-            ++level;
-        p.bn = c.bn0 >> level;
-        p.n_ntiles = c.L.coutp / p.bn;
-        const int items2 = n_super * p.n_ntiles;
-        // fp16 rung, one N tile, <= 18 weight stages per item: weights stay resident in shared memory
-        p.resident = (e->resident_weights && !Split(e) && p.n_ntiles == 1 && c.L.kh * c.L.taps <= Conv2Cfg<false>::kNumBStages &&
-                      items2 > max_pairs) ? 1 : 0;
-        // persistent CTA pairs; the items of a partial last wave are split into N-halves when that makes the
-        // wave half as long (conv_unit in conv3x3_tc2.cuh)
-        const int pairs = std::min(items2, max_pairs);
-        const int grid2 = 2 * pairs;
-        const int rem = items2 % pairs;
-        int n_tail = 0;
-        if (e->tail_split && !p.resident && items2 > pairs && rem > 0 && 2 * rem <= pairs && level + 1 < c.levels) n_tail = rem;
-        p.n_full = items2 - n_tail;
-        p.n_units = items2 + n_tail;
-        out.done = p.done_out;
-        out.done_full = 8 * p.n_ntiles * p.bn;
-        out.done_src = &in;
-        const CUtensorMap& w_hi = c.tm2_hi[level];
-        const CUtensorMap& w_lo = c.tm2_lo[level];
-        const CUtensorMap& wq_hi = c.tm2_hi[level + 1];
-        const CUtensorMap& wq_lo = c.tm2_lo[level + 1];
-        // launched with the programmatic-stream-serialization attribute: see pdl_wait() in conv3x3_tc2.cuh
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid2);
-        const bool wide = !Split(e) && p.bn > 128;   // N = 256 tiles of the fp16 rung: tensor-bound, fewer epilogue warps
-        cfg.blockDim = dim3(Split(e) ? Conv2Cfg<true, kPartsSplit>::kThreads
-                                     : wide ? Conv2Cfg<false, kPartsFp16Wide>::kThreads : Conv2Cfg<false, kPartsFp16>::kThreads);
-        cfg.stream = s.stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        if (pool) {   // the last convolution of an SE block: identity activation, pooling partials from the epilogue
-            if (act != kIdentity) throw CudaError{"internal error: pooled convolution with an activation"};
-            if (Split(e)) {
-                cfg.dynamicSmemBytes = Conv2Cfg<true>::kSmemBytes;
-                SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, kIdentity, true, kPartsSplit>, in.tm3_hi, in.tm3_lo, w_hi, w_lo, wq_hi, wq_lo, p));
-            } else {
-                cfg.dynamicSmemBytes = Conv2Cfg<false>::kSmemBytes;
-                if (wide) SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, kIdentity, true, kPartsFp16Wide>, in.tm3_hi, in.tm3_hi, w_hi, w_hi, wq_hi, wq_hi, p));
-                else SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, kIdentity, true, kPartsFp16>, in.tm3_hi, in.tm3_hi, w_hi, w_hi, wq_hi, wq_hi, p));
-            }
-        } else if (Split(e)) {
-            cfg.dynamicSmemBytes = Conv2Cfg<true>::kSmemBytes;
-            SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<true, ACT, false, kPartsSplit>, in.tm3_hi, in.tm3_lo, w_hi,
-                                                                  w_lo, wq_hi, wq_lo, p)));
-        } else {
-            cfg.dynamicSmemBytes = Conv2Cfg<false>::kSmemBytes;
-            if (wide) {
-                SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT, false, kPartsFp16Wide>, in.tm3_hi, in.tm3_hi,
-                                                                      w_hi, w_hi, wq_hi, wq_hi, p)));
-            } else {
-                SB_DISPATCH_ACT(act, ACT, SB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<false, ACT, false, kPartsFp16>, in.tm3_hi, in.tm3_hi,
-                                                                      w_hi, w_hi, wq_hi, wq_hi, p)));
-            }
-        }
+        SB_CUDA(cudaGetLastError());
+        e->launches++;
+        return;
     }
-    SB_CUDA(cudaGetLastError());
-    e->launches++;
+    ConvLayer lay;
+    ConvParams& p = lay.p;
+    p.out_hi = out.hi;
+    p.out_lo = out.lo;
+    p.res_hi = res ? res->hi : nullptr;
+    p.res_lo = res ? res->lo : nullptr;
+    p.bias = reinterpret_cast<const float*>(r.blob + c.L.bias);
+    p.mask = s.mask;
+    p.cout = c.L.cout;
+    p.rows = out.rows;
+    p.kh = c.L.kh;
+    p.n_super = n_super;
+    p.pitch = e->geom.P;
+    p.ntaps = c.L.taps;
+    p.dbg = e->conv_dbg;
+    // split rung: the main accumulator is drained and re-accumulated in fp32 RN after every k-half (conv3x3_tc2.cuh,
+    // "Precision"); a 1x1 convolution (<= 24 main MMAs) is one chunk
+    p.chunk_kh = (c.L.taps == 9 && e->chunk_accumulate) ? 1 : c.L.kh;
+    p.chunk_scale = 1.0f + 1e-9f * (float)e->acc_comp_ppb * (float)(4 * p.chunk_kh * c.L.taps);
+    p.pool_part = pool ? s.pool_part : nullptr;
+    p.pool_log2 = PoolLog2(e->geom);
+    p.pool_groups = (n * e->geom.SS) >> std::max(p.pool_log2, 1);
+    p.pool_c = e->net_shape.channels;
+    p.err = s.d_err;
+    p.stats = (e->collect_stats && (e->stats_launch < 0 || e->stats_launch == s.conv_counter)) ? s.d_stats : nullptr;
+    // Small batches: narrow the N tile (bn >> level) while all items still fit in one wave, so that a handful of
+    // positions is spread over up to 4x more CTA pairs (latency of the single-position / GTP case).
+    int level = 0;
+    const int max_pairs = r.sm_count / 2;
+    while (e->small_batch_split && level + 1 < c.levels && level < 2 &&
+           n_super * (c.L.coutp / (c.bn0 >> (level + 1))) <= max_pairs)
+        ++level;
+    p.bn = c.bn0 >> level;
+    p.n_ntiles = c.L.coutp / p.bn;
+    const int items2 = n_super * p.n_ntiles;
+    // fp16 rung, one N tile, <= 18 weight stages per item: weights stay resident in shared memory
+    p.resident = (e->resident_weights && !Split(e) && p.n_ntiles == 1 && c.L.kh * c.L.taps <= Conv2Cfg<false>::kNumBStages &&
+                  items2 > max_pairs) ? 1 : 0;
+    const int pairs = std::min(items2, max_pairs);
+    const int grid2 = 2 * pairs;
+    const int rem = items2 % pairs;
+    const bool split = Split(e);
+    const bool wide = !split && p.bn > 128;   // N = 256 tiles of the fp16 rung: tensor-bound, fewer epilogue warps
+    // weight-ring geometry (must agree along a chain): stage size class, and for resident weights the stages per layer
+    const int ring_key = (p.bn > 128 ? 1 : 0) | (p.resident ? (c.L.kh * c.L.taps) << 1 : 0);
+
+    // Dependencies.  The launch publishes per-tile completion counters when something may consume them; it depends on its
+    // producer tile by tile when the input is the output of a launch that published them and the residual (if any) is that
+    // launch's own input (conv3x3_tc2.cuh, "Cross-layer dependencies").
+    const bool chain_mode = ChainMode(e) && !pool && p.stats == nullptr && items2 >= pairs;
+    const bool overlap = LayerOverlap(e, n);
+    const bool counters = (overlap || ChainMode(e)) && s.conv_counter < kMaxDoneLaunches;
+    const bool deps_ok = in.done != nullptr && (res == nullptr || res == in.done_src);
+    PendingChain& pc = *s.pending;
+    const bool append = chain_mode && pc.chain.n_layers > 0 && pc.chain.n_layers < kMaxChain && deps_ok && !pc.pool &&
+                        in.done == pc.chain.layer[pc.chain.n_layers - 1].p.done_out && pc.split == split && pc.wide == wide &&
+                        pc.act == act && pc.grid2 == grid2 && pc.resident == p.resident && pc.ring_key == ring_key && pc.bn == p.bn;
+    if (!append) FlushChain(e, s);
+    p.done_out = counters ? s.d_done + (size_t)s.conv_counter * s.done_stride : nullptr;
+    const bool tile_deps = deps_ok && (append || overlap);
+    p.done_in = tile_deps ? in.done : nullptr;
+    p.done_in_full = in.done_full;
+    s.conv_counter++;
+    // persistent CTA pairs; the items of a partial last wave are split into N-halves when that makes the wave half as long
+    // (conv_unit in conv3x3_tc2.cuh).  Inside a chain the next layer fills the partial wave instead: no split, and the pair
+    // that takes the first item rotates by the remainder from layer to layer.
+    int n_tail = 0;
+    if (e->tail_split && !chain_mode && !p.resident && items2 > pairs && rem > 0 && 2 * rem <= pairs && level + 1 < c.levels) n_tail = rem;
+    p.n_full = items2 - n_tail;
+    p.n_units = items2 + n_tail;
+    p.rot = append ? (pc.chain.layer[pc.chain.n_layers - 1].p.rot + pc.last_rem) % pairs : 0;
+    out.done = p.done_out;
+    out.done_full = 8 * p.n_ntiles * p.bn;
+    out.done_src = &in;
+    lay.tmA_hi = in.tm3_hi;
+    lay.tmA_lo = split ? in.tm3_lo : in.tm3_hi;
+    lay.tmW_hi = c.tm2_hi[level];
+    lay.tmW_lo = split ? c.tm2_lo[level] : c.tm2_hi[level];
+    lay.tmWq_hi = c.tm2_hi[level + 1];
+    lay.tmWq_lo = split ? c.tm2_lo[level + 1] : c.tm2_hi[level + 1];
+    if (!append) {
+        pc.split = split;
+        pc.wide = wide;
+        pc.pool = pool;
+        pc.act = act;
+        pc.grid2 = grid2;
+        pc.resident = p.resident;
+        pc.ring_key = ring_key;
+        pc.bn = p.bn;   // the TMEM accumulator stages are laid out in multiples of bn: one layout along a chain
+    }
+    pc.last_rem = rem;
+    pc.chain.layer[pc.chain.n_layers++] = lay;
+    if (!chain_mode) FlushChain(e, s);   // not chainable: a chain of one, launched now
 }
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait() in common.cuh).
@@ -1069,14 +1118,19 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
 
     s.conv_counter = 0;
     for (ActBuf* b : {&s.in, &s.x, &s.t, &s.u, &s.ia, &s.ib, &s.ic, &s.pv, &s.pq}) b->done = nullptr;
-    if (LayerOverlap(e, n)) {   // per-tile completion counters of this forward's convolution launches
+    s.pending->chain.n_layers = 0;
+    if (LayerOverlap(e, n) || ChainMode(e)) {   // per-tile completion counters of this forward's convolution launches
         size_t n_conv = 3;   // input, head entry, RepLK 1x1
         for (const auto& blk : r.bconv) n_conv += blk.size();
         SB_CUDA(cudaMemsetAsync(s.d_done, 0, std::min<size_t>(n_conv, kMaxDoneLaunches) * s.done_stride * sizeof(int), s.stream));
     }
     const int pool_log2 = PoolLog2(g);
     const bool pool_fused = e->fuse_se_pool && pool_log2 > 0 && e->precision != SB_PRECISION_SIMT_DEBUG;
-    auto mark = [&]() { if (tm) tm->Mark(s.stream); };   // brackets groups of non-convolution kernels (profiling pass)
+    // brackets groups of non-convolution kernels (profiling pass); pending convolutions are issued first
+    auto mark = [&]() {
+        FlushChain(e, s);
+        if (tm) tm->Mark(s.stream);
+    };
     mark();
     {   // input planes -> canvas
         const int threads = n_rows * 8;
@@ -2532,6 +2586,10 @@ int sb_set_option(sb_engine* e, const char* key, int value) {
     }
     if (!std::strcmp(key, "pdl_aux")) {
         e->pdl_aux = value < 0 ? 0 : value > 2 ? 2 : value;
+        return SB_OK;
+    }
+    if (!std::strcmp(key, "conv_chain")) {
+        e->conv_chain = value ? 1 : 0;
         return SB_OK;
     }
     if (!std::strcmp(key, "layer_overlap")) {

@@ -386,9 +386,10 @@ def test_tail_wave_split_is_bit_exact(eng):
 
 
 def test_scheduling_knobs_do_not_change_a_single_bit(eng):
-    """Resident weights (fp16 rung), programmatic dependent launch, tile-by-tile dependencies between consecutive convolution
-    launches (layer_overlap), the small-batch N-tile split, the tail-wave split, chained forwards and the form of the MMA issue
-    loop only change WHEN and WHERE the same MMAs run: outputs are bit-identical with every knob on and off."""
+    """Resident weights (fp16 rung), programmatic dependent launch, chains of convolutions in one launch (conv_chain), tile-by-tile
+    dependencies between consecutive convolution launches (layer_overlap), the small-batch N-tile split, the tail-wave split,
+    chained forwards and the form of the MMA issue loop only change WHEN and WHERE the same MMAs run: outputs are bit-identical
+    with every knob on and off."""
     from sayuri_b200 import synth
     path = os.path.join(tempfile.gettempdir(), "sb_test_4bx128.bin")
     synth.write_synth_net(path, (4, 128, 16, 16), seed=77)
@@ -399,7 +400,8 @@ def test_scheduling_knobs_do_not_change_a_single_bit(eng):
             try:
                 base = pipe.batch_forward(0, list(x), [19] * n, [0] * n)
                 assert np.isfinite(base["probabilities"]).all()
-                for knob in ("resident_weights", "pdl", "pdl_aux", "small_batch_split", "chain_forwards", "layer_overlap", "tail_split"):
+                for knob in ("resident_weights", "pdl", "pdl_aux", "small_batch_split", "chain_forwards", "layer_overlap", "tail_split",
+                             "conv_chain"):
                     # pdl_aux, layer_overlap: 0 off, 1 small batches only (the default), 2 always
                     for value in ((0, 2) if knob in ("pdl_aux", "layer_overlap") else (0,)):
                         pipe.set_option(knob, value)
