@@ -282,11 +282,12 @@ def run_ours(args, rank, local_rank, world):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": "conv3x3_tc2_kernel<%s, mish> (tcgen05 cta_group::2)" % ("split" if precision == engine.PRECISION_FP32_SPLIT else "fp16"),
-                "launches_per_step": conv_n, "kernel_ms_per_step": conv_ms,
+                "launches_per_step": conv_n, "launches_note": "convolutions per step; the engine chains consecutive ones into fewer kernel launches (option conv_chain), `traffic` and algorithmic_flops_per_launch_avg are per convolution",
+                "kernel_ms_per_step": conv_ms,
                 "kernel_share_of_step": conv_share,
                 "algorithmic_flops_per_launch_avg": conv_flops / max(conv_n, 1),
                 "peak_source": peaks["source"] + ", dense bf16/fp16 sustained; kernel timed inside the step",
-                "how": "achieved = algorithmic flops of the %d conv launches of a step / (kernel_share_of_step x ms_per_step); the share comes from extra L2-flushed forwards (median of 5) whose non-conv kernels are bracketed with CUDA events on the engine's stream, so the conv launches keep their dependent-launch overlap" % conv_n,
+                "how": "achieved = algorithmic flops of the %d convolutions of a step / (kernel_share_of_step x ms_per_step); the share comes from extra L2-flushed forwards (median of 5) whose non-conv kernels are bracketed with CUDA events on the engine's stream, so the conv launches keep their dependent-launch overlap" % conv_n,
                 "tensor_flops_issued_per_algorithmic": 3 * (400.0 / 361.0) if precision == engine.PRECISION_FP32_SPLIT else (400.0 / 361.0),
                 "note": "fp32-faithful rung issues 3 fp16 MMAs per algorithmic MAC (hi*hi + lo*hi + hi*lo) on a 400-row/361-cell canvas"}
 

@@ -36,8 +36,10 @@
 // SPLIT = false uses the hi parts only, one chunk per item (the reference's own --fp16 trade).
 //
 // Warp roles:  warp 0 : TMA producer for weight stages      warp 1 : tcgen05.mma issuer (leader CTA; converged, elected lane)
-//              warp 2 : TMEM allocator                       warp 3 : TMA producer for activation slabs
+//              warp 2 : TMEM allocator, then publisher of    warp 3 : TMA producer for activation slabs (acquires the
+//                       the per-tile completion counters              completion counters of its input tiles first)
 //              warps 4.. : epilogue (warp%4 = TMEM lane quadrant, (warp-4)/4 = column part of the accumulator row)
+// One launch runs a CHAIN of convolutions ("Chains of convolutions in one launch" below); a plain launch is a chain of one.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -49,7 +51,8 @@ struct ConvParams {
     __half* out_lo;          // unused when !SPLIT
     const __half* res_hi;    // optional residual (same layout as out), nullptr if none
     const __half* res_lo;
-    const float* bias;       // [cout]
+    const float* bias;       // [cout padded to the N tile]
+    int bias_off;            // first float of this layer's biases in the kernel's shared-memory staging area (all layers of a chain)
     const uint8_t* mask;     // [rows]: 1 = real board cell of its sample, 0 = halo / off-board / padding
     int cout;                // real output channels (bias length)
     int rows;                // R: rows per channel chunk of the C8 activation tensors (out/res)
@@ -102,6 +105,7 @@ struct ConvParams {
 #ifndef SB_TC2_NB
 #define SB_TC2_NB 12     // weight-stage ring depth (split rung, <= 18)
 #endif
+constexpr int kChainBiasFloats = 2048;                       // padded output channels of all layers of a chain, at most
 constexpr int kTileRows2 = 128;                              // rows per CTA per item
 constexpr int kSlabRows2 = kTileRows2 + 2 * kSlabMargin;     // 176
 
@@ -118,7 +122,8 @@ struct Conv2Cfg {
     static constexpr int kNumBStages = SPLIT ? SB_TC2_NB : 18;
     static constexpr int kOffB = kNumSlabs * kSlabBytes;
     static constexpr int kOffBar = kOffB + kNumBStages * kBStageBytes;
-    static constexpr int kSmemBytes = kOffBar + 512 + 1024;   // + slack for the 1024-byte alignment of the base
+    static constexpr int kOffBias = kOffBar + 512;            // biases of all layers of a chain, staged once per launch
+    static constexpr int kSmemBytes = kOffBias + kChainBiasFloats * 4 + 1024;   // + slack for the 1024-byte alignment of the base
     static constexpr int kTmemCols = 512;
     // Epilogue column parts per TMEM lane quadrant = epilogue warps per scheduler (see SB_TC2_EPI_PARTS_* above).
     static constexpr int kEpiParts = PARTS;
@@ -647,6 +652,12 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvChain chain) {
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int n_layers = chain.n_layers;
 
+    float* sbias = reinterpret_cast<float*>(smem_gen + Cfg::kOffBias);
+    for (int l = 0; l < n_layers; ++l) {   // weights are constants: staged before any dependency wait
+        const ConvParams& pl = chain.layer[l].p;
+        const int nb = pl.n_ntiles * pl.bn;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) sbias[pl.bias_off + i] = pl.bias[i];
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < (int)kNA; ++i) {
             mbar_init(a_full + 8 * i, 1);    // leader's own arrive.expect_tx (bytes of both CTAs)
@@ -842,6 +853,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvChain chain) {
         long long t_wait_full = 0, t_drain = 0;
         const long long t_begin = stats ? clock64() : 0;
         const float chunk_scale = p.chunk_scale;
+        const float* sb = sbias + p.bias_off;
         const bool tile_deps = p.done_in != nullptr;
         if (!tile_deps) pdl_wait();   // residual reads, and our stores may overwrite a buffer the previous launch still reads
         for (int item = conv_first_item(cluster_id, n_clusters, p); item < p.n_units; item += n_clusters, ++j) {
@@ -988,20 +1000,9 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvChain chain) {
                                 rl[(g + 1) & 1][1] = *reinterpret_cast<const uint4*>(p.res_lo + n1);
                             }
                         }
-                        // the 16 biases of this group: same address in every lane (one transaction each, L1 / constant path);
-                        // bias blocks are padded to the N tile by the host
                         float v[16];
-                        {
-                            const float4* bp = reinterpret_cast<const float4*>(p.bias + w.n0 + pbase + c0);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float4 b4 = __ldg(bp + i);
-                                v[4 * i + 0] = acc[c0 + 4 * i + 0] + b4.x;
-                                v[4 * i + 1] = acc[c0 + 4 * i + 1] + b4.y;
-                                v[4 * i + 2] = acc[c0 + 4 * i + 2] + b4.z;
-                                v[4 * i + 3] = acc[c0 + 4 * i + 3] + b4.w;
-                            }
-                        }
+                        for (int i = 0; i < 16; ++i) v[i] = acc[c0 + i] + sb[w.n0 + pbase + c0 + i];
                         if (has_res) {
                             const __half* hh0 = reinterpret_cast<const __half*>(&rh[g & 1][0]);
                             const __half* hh1 = reinterpret_cast<const __half*>(&rh[g & 1][1]);

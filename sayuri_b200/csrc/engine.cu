@@ -301,7 +301,7 @@ struct ActBuf {
 struct PendingChain {
     ConvChain chain{};
     bool split = false, wide = false, pool = false;
-    int act = 0, grid2 = 0, resident = 0, ring_key = 0, last_rem = 0, bn = 0;
+    int act = 0, grid2 = 0, resident = 0, ring_key = 0, last_rem = 0, bn = 0, bias_floats = 0;
 };
 
 struct Slot {
@@ -1034,8 +1034,11 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
     PendingChain& pc = *s.pending;
     const bool append = chain_mode && pc.chain.n_layers > 0 && pc.chain.n_layers < kMaxChain && deps_ok && !pc.pool &&
                         in.done == pc.chain.layer[pc.chain.n_layers - 1].p.done_out && pc.split == split && pc.wide == wide &&
-                        pc.act == act && pc.grid2 == grid2 && pc.resident == p.resident && pc.ring_key == ring_key && pc.bn == p.bn;
+                        pc.act == act && pc.grid2 == grid2 && pc.resident == p.resident && pc.ring_key == ring_key && pc.bn == p.bn &&
+                        pc.bias_floats + c.L.coutp <= kChainBiasFloats;
     if (!append) FlushChain(e, s);
+    if (c.L.coutp > kChainBiasFloats) throw CudaError{"internal error: convolution wider than the bias staging area"};
+    p.bias_off = append ? pc.bias_floats : 0;
     p.done_out = counters ? s.d_done + (size_t)s.conv_counter * s.done_stride : nullptr;
     const bool tile_deps = deps_ok && (append || overlap);
     p.done_in = tile_deps ? in.done : nullptr;
@@ -1069,6 +1072,7 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         pc.bn = p.bn;   // the TMEM accumulator stages are laid out in multiples of bn: one layout along a chain
     }
     pc.last_rem = rem;
+    pc.bias_floats = p.bias_off + c.L.coutp;
     pc.chain.layer[pc.chain.n_layers++] = lay;
     if (!chain_mode) FlushChain(e, s);   // not chainable: a chain of one, launched now
 }
@@ -1384,6 +1388,20 @@ static int CreateImpl(sb_engine** out, HostNet* net, const sb_net_desc* shape_on
         return Fail(nullptr, SB_ERR_CUDA, ce.msg);
     }
     *out = e.release();
+    // SAYURI_B200_OPTIONS="key=value,key=value": sb_set_option knobs for callers that cannot reach the C ABI (A/B runs through the
+    // unmodified reference front-end).  Unknown keys are reported on stderr and ignored.
+    if (const char* env = std::getenv("SAYURI_B200_OPTIONS")) {
+        std::string all(env);
+        size_t at = 0;
+        while (at < all.size()) {
+            const size_t end = std::min(all.find(',', at), all.size());
+            const std::string kv = all.substr(at, end - at);
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos && sb_set_option(*out, kv.substr(0, eq).c_str(), std::atoi(kv.c_str() + eq + 1)) != SB_OK)
+                std::fprintf(stderr, "sayuri_b200: SAYURI_B200_OPTIONS: %s ignored (%s)\n", kv.c_str(), sb_last_error(*out));
+            at = end + 1;
+        }
+    }
     return SB_OK;
 }
 
