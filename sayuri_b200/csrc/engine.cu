@@ -364,6 +364,7 @@ struct Replica {
     // evict each other's activations from L2).
     std::unique_ptr<std::mutex> chain_mutex{new std::mutex};
     cudaEvent_t chain_tail = nullptr;   // ev_done of the forward enqueued last on this replica
+    bool registered = false;            // counted in g_replicas_on_device (chained launches need the device to themselves)
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     int sm_count = 0;
@@ -466,7 +467,7 @@ struct sb_engine {
     int tail_split = 1;  // split the items of a partial last wave into N-halves (conv3x3_tc2)
     int conv_chain = 1;      // consecutive convolution launches of one kernel instantiation run as ONE launch, layer l+1
                              // starting on its tiles while layer l is still being finished elsewhere (conv3x3_tc2.cuh)
-    long long chained_layers = 0;   // convolutions issued as part of a multi-layer launch (sb_launch_count counts launches)
+    std::atomic<long long> chained_layers{0};   // convolutions issued as part of a multi-layer launch (sb_launch_count counts launches)
     int layer_overlap = 1;   // convolution launches depend on their producer tile by tile instead of grid by grid
                              // (conv3x3_tc2.cuh, "Cross-layer dependencies"; needs use_pdl): 0 off, 1 split rung at batches
                              // <= 64, 2 always.  Measured (profiles/r02_layer_overlap.md): -2..-4 % per forward at batch
@@ -503,10 +504,18 @@ static std::string g_create_error;
 namespace sb {
 
 static bool Split(const sb_engine* e) { return e->precision != SB_PRECISION_FP16; }
-// Convolutions are chained into one launch when option conv_chain is on, programmatic dependent launch is on and forwards of a
-// GPU are serialised (the co-residency argument of the kernel needs that).
-static bool ChainMode(const sb_engine* e) {
-    return e->conv_chain && e->use_pdl && e->chain_forwards && e->precision != SB_PRECISION_SIMT_DEBUG;
+// Replicas (of any engine of this process) per device.  A chained launch waits, inside the kernel, for tiles owned by
+// CTAs of the same grid: every CTA of the grid must become resident without any waiter having to finish.  That holds
+// when the forwards on a device are serialised — one replica, chain_forwards — and not when two replicas (two engines, or
+// one engine created with the same device twice) may each hold a part of the SMs with a part of their grid.
+constexpr int kMaxDevices = 64;
+static std::atomic<int> g_replicas_on_device[kMaxDevices];
+// Convolutions are chained into one launch when option conv_chain is on, programmatic dependent launch is on, forwards of
+// the replica are serialised and the replica has its device to itself (within this process: another PROCESS on the same
+// device time-slices the whole GPU unless MPS is used; under MPS set conv_chain = 0).
+static bool ChainMode(const sb_engine* e, const Replica& r) {
+    return e->conv_chain && e->use_pdl && e->chain_forwards && e->precision != SB_PRECISION_SIMT_DEBUG && r.device >= 0 &&
+           r.device < kMaxDevices && g_replicas_on_device[r.device].load(std::memory_order_relaxed) == 1;
 }
 
 static bool LayerOverlap(const sb_engine* e, int n) {
@@ -677,6 +686,10 @@ static void MakeSimtWeights(sb_engine* e, Replica& r, DevConv& c, const std::vec
 
 static void BuildReplica(sb_engine* e, Replica& r, const std::vector<uint8_t>* blob) {
     SB_CUDA(cudaSetDevice(r.device));
+    if (!r.registered && r.device >= 0 && r.device < kMaxDevices) {
+        g_replicas_on_device[r.device].fetch_add(1);
+        r.registered = true;
+    }
     cudaDeviceProp prop;
     SB_CUDA(cudaGetDeviceProperties(&prop, r.device));
     if (prop.major != 10) {
@@ -891,6 +904,8 @@ static void DistributeBlob(sb_engine* e, const std::vector<uint8_t>* host_blob) 
 }
 
 static void DestroyReplica(Replica& r) {
+    if (r.registered && r.device >= 0 && r.device < kMaxDevices) g_replicas_on_device[r.device].fetch_sub(1);
+    r.registered = false;
     if (r.device >= 0) cudaSetDevice(r.device);
     for (Slot& s : r.slots) FreeSlot(s);
     r.slots.clear();
@@ -1027,9 +1042,9 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
     // Dependencies.  The launch publishes per-tile completion counters when something may consume them; it depends on its
     // producer tile by tile when the input is the output of a launch that published them and the residual (if any) is that
     // launch's own input (conv3x3_tc2.cuh, "Cross-layer dependencies").
-    const bool chain_mode = ChainMode(e) && !pool && p.stats == nullptr && items2 >= pairs;
+    const bool chain_mode = ChainMode(e, r) && !pool && p.stats == nullptr && items2 >= pairs;
     const bool overlap = LayerOverlap(e, n);
-    const bool counters = (overlap || ChainMode(e)) && s.conv_counter < kMaxDoneLaunches;
+    const bool counters = (overlap || ChainMode(e, r)) && s.conv_counter < kMaxDoneLaunches;
     const bool deps_ok = in.done != nullptr && (res == nullptr || res == in.done_src);
     PendingChain& pc = *s.pending;
     const bool append = chain_mode && pc.chain.n_layers > 0 && pc.chain.n_layers < kMaxChain && deps_ok && !pc.pool &&
@@ -1123,7 +1138,7 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     s.conv_counter = 0;
     for (ActBuf* b : {&s.in, &s.x, &s.t, &s.u, &s.ia, &s.ib, &s.ic, &s.pv, &s.pq}) b->done = nullptr;
     s.pending->chain.n_layers = 0;
-    if (LayerOverlap(e, n) || ChainMode(e)) {   // per-tile completion counters of this forward's convolution launches
+    if (LayerOverlap(e, n) || ChainMode(e, r)) {   // per-tile completion counters of this forward's convolution launches
         size_t n_conv = 3;   // input, head entry, RepLK 1x1
         for (const auto& blk : r.bconv) n_conv += blk.size();
         SB_CUDA(cudaMemsetAsync(s.d_done, 0, std::min<size_t>(n_conv, kMaxDoneLaunches) * s.done_stride * sizeof(int), s.stream));

@@ -205,3 +205,43 @@ def test_symmetry_ensemble_matches_eight_oracle_forwards_post_processed_like_the
             assert abs(got["score_error"] - exp["se"]) < 2e-2      # 150 x a 1e-4-accurate quantity
     finally:
         pipe.destroy()
+
+
+def test_convolutions_are_chained_only_while_the_replica_has_its_device_to_itself(eng):
+    """Chained convolution launches wait inside the kernel for tiles of their own grid, which is only safe when every CTA of
+    the grid becomes resident without a waiter having to finish: one replica per device, forwards serialised.  A second
+    engine on the same device (or conv_chain = 0) switches the engine back to one launch per convolution — fewer layers per
+    launch, the same bits."""
+    from sayuri_b200 import synth
+    path = os.path.join(tempfile.gettempdir(), "sb_chain_guard.bin")
+    synth.write_synth_net(path, (4, 64, 16, 16), seed=12)
+    n = 96
+    x = list(synth.synth_positions(n, 19, seed=5).reshape(n, -1))
+
+    def launches_of_a_forward(pipe):
+        before = pipe.launch_count()
+        out = pipe.batch_forward(0, x, [19] * n, [0] * n)
+        return pipe.launch_count() - before, out
+
+    a = eng.B200ForwardPipe().initialize(path, 19, n, gpus=[0])
+    try:
+        launches_of_a_forward(a)
+        chained, ref = launches_of_a_forward(a)
+        a.set_option("conv_chain", 0)
+        plain, out = launches_of_a_forward(a)
+        a.set_option("conv_chain", 1)
+        assert chained < plain, (chained, plain)
+        for f in FIELDS:
+            assert np.array_equal(out[f], ref[f]), f
+        b = eng.B200ForwardPipe().initialize(path, 19, 8, gpus=[0])   # a second engine on the same device
+        try:
+            shared, out = launches_of_a_forward(a)
+            assert shared == plain, (shared, plain)
+            for f in FIELDS:
+                assert np.array_equal(out[f], ref[f]), f
+        finally:
+            b.destroy()
+        again, _ = launches_of_a_forward(a)
+        assert again == chained, (again, chained)
+    finally:
+        a.destroy()
