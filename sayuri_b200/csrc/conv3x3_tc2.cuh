@@ -260,11 +260,12 @@ __device__ __forceinline__ int pool_first(int lane, int L) {   // first channel 
 // ---- Cross-layer dependencies ------------------------------------------------------------------------------------
 // A convolution launch whose input was written by the previous convolution launch does not wait for that whole grid
 // (griddepcontrol.wait): item st needs rows of the input's super tiles st-1, st, st+1 only (its slab reaches 24 rows into
-// the neighbours).  When the epilogue warps of a CTA have stored their parts of an item, its publisher warp adds the CTA's
-// share to done[st] with a gpu-scope release; the slab producer of the consuming launch acquires done[st-1 .. st+1] before the
-// first TMA load of an item (plus a generic->async proxy fence), and every epilogue warp acquires done[st] before it
-// prefetches residual pieces (the residual tensor is the input of the producing launch: complete for these rows by
-// transitivity, the engine enables the mode only then).  With programmatic dependent launch the CTAs of layer l+1 become
+// the neighbours).  When the epilogue warps of a CTA have stored their parts of an item, the CTA's share is added to
+// done[st] with a gpu-scope release (by its publisher warp, or by the epilogue warps themselves: SB_TC2_PUBLISHER_* below);
+// the slab producer of the consuming launch acquires done[st-1 .. st+1] before the first TMA load of an item (plus a
+// generic->async proxy fence) and then tells the epilogue warps of its CTA, through a counter in shared memory, that the
+// residual pieces of the item may be prefetched (the residual tensor is the input of the producing launch: complete for
+// these rows by transitivity, the engine enables the mode only then).  With programmatic dependent launch the CTAs of layer l+1 become
 // resident as the CTA pairs of layer l run out of items and start on the tiles that are ready: the partial last wave
 // (400 items over 74 pairs = 5.4 waves) and the launch ramp of one layer are filled with the next layer's work.
 // No deadlock: a dependent grid starts only after EVERY CTA of the primary has started (each triggers at its top), so a
@@ -280,19 +281,9 @@ __device__ __forceinline__ void red_release_gpu(int* ptr, int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-// Bounded like mbar_wait: a protocol bug surfaces as a launch failure with a site code, never as a hung GPU.
-__device__ __forceinline__ void wait_tile_done(const int* ctr, int full, int* err, int site) {
-#pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
-        if (ld_acquire_gpu(ctr) >= full) return;
-        __nanosleep(64);
-    }
-    if (err) atomicExch(err, site);
-    __threadfence_system();
-    __trap();
-}
 
 // The three super tiles a slab of item st reads (st - 1 and st + 1 where they exist), polled together: one round trip.
+// Bounded like mbar_wait: a protocol bug surfaces as a launch failure with a site code, never as a hung GPU.
 __device__ __forceinline__ void wait_tiles_done3(const int* done, int st, int n_super, int full, int* err, int site) {
     const int* c0 = done + (st > 0 ? st - 1 : st);
     const int* c1 = done + st;
