@@ -338,6 +338,7 @@ struct Slot {
     int* d_done = nullptr;     // [kMaxDoneLaunches][done_stride] per-tile completion counters of the conv launches of a forward
     int done_stride = 0;
     PendingChain* pending = nullptr;   // convolution launches collected into the next chained launch
+    bool fwd_chain = false, fwd_overlap = false;   // ChainMode / LayerOverlap, decided ONCE for the forward being enqueued
     bool busy = false;
     std::vector<int> sizes, offsets;
 };
@@ -993,6 +994,7 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
         e->launches++;
         return;
     }
+    if (pool && act != kIdentity) throw CudaError{"internal error: pooled convolution with an activation"};
     ConvLayer lay;
     ConvParams& p = lay.p;
     p.out_hi = out.hi;
@@ -1042,9 +1044,9 @@ static void LaunchConv(sb_engine* e, Replica& r, Slot& s, const DevConv& c, cons
     // Dependencies.  The launch publishes per-tile completion counters when something may consume them; it depends on its
     // producer tile by tile when the input is the output of a launch that published them and the residual (if any) is that
     // launch's own input (conv3x3_tc2.cuh, "Cross-layer dependencies").
-    const bool chain_mode = ChainMode(e, r) && !pool && p.stats == nullptr && items2 >= pairs;
-    const bool overlap = LayerOverlap(e, n);
-    const bool counters = (overlap || ChainMode(e, r)) && s.conv_counter < kMaxDoneLaunches;
+    const bool chain_mode = s.fwd_chain && !pool && p.stats == nullptr && items2 >= pairs;
+    const bool overlap = s.fwd_overlap;
+    const bool counters = (overlap || s.fwd_chain) && s.conv_counter < kMaxDoneLaunches;
     const bool deps_ok = in.done != nullptr && (res == nullptr || res == in.done_src);
     PendingChain& pc = *s.pending;
     const bool append = chain_mode && pc.chain.n_layers > 0 && pc.chain.n_layers < kMaxChain && deps_ok && !pc.pool &&
@@ -1138,7 +1140,9 @@ static void EnqueueForward(sb_engine* e, Replica& r, Slot& s, int n, ConvTimer* 
     s.conv_counter = 0;
     for (ActBuf* b : {&s.in, &s.x, &s.t, &s.u, &s.ia, &s.ib, &s.ic, &s.pv, &s.pq}) b->done = nullptr;
     s.pending->chain.n_layers = 0;
-    if (LayerOverlap(e, n) || ChainMode(e, r)) {   // per-tile completion counters of this forward's convolution launches
+    s.fwd_chain = ChainMode(e, r);   // decided once: the counters zeroed below are the ones every launch of this forward uses
+    s.fwd_overlap = LayerOverlap(e, n);
+    if (s.fwd_overlap || s.fwd_chain) {   // per-tile completion counters of this forward's convolution launches
         size_t n_conv = 3;   // input, head entry, RepLK 1x1
         for (const auto& blk : r.bconv) n_conv += blk.size();
         SB_CUDA(cudaMemsetAsync(s.d_done, 0, std::min<size_t>(n_conv, kMaxDoneLaunches) * s.done_stride * sizeof(int), s.stream));
