@@ -16,7 +16,10 @@ def conv_kernels():
     if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump is not installed")
     if not os.path.exists(LIB):
-        pytest.fail("sayuri_b200/libsayuri_b200.so is not built: python -c 'import __graft_entry__ as g; g.build()'")
+        import sys
+        sys.path.insert(0, ROOT)
+        import __graft_entry__ as g
+        g.build()
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
     assert "sm_100a" in sass or "SM100" in sass.upper(), "the library holds no sm_100a code"
     funcs = re.split(r"\n\s*Function : ", sass)[1:]
