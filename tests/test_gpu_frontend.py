@@ -97,9 +97,13 @@ def _compare(weights, board, playouts, moves, seeds, our_extra=(), our_env=None,
             total += 1
             d = l1(x, y)
             if d == 0:
-                assert rm[i] == om[i], "seed %d search %d: identical visit vectors but different moves (%s vs %s)" % (s, i, rm[i], om[i])
                 same += 1
-                continue
+                if rm[i] == om[i]:
+                    continue
+                # identical visits, different move: the move was chosen on the children's values (two candidates on the
+                # edge of the criterion); the games part here
+                moves_parted.append((s, i, rm[i], om[i], 0, x.get(rm[i], 0), x.get(om[i], 0), y.get(rm[i], 0), y.get(om[i], 0)))
+                break
             flips.append((s, i, d))
             assert d <= max(2, playouts // 10), "seed %d search %d: visit vectors differ by L1 = %d: %r vs %r" % (s, i, d, x, y)
             if rm[i] != om[i]:
