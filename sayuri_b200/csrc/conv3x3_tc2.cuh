@@ -82,9 +82,9 @@ struct ConvParams {
     long long* stats;        // optional [grid][8] cycle counters (see sb_conv_stats), nullptr = off
 };
 
-// Split rung: 2 activation-slab buffers and a 12-stage weight ring measured best (profiles/r01s2_ring_depth.log: +2.4 % on
-// 10bx128, +3.5 % on 20bx256 over 3 slabs + 8 stages; 16 stages: +2 % / +3 %) — the weight stream is what the MMA
-// issuer waits for, a third slab buffer is not.  Overridable for experiments.
+// Split rung: 2 activation-slab buffers and a 12-stage weight ring measured best, in round 1 (profiles/r01s2_ring_depth.log)
+// and again after the MMA issue loop was rewritten (profiles/r02_epilogue_parts.log: 16 stages -4 %, 3 slabs + 6 stages
+// -8 % on 10bx128).  Overridable for experiments.
 // Epilogue warps per TMEM lane quadrant (= column parts of an accumulator row), a template parameter of the kernel.
 // Measured after the MMA issue loop stopped being the limiter (profiles/r02_epilogue_parts.log, 10bx128, batch 256): the
 // epilogue of 2 warps per scheduler is latency-bound (tcgen05.ld waits, ex2/rcp chains, residual loads) and takes as long
@@ -117,8 +117,9 @@ struct Conv2Cfg {
     static constexpr int kNumSlabs = SPLIT ? SB_TC2_NA : 3;
     static constexpr int kBStageBytes = 64 * 128;                    // this CTA's half: up to 64 rows x 64 fp16
     // fp16 rung: 18 stages x 8 KB hold ALL of this CTA's weights of a C <= 128 layer (9 taps x 2 k-halves): they are
-    // then loaded once per launch and stay resident (ConvParams::resident), instead of being re-streamed for every
-    // work item (147 KB per item per CTA, the L2 -> SM bound of this rung).  The split rung has no room for that.
+    // then loaded once per layer and stay resident (ConvParams::resident) instead of being re-streamed for every work
+    // item (147 KB per item per CTA), and the MMA issuer waits for no weight barrier after the first item of a layer.
+    // The split rung has no room for that (288 KB per CTA and layer) and, with the unrolled issuer, no need.
     static constexpr int kNumBStages = SPLIT ? SB_TC2_NB : 18;
     static constexpr int kOffB = kNumSlabs * kSlabBytes;
     static constexpr int kOffBar = kOffB + kNumBStages * kBStageBytes;
