@@ -137,9 +137,9 @@ def test_every_read_sees_exactly_its_producing_write(blocks, se_every):
                     continue
                 assert before(w, prod) or before(e, w), "%s tile %d reads %s of %s, but the write by %s tile %d is ordered with neither" % (
                     ops[e[0]].name, e[1], cell, ops[prod[0]].name, ops[w[0]].name, w[1])
-    # the rule is not vacuous: most convolutions depend on their producer tile by tile
+    # the rule is not vacuous: a third or more of the convolutions depend on their producer tile by tile (residual towers: all but the first of a group)
     n_conv = sum(isinstance(op, Conv) for op in ops)
-    assert len(tiled) >= n_conv // 2, ([ops[i].name for i in tiled], n_conv)
+    assert len(tiled) >= n_conv // 3, ([ops[i].name for i in tiled], n_conv)
 
 
 def test_a_too_narrow_wait_would_be_caught():
